@@ -1,0 +1,383 @@
+// C ABI of libcup1d_b200.so: context management and the batched drivers that chain the
+// stage kernels on the caller's stream.  See include/cup1d_b200.h for the contract.
+#include <new>
+
+#include "c1d_internal.h"
+
+static const char* k_no_ctx = "null context";
+static const int64_t CHUNK_MAX = 1 << 17;  // walkers evaluated per pass (workspace bound)
+
+extern "C" int c1d_abi_version(void) { return C1D_ABI_VERSION; }
+
+extern "C" const char* c1d_last_error(const c1d_ctx* ctx) { return ctx ? ctx->err : k_no_ctx; }
+
+extern "C" int64_t c1d_launch_count(const c1d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static size_t field_elem_size(int f) {
+  switch (f) {
+    case C1D_F_ZIDX: case C1D_F_ZOTYPE: case C1D_F_HULL_DIM: case C1D_F_ZOFF_F: case C1D_F_ZOFF_D:
+    case C1D_F_RB_START: case C1D_F_ZMASK:
+      return sizeof(int32_t);
+    default:
+      return sizeof(double);
+  }
+}
+
+// expected element count of a field, or -1 when the field is optional/unsized
+static int64_t field_count(const c1d_config& c, int f, int64_t icov_blocks_n, int64_t nn_w_n, int64_t nn_b_n) {
+  switch (f) {
+    case C1D_F_PMIN: case C1D_F_PSCALE: case C1D_F_PRIOR_X0: case C1D_F_PRIOR_W: return c.ndim;
+    case C1D_F_ZBASE: return (int64_t)C1D_NQ * c.nz;
+    case C1D_F_ZWGT: case C1D_F_ZIDX: return (int64_t)C1D_NQ * c.nz * c.ell_width;
+    case C1D_F_ZNULL: case C1D_F_ZOTYPE: return C1D_NQ;
+    case C1D_F_LINP: return 3 * c.nz;
+    case C1D_F_MZ: return c.nz;
+    case C1D_F_IGMFID: return 4 * c.nz;
+    case C1D_F_EMU_LO: case C1D_F_EMU_HI: return c.n_emu;
+    case C1D_F_HULL_ABC: return 3 * (int64_t)c.n_hull_facets;
+    case C1D_F_HULL_DIM: return 2 * (int64_t)c.n_hull_facets;
+    case C1D_F_ZOFF_F: case C1D_F_ZOFF_D: return c.nz + 1;
+    case C1D_F_TAB: return (int64_t)C1D_NCOL * c.nf;
+    case C1D_F_RB_START: return c.nd;
+    case C1D_F_RB_WGT: return (int64_t)c.nd * c.rebin_width;
+    case C1D_F_DATA: return c.nd;
+    case C1D_F_ICOV_BLOCKS: return icov_blocks_n;
+    case C1D_F_ICOV_FULL: return c.has_full ? (int64_t)c.nd * c.nd : 0;
+    case C1D_F_NN_W: return c.emu_kind == 0 ? nn_w_n : 0;
+    case C1D_F_NN_B: return c.emu_kind == 0 ? nn_b_n : 0;
+    case C1D_F_GP_X: return c.emu_kind == 1 ? (int64_t)c.gp_ntrain * c.n_emu : 0;
+    case C1D_F_GP_INVELL: return c.emu_kind == 1 ? c.n_emu : 0;
+    case C1D_F_GP_ALPHA: return c.emu_kind == 1 ? (int64_t)c.gp_ntrain * c.nc : 0;
+    case C1D_F_GP_YMEAN: case C1D_F_GP_YSTD: return c.emu_kind == 1 ? c.nc : 0;
+    case C1D_F_GP_NORM: return c.emu_kind == 1 ? c.gp_nnorm : 0;
+    case C1D_F_ZMASK: return c.nz;
+    default: return -1;
+  }
+}
+
+extern "C" int c1d_ctx_create(const c1d_config* cfg, c1d_ctx** out) {
+  if (!cfg || !out) return C1D_ERR_ARG;
+  *out = nullptr;
+  if (cfg->abi_version != C1D_ABI_VERSION) return C1D_ERR_ARG;
+  c1d_ctx* ctx = new (std::nothrow) c1d_ctx();
+  if (!ctx) return C1D_ERR_ALLOC;
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->cfg = *cfg;
+  *out = ctx;  // returned even on failure so that the caller can read the message
+  const c1d_config& c = ctx->cfg;
+  bool ok = c.nz > 0 && c.ndim > 0 && c.n_emu > 0 && c.n_emu <= C1D_MAX_EMU && c.nd > 0 && c.nf > 0 &&
+            c.ell_width >= 1 && c.rebin_width >= 1 && c.nc >= 1 && c.nc <= C1D_MAX_COEF &&
+            (c.emu_kind == 0 || c.emu_kind == 1);
+  if (ok && c.emu_kind == 0) {
+    ok = c.n_layers >= 1 && c.n_layers <= C1D_MAX_LAYERS && c.layer_dims[0] == c.n_emu &&
+         c.layer_dims[c.n_layers] == c.nc;
+    for (int l = 0; ok && l <= c.n_layers; ++l) ok = c.layer_dims[l] >= 1 && c.layer_dims[l] <= 256;
+  }
+  if (ok && c.emu_kind == 1) ok = c.gp_ntrain > 0 && c.gp_imf >= 0 && c.gp_imf < c.n_emu && c.gp_nnorm >= 0;
+  if (!ok) {
+    snprintf(ctx->err, sizeof(ctx->err), "inconsistent configuration (sizes / emulator layout; NN layers must be <= 256 wide)");
+    return C1D_ERR_ARG;
+  }
+  C1D_CUDA(ctx, cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  C1D_CUDA(ctx, cudaGetDeviceProperties(&prop, c.device));
+  ctx->num_sms = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    snprintf(ctx->err, sizeof(ctx->err), "device %s is sm_%d%d; this library is built for sm_100a only",
+             prop.name, prop.major, prop.minor);
+    return C1D_ERR_CUDA;
+  }
+  for (int i = 0; i < 9; ++i) C1D_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+  return C1D_OK;
+}
+
+extern "C" int c1d_ctx_upload(c1d_ctx* ctx, int field_id, const void* host_ptr, size_t bytes) {
+  if (!ctx) return C1D_ERR_ARG;
+  if (field_id < 0 || field_id >= C1D_F_COUNT || (!host_ptr && bytes)) {
+    snprintf(ctx->err, sizeof(ctx->err), "bad field id %d", field_id);
+    return C1D_ERR_ARG;
+  }
+  C1D_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  if (ctx->dev[field_id] && ctx->bytes[field_id] != bytes) {
+    C1D_CUDA(ctx, cudaFree(ctx->dev[field_id]));
+    ctx->dev[field_id] = nullptr;
+  }
+  if (bytes == 0) { ctx->bytes[field_id] = 0; return C1D_OK; }
+  if (!ctx->dev[field_id]) C1D_CUDA(ctx, cudaMalloc(&ctx->dev[field_id], bytes));
+  // re-uploads (new data vector, zmask) must not race with work in flight
+  C1D_CUDA(ctx, cudaDeviceSynchronize());
+  C1D_CUDA(ctx, cudaMemcpy(ctx->dev[field_id], host_ptr, bytes, cudaMemcpyHostToDevice));
+  ctx->bytes[field_id] = bytes;
+  if (ctx->finalized) return c1d_ctx_finalize(ctx);
+  return C1D_OK;
+}
+
+extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
+  if (!ctx) return C1D_ERR_ARG;
+  c1d_config& c = ctx->cfg;
+  C1D_CUDA(ctx, cudaSetDevice(c.device));
+  // z offsets are needed on the host to size the per-z blocks
+  int32_t zf[1024], zd[1024];
+  if (c.nz + 1 > 1024) { snprintf(ctx->err, sizeof(ctx->err), "too many z bins"); return C1D_ERR_ARG; }
+  if (!ctx->dev[C1D_F_ZOFF_F] || !ctx->dev[C1D_F_ZOFF_D] ||
+      ctx->bytes[C1D_F_ZOFF_F] != (size_t)(c.nz + 1) * 4 || ctx->bytes[C1D_F_ZOFF_D] != (size_t)(c.nz + 1) * 4) {
+    snprintf(ctx->err, sizeof(ctx->err), "z offsets not uploaded");
+    return C1D_ERR_STATE;
+  }
+  C1D_CUDA(ctx, cudaMemcpy(zf, ctx->dev[C1D_F_ZOFF_F], (c.nz + 1) * 4, cudaMemcpyDeviceToHost));
+  C1D_CUDA(ctx, cudaMemcpy(zd, ctx->dev[C1D_F_ZOFF_D], (c.nz + 1) * 4, cudaMemcpyDeviceToHost));
+  int64_t blocks_n = 0;
+  int nfz_max = 0, ndz_max = 0;
+  for (int z = 0; z < c.nz; ++z) {
+    int nfz = zf[z + 1] - zf[z], ndz = zd[z + 1] - zd[z];
+    if (nfz <= 0 || ndz <= 0) { snprintf(ctx->err, sizeof(ctx->err), "empty z bin %d", z); return C1D_ERR_ARG; }
+    blocks_n += (int64_t)ndz * ndz;
+    if (nfz > nfz_max) nfz_max = nfz;
+    if (ndz > ndz_max) ndz_max = ndz;
+  }
+  if (zf[0] != 0 || zd[0] != 0 || zf[c.nz] != c.nf || zd[c.nz] != c.nd) {
+    snprintf(ctx->err, sizeof(ctx->err), "z offsets do not cover the grids");
+    return C1D_ERR_ARG;
+  }
+  c.reserved_i[0] = nfz_max;
+  c.reserved_i[1] = ndz_max;
+  int64_t nn_w_n = 0, nn_b_n = 0;
+  if (c.emu_kind == 0)
+    for (int l = 0; l < c.n_layers; ++l) {
+      nn_w_n += (int64_t)c.layer_dims[l] * c.layer_dims[l + 1];
+      nn_b_n += c.layer_dims[l + 1];
+    }
+  for (int f = 0; f < C1D_F_COUNT; ++f) {
+    int64_t n = field_count(c, f, blocks_n, nn_w_n, nn_b_n);
+    if (f == C1D_F_ZMASK && !ctx->dev[f]) continue;  // optional until a zmask evaluation
+    if (n < 0) continue;
+    if ((size_t)n * field_elem_size(f) != ctx->bytes[f]) {
+      snprintf(ctx->err, sizeof(ctx->err), "field %d: expected %lld elements, have %zu bytes", f,
+               (long long)n, ctx->bytes[f]);
+      return C1D_ERR_STATE;
+    }
+  }
+  DevCtx& d = ctx->d;
+  d.nz = c.nz; d.ndim = c.ndim; d.n_emu = c.n_emu; d.nd = c.nd; d.nf = c.nf;
+  d.ell_width = c.ell_width; d.rebin_width = c.rebin_width; d.emu_kind = c.emu_kind; d.nc = c.nc;
+  d.n_layers = c.n_layers;
+  for (int l = 0; l <= C1D_MAX_LAYERS; ++l) d.layer_dims[l] = c.layer_dims[l];
+  d.gp_ntrain = c.gp_ntrain; d.gp_nnorm = c.gp_nnorm; d.gp_imf = c.gp_imf;
+  d.metal_model = c.metal_model; d.apply_resolution = c.apply_resolution; d.has_full = c.has_full;
+  d.has_gauss = c.has_gauss; d.n_hull_facets = c.n_hull_facets;
+  d.idx_As = c.idx_As; d.idx_ns = c.idx_ns; d.idx_nrun = c.idx_nrun;
+  for (int j = 0; j < C1D_MAX_EMU; ++j) d.emu_code[j] = c.emu_code[j];
+  d.As_fid = c.As_fid; d.ns_fid = c.ns_fid; d.nrun_fid = c.nrun_fid; d.L_emu = c.L_emu; d.L_star = c.L_star;
+  for (int i = 0; i < 6; ++i) d.blob_fid[i] = c.blob_fid[i];
+  for (int i = 0; i < 3; ++i) { d.star_lo[i] = c.star_lo[i]; d.star_hi[i] = c.star_hi[i]; }
+  d.min_log_like = c.min_log_like; d.hull_tol = c.hull_tol; d.nn_slope = c.nn_slope; d.gp_sigma2 = c.gp_sigma2;
+  d.rb3 = c.rb3; d.ra3_over_rb3 = c.ra3_over_rb3; d.c0_o1 = c.c0_o1; d.c0_o2 = c.c0_o2; d.c0_o3c = c.c0_o3c;
+#define DP(name, F) d.name = (const double*)ctx->dev[F]
+#define IP(name, F) d.name = (const int*)ctx->dev[F]
+  DP(pmin, C1D_F_PMIN); DP(pscale, C1D_F_PSCALE); DP(prior_x0, C1D_F_PRIOR_X0); DP(prior_w, C1D_F_PRIOR_W);
+  DP(zbase, C1D_F_ZBASE); DP(zwgt, C1D_F_ZWGT); DP(znull, C1D_F_ZNULL); IP(zidx, C1D_F_ZIDX); IP(zotype, C1D_F_ZOTYPE);
+  DP(linp, C1D_F_LINP); DP(mz, C1D_F_MZ); DP(igmfid, C1D_F_IGMFID); DP(emu_lo, C1D_F_EMU_LO); DP(emu_hi, C1D_F_EMU_HI);
+  DP(hull_abc, C1D_F_HULL_ABC); IP(hull_dim, C1D_F_HULL_DIM); IP(zoff_f, C1D_F_ZOFF_F); IP(zoff_d, C1D_F_ZOFF_D);
+  DP(tab, C1D_F_TAB); IP(rb_start, C1D_F_RB_START); DP(rb_wgt, C1D_F_RB_WGT); DP(data, C1D_F_DATA);
+  DP(icov_blocks, C1D_F_ICOV_BLOCKS); DP(icov_full, C1D_F_ICOV_FULL); DP(nn_w, C1D_F_NN_W); DP(nn_b, C1D_F_NN_B);
+  DP(gp_x, C1D_F_GP_X); DP(gp_invell, C1D_F_GP_INVELL); DP(gp_alpha, C1D_F_GP_ALPHA);
+  DP(gp_ymean, C1D_F_GP_YMEAN); DP(gp_ystd, C1D_F_GP_YSTD); DP(gp_norm, C1D_F_GP_NORM); IP(zmask, C1D_F_ZMASK);
+#undef DP
+#undef IP
+  ctx->finalized = 1;
+  if (c.emu_kind == 0) {
+    int rc = c1d_tc_prepare(ctx);  // builds the tensor-core weight images (no-op when unsupported)
+    if (rc != C1D_OK) return rc;
+  }
+  return C1D_OK;
+}
+
+static void ws_free(c1d_ctx* ctx) {
+  Workspace& w = ctx->ws;
+  cudaFree(w.status); cudaFree(w.lnprior); cudaFree(w.blobs); cudaFree(w.emu_in); cudaFree(w.amp);
+  cudaFree(w.dvec); cudaFree(w.chi2z); cudaFree(w.chi2f); cudaFree(w.lnp); cudaFree(w.xdev); cudaFree(w.out7);
+  memset(&w, 0, sizeof(w));
+}
+
+static int ws_reserve(c1d_ctx* ctx, int64_t W) {
+  Workspace& w = ctx->ws;
+  if (W <= w.cap) return C1D_OK;
+  const c1d_config& c = ctx->cfg;
+  C1D_CUDA(ctx, cudaDeviceSynchronize());
+  ws_free(ctx);
+  int64_t cap = W;
+  C1D_CUDA(ctx, cudaMalloc(&w.status, cap * sizeof(int)));
+  C1D_CUDA(ctx, cudaMalloc(&w.lnprior, cap * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.blobs, cap * 6 * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.emu_in, (size_t)cap * c.nz * C1D_MAX_EMU * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.amp, (size_t)cap * c.nz * C1D_NAMP * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.dvec, (size_t)cap * c.nd * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.chi2z, (size_t)cap * c.nz * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.chi2f, cap * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.lnp, cap * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.xdev, (size_t)cap * c.ndim * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.out7, (size_t)cap * 7 * sizeof(double)));
+  // rows of rejected walkers are never written by stage 1: keep them finite
+  C1D_CUDA(ctx, cudaMemset(w.emu_in, 0, (size_t)cap * c.nz * C1D_MAX_EMU * sizeof(double)));
+  C1D_CUDA(ctx, cudaMemset(w.amp, 0, (size_t)cap * c.nz * C1D_NAMP * sizeof(double)));
+  w.cap = cap;
+  return C1D_OK;
+}
+
+static int check_ready(c1d_ctx* ctx, uint32_t flags) {
+  if (!ctx) return C1D_ERR_ARG;
+  if (!ctx->finalized) {
+    snprintf(ctx->err, sizeof(ctx->err), "context not finalised");
+    return C1D_ERR_STATE;
+  }
+  if ((flags & C1D_FLAG_ZMASK) && !ctx->dev[C1D_F_ZMASK]) {
+    snprintf(ctx->err, sizeof(ctx->err), "C1D_FLAG_ZMASK without an uploaded C1D_F_ZMASK");
+    return C1D_ERR_STATE;
+  }
+  return C1D_OK;
+}
+
+#define TICK(i)                                                        \
+  do {                                                                 \
+    if (ctx->timing) C1D_CUDA(ctx, cudaEventRecord(ctx->ev[i], s));    \
+  } while (0)
+
+extern "C" int c1d_loglike_batch(c1d_ctx* ctx, const double* x_dev, int64_t W, double* lnp_dev,
+                                 double* lnl_z_dev, double* blobs_dev, double* chi2_dev,
+                                 uint32_t flags, void* cuda_stream) {
+  int rc = check_ready(ctx, flags);
+  if (rc) return rc;
+  if (W < 0 || (W > 0 && (!x_dev || !lnp_dev))) {
+    snprintf(ctx->err, sizeof(ctx->err), "bad arguments to c1d_loglike_batch");
+    return C1D_ERR_ARG;
+  }
+  if (W == 0) return C1D_OK;
+  const c1d_config& c = ctx->cfg;
+  C1D_CUDA(ctx, cudaSetDevice(c.device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  int64_t chunk = W < CHUNK_MAX ? W : CHUNK_MAX;
+  rc = ws_reserve(ctx, chunk);
+  if (rc) return rc;
+  const int use_full = c.has_full && !(flags & C1D_FLAG_ZMASK);
+  const int want_chi2z = !use_full || lnl_z_dev != nullptr;
+  if (ctx->timing) for (int i = 0; i < 8; ++i) ctx->last_ms[i] = 0.0;
+  for (int64_t w0 = 0; w0 < W; w0 += chunk) {
+    int64_t n = (W - w0 < chunk) ? (W - w0) : chunk;
+    double* blobs = blobs_dev ? blobs_dev + w0 * 6 : ctx->ws.blobs;
+    TICK(0);
+    if ((rc = c1d_launch_stage1(ctx, x_dev + w0 * c.ndim, n, blobs, flags, s))) return rc;
+    TICK(1);
+    if ((rc = c1d_launch_emulator(ctx, ctx->ws.emu_in, n * c.nz, ctx->ws.amp, C1D_NAMP, flags, s))) return rc;
+    TICK(2);
+    if ((rc = c1d_launch_stage3(ctx, n, nullptr, use_full, want_chi2z, s))) return rc;
+    TICK(3);
+    if (use_full && (rc = c1d_launch_chi2(ctx, n, s))) return rc;
+    TICK(4);
+    if ((rc = c1d_launch_finalize(ctx, n, lnp_dev + w0, lnl_z_dev ? lnl_z_dev + w0 * c.nz : nullptr, blobs,
+                                  chi2_dev ? chi2_dev + w0 : nullptr, flags, s)))
+      return rc;
+    TICK(5);
+    if (ctx->timing) {
+      C1D_CUDA(ctx, cudaEventSynchronize(ctx->ev[5]));
+      for (int i = 0; i < 5; ++i) {
+        float ms = 0.f;
+        C1D_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
+        ctx->last_ms[i] += ms;
+      }
+    }
+  }
+  return C1D_OK;
+}
+
+extern "C" int c1d_p1d_batch(c1d_ctx* ctx, const double* x_dev, int64_t W, double* p_dev,
+                             double* emu_dev, uint32_t flags, void* cuda_stream) {
+  int rc = check_ready(ctx, flags);
+  if (rc) return rc;
+  if (W < 0 || (W > 0 && (!x_dev || !p_dev))) {
+    snprintf(ctx->err, sizeof(ctx->err), "bad arguments to c1d_p1d_batch");
+    return C1D_ERR_ARG;
+  }
+  if (W == 0) return C1D_OK;
+  const c1d_config& c = ctx->cfg;
+  C1D_CUDA(ctx, cudaSetDevice(c.device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  int64_t chunk = W < CHUNK_MAX ? W : CHUNK_MAX;
+  rc = ws_reserve(ctx, chunk);
+  if (rc) return rc;
+  for (int64_t w0 = 0; w0 < W; w0 += chunk) {
+    int64_t n = (W - w0 < chunk) ? (W - w0) : chunk;
+    if ((rc = c1d_launch_stage1(ctx, x_dev + w0 * c.ndim, n, ctx->ws.blobs, flags, s))) return rc;
+    if ((rc = c1d_launch_emulator(ctx, ctx->ws.emu_in, n * c.nz, ctx->ws.amp, C1D_NAMP, flags, s))) return rc;
+    if ((rc = c1d_launch_stage3(ctx, n, p_dev + w0 * c.nd, 0, 0, s))) return rc;
+    if (emu_dev) {
+      // workspace layout is [z][w][8]; hand back [w][z][n_emu]
+      for (int z = 0; z < c.nz; ++z)
+        C1D_CUDA(ctx, cudaMemcpy2DAsync(emu_dev + (w0 * c.nz + z) * c.n_emu, (size_t)c.nz * c.n_emu * sizeof(double),
+                                        ctx->ws.emu_in + (size_t)z * n * C1D_MAX_EMU, C1D_MAX_EMU * sizeof(double),
+                                        c.n_emu * sizeof(double), n, cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  return C1D_OK;
+}
+
+extern "C" int c1d_emulator_only(c1d_ctx* ctx, const double* emu_in_dev, int64_t nrows, double* coef_dev,
+                                 uint32_t flags, void* cuda_stream) {
+  int rc = check_ready(ctx, 0);
+  if (rc) return rc;
+  if (nrows < 0 || (nrows > 0 && (!emu_in_dev || !coef_dev))) return C1D_ERR_ARG;
+  C1D_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  return c1d_launch_emulator(ctx, emu_in_dev, nrows, coef_dev, C1D_MAX_COEF, flags, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int c1d_loglike_batch_host(c1d_ctx* ctx, const double* x_host, int64_t W, double* out_host,
+                                      uint32_t flags) {
+  int rc = check_ready(ctx, flags);
+  if (rc) return rc;
+  if (W < 0 || (W > 0 && (!x_host || !out_host))) return C1D_ERR_ARG;
+  if (W == 0) return C1D_OK;
+  const c1d_config& c = ctx->cfg;
+  C1D_CUDA(ctx, cudaSetDevice(c.device));
+  cudaStream_t s = 0;
+  int64_t chunk = W < CHUNK_MAX ? W : CHUNK_MAX;
+  rc = ws_reserve(ctx, chunk);
+  if (rc) return rc;
+  for (int64_t w0 = 0; w0 < W; w0 += chunk) {
+    int64_t n = (W - w0 < chunk) ? (W - w0) : chunk;
+    C1D_CUDA(ctx, cudaMemcpyAsync(ctx->ws.xdev, x_host + w0 * c.ndim, (size_t)n * c.ndim * sizeof(double),
+                                  cudaMemcpyHostToDevice, s));
+    rc = c1d_loglike_batch(ctx, ctx->ws.xdev, n, ctx->ws.lnp, nullptr, ctx->ws.blobs, nullptr, flags, s);
+    if (rc) return rc;
+    // out_host rows are (lnP, blob[6]): pack on the device, one contiguous copy back
+    if ((rc = c1d_launch_pack7(ctx, n, s))) return rc;
+    C1D_CUDA(ctx, cudaMemcpyAsync(out_host + w0 * 7, ctx->ws.out7, (size_t)n * 7 * sizeof(double),
+                                  cudaMemcpyDeviceToHost, s));
+    C1D_CUDA(ctx, cudaStreamSynchronize(s));
+  }
+  return C1D_OK;
+}
+
+extern "C" int c1d_set_timing(c1d_ctx* ctx, int enable) {
+  if (!ctx) return C1D_ERR_ARG;
+  ctx->timing = enable ? 1 : 0;
+  return C1D_OK;
+}
+
+extern "C" int c1d_get_timing(c1d_ctx* ctx, double* ms_out) {
+  if (!ctx || !ms_out) return C1D_ERR_ARG;
+  for (int i = 0; i < 8; ++i) ms_out[i] = ctx->last_ms[i];
+  return C1D_OK;
+}
+
+extern "C" int c1d_ctx_destroy(c1d_ctx* ctx) {
+  if (!ctx) return C1D_OK;
+  cudaSetDevice(ctx->cfg.device);
+  cudaDeviceSynchronize();
+  c1d_tc_destroy(ctx);
+  ws_free(ctx);
+  for (int f = 0; f < C1D_F_COUNT; ++f)
+    if (ctx->dev[f]) cudaFree(ctx->dev[f]);
+  for (int i = 0; i < 9; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  delete ctx;
+  return C1D_OK;
+}

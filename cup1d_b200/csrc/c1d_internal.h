@@ -1,0 +1,116 @@
+// Internal declarations shared by the translation units of libcup1d_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "cup1d_b200.h"
+
+// slots of the per-(walker, z) amplitude record handed from stage 1/2 to stage 3
+enum {
+  A_COEF0 = 0,   // .. A_COEF0 + C1D_MAX_COEF - 1 : emulator polynomial coefficients
+  A_S3 = 8,      // s_Lya_SiIII
+  A_S2 = 9,      // s_Lya_SiII
+  A_M0 = 10,     // 1 + C0                                  (si_mult.py:267-271)
+  A_C1 = 11,     // 2 a3            | SiVid: f3/(1-mF)
+  A_C2A = 12,    // 2 a2 r          | SiVid: f2/(1-mF)
+  A_C2B = 13,    // 2 a2
+  A_C3A = 14,    // 2 a3 a2 Gmm r
+  A_C3B = 15,    // 2 a3 a2 Gmm
+  A_H0 = 16,     // 1 + HCD_const
+  A_HCD1 = 17,   // .. A_HCD1 + 3
+  A_AA = 21,     // f_SiIIa_SiIIb^2
+  A_SA2 = 22,    // s_SiIIa_SiIIb^2
+  A_RES = 23     // R_coeff(z) (0 when the resolution term is not applied)
+};
+
+// walker status written by stage 1
+enum { ST_OK = 0, ST_OUT_OF_CUBE = 1, ST_REJECTED = 2 };
+
+struct DevCtx {
+  int nz, ndim, n_emu, nd, nf, ell_width, rebin_width, emu_kind, nc, n_layers;
+  int layer_dims[C1D_MAX_LAYERS + 1];
+  int gp_ntrain, gp_nnorm, gp_imf;
+  int metal_model, apply_resolution, has_full, has_gauss, n_hull_facets;
+  int idx_As, idx_ns, idx_nrun;
+  int emu_code[C1D_MAX_EMU];
+  double As_fid, ns_fid, nrun_fid, L_emu, L_star;
+  double blob_fid[6], star_lo[3], star_hi[3];
+  double min_log_like, hull_tol, nn_slope, gp_sigma2;
+  double rb3, ra3_over_rb3, c0_o1, c0_o2, c0_o3c;
+  const double *pmin, *pscale, *prior_x0, *prior_w;
+  const double *zbase, *zwgt, *znull;
+  const int *zidx, *zotype;
+  const double *linp, *mz, *igmfid, *emu_lo, *emu_hi;
+  const double* hull_abc;
+  const int* hull_dim;
+  const int *zoff_f, *zoff_d;
+  const double* tab;
+  const int* rb_start;
+  const double *rb_wgt, *data, *icov_blocks, *icov_full;
+  const double *nn_w, *nn_b;
+  const double *gp_x, *gp_invell, *gp_alpha, *gp_ymean, *gp_ystd, *gp_norm;
+  const int* zmask;
+};
+
+struct Workspace {
+  int64_t cap;     // walkers the buffers hold
+  int* status;     // [cap]
+  double* lnprior; // [cap]
+  double* blobs;   // [cap*6]
+  double* emu_in;  // [nz*cap*C1D_MAX_EMU]
+  double* amp;     // [nz*cap*C1D_NAMP]
+  double* dvec;    // [cap*nd]
+  double* chi2z;   // [cap*nz]
+  double* chi2f;   // [cap]
+  double* lnp;     // [cap]   (host-variant staging on the device)
+  double* xdev;    // [cap*ndim]
+  double* out7;    // [cap*7] packed (lnP, blob[6]) rows for the host variant
+};
+
+struct c1d_ctx {
+  c1d_config cfg;
+  void* dev[C1D_F_COUNT];
+  size_t bytes[C1D_F_COUNT];
+  DevCtx d;
+  Workspace ws;
+  int finalized;
+  int num_sms;
+  int64_t launches;
+  int timing;
+  cudaEvent_t ev[9];
+  double last_ms[8];
+  // tensor-core emulator path (c1d_mlp_tc.cu)
+  void* tc_state;
+  char err[512];
+};
+
+#define C1D_CUDA(ctx, call)                                                              \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+               cudaGetErrorString(e_));                                                  \
+      return C1D_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+// launchers (each returns a c1d_status and bumps ctx->launches)
+int c1d_launch_stage1(c1d_ctx* ctx, const double* x, int64_t W, double* blobs_out, uint32_t flags,
+                      cudaStream_t s);
+int c1d_launch_emulator(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out,
+                        int out_stride, uint32_t flags, cudaStream_t s);
+int c1d_launch_stage3(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int want_chi2z,
+                      cudaStream_t s);
+int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, cudaStream_t s);
+int c1d_launch_finalize(c1d_ctx* ctx, int64_t W, double* lnp, double* lnl_z, double* blobs,
+                        double* chi2, uint32_t flags, cudaStream_t s);
+
+int c1d_launch_pack7(c1d_ctx* ctx, int64_t W, cudaStream_t s);
+
+// tensor-core MLP (optional translation unit)
+int c1d_tc_prepare(c1d_ctx* ctx);
+int c1d_tc_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out, int out_stride,
+                  cudaStream_t s);
+void c1d_tc_destroy(c1d_ctx* ctx);

@@ -1,0 +1,711 @@
+// Hand-written sm_100a kernels of the batched P1D log-likelihood.
+//
+//   stage 0/1/5  k_stage1      cube -> parameters -> per-z emulator inputs, contaminant
+//                              amplitudes, blobs, Gaussian prior, star box, hull
+//   stage 2      k_mlp_f64     LaCE-style MLP on fp64 CUDA cores (exact-parity mode)
+//                k_gp_f64      GP posterior mean = batched kernel-vector product
+//   stage 3      k_fused_p1d   emulator polynomial -> contaminant templates -> rebin ->
+//                              residual, tables staged in shared memory per z
+//   stage 4      k_quadform    chi2 = d^T C^-1 d, register-tiled fp64 with the residual
+//                              tile in shared memory
+//   stage 5      k_finalize    regulate + prior, blobs conventions
+//
+// Reference lines are cited next to each formula.
+#include "c1d_internal.h"
+
+// ---------------------------------------------------------------------------------------
+// stage 1
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double param_value(const DevCtx& c, const double* xw, int i) {
+  // likelihood_parameter.py:58-61
+  return c.pmin[i] + xw[i] * c.pscale[i];
+}
+
+__global__ void __launch_bounds__(128)
+k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ status,
+         double* __restrict__ lnprior, double* __restrict__ blobs, double* __restrict__ emu_in,
+         double* __restrict__ amp, uint32_t flags) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  const double* xw = x + w * c.ndim;
+  double* bl = blobs + w * 6;
+
+  // compute_log_prob: out of the unit cube (likelihood.py:989-994)
+  bool out = false;
+  double lp = 0.0;
+  for (int i = 0; i < c.ndim; ++i) {
+    double xi = xw[i];
+    out |= (xi > 1.0) | (xi < 0.0);
+    if (c.has_gauss) {
+      double d = c.prior_x0[i] - xi;  // get_log_prior, likelihood.py:1060-1063
+      lp += d * d * c.prior_w[i];
+    }
+  }
+  if (out) {
+    status[w] = ST_OUT_OF_CUBE;
+    lnprior[w] = 0.0;
+    double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = 0; i < 6; ++i) bl[i] = qnan;  // Theory.get_blob(), lya_theory.py:514-523
+    return;
+  }
+  lnprior[w] = -lp;
+
+  // primordial-power rescaling (lya_theory.py:281-307, 542-580)
+  double ratio_As = 1.0, d_ns = 0.0, d_nrun = 0.0;
+  if (c.idx_As >= 0) ratio_As = param_value(c, xw, c.idx_As) / c.As_fid;
+  if (c.idx_ns >= 0) d_ns = param_value(c, xw, c.idx_ns) - c.ns_fid;
+  if (c.idx_nrun >= 0) d_nrun = param_value(c, xw, c.idx_nrun) - c.nrun_fid;
+  double ln_rA = log(ratio_As);
+  double e_emu = exp(ln_rA + (d_ns + 0.5 * d_nrun * c.L_emu) * c.L_emu);
+  double dn_emu = d_ns + d_nrun * c.L_emu;
+  double b0 = c.blob_fid[0] * exp(ln_rA + (d_ns + 0.5 * d_nrun * c.L_star) * c.L_star);
+  double b1 = c.blob_fid[1] + d_ns + d_nrun * c.L_star;
+  double b2 = c.blob_fid[2] + d_nrun;
+  bl[0] = b0; bl[1] = b1; bl[2] = b2;
+  bl[3] = c.blob_fid[3]; bl[4] = c.blob_fid[4]; bl[5] = c.blob_fid[5];
+
+  // star-prior box (lya_theory.py:647-654)
+  bool rej = (b0 > c.star_hi[0]) | (b0 < c.star_lo[0]) | (b1 > c.star_hi[1]) | (b1 < c.star_lo[1]) |
+             (b2 > c.star_hi[2]) | (b2 < c.star_lo[2]);
+
+  const bool use_hull = (c.n_hull_facets > 0) && !(flags & C1D_FLAG_NO_HULL);
+  const bool use_zmask = (flags & C1D_FLAG_ZMASK) != 0;
+
+  for (int z = 0; z < c.nz && !rej; ++z) {
+    double q[C1D_NQ];
+#pragma unroll 1
+    for (int iq = 0; iq < C1D_NQ; ++iq) {
+      int row = iq * c.nz + z;
+      double lin = c.zbase[row];
+      for (int e = 0; e < c.ell_width; ++e) {
+        int idx = c.zidx[row * c.ell_width + e];
+        if (idx >= 0) lin += c.zwgt[row * c.ell_width + e] * param_value(c, xw, idx);
+      }
+      // zero the '<= null' values (si_mult.py:170-176), then the output type
+      double v = c.zotype[iq] ? exp(lin) : lin;
+      q[iq] = (lin <= c.znull[iq]) ? 0.0 : v;
+    }
+    double M = c.mz[z];
+    // IGM histories (mean_flux_class.py:51-61, thermal_class.py:52-72, pressure_class.py:51-56)
+    double tau = q[C1D_Q_TAU] * c.igmfid[0 * c.nz + z];
+    double mF = exp(-tau);
+    double sigT_kms = q[C1D_Q_SIGT] * c.igmfid[1 * c.nz + z];
+    double gamma = q[C1D_Q_GAMMA] * c.igmfid[2 * c.nz + z];
+    double kF_kms = q[C1D_Q_KF] * c.igmfid[3 * c.nz + z];
+    double ev[C1D_MAX_EMU];
+    for (int j = 0; j < C1D_MAX_EMU; ++j) {
+      double v = 0.0;
+      if (j < c.n_emu) {
+        switch (c.emu_code[j]) {  // lya_theory.py:447-487
+          case 0: v = c.linp[z * 3 + 0] * e_emu; break;
+          case 1: v = c.linp[z * 3 + 1] + dn_emu; break;
+          case 2: v = c.linp[z * 3 + 2] + d_nrun; break;
+          case 3: v = mF; break;
+          case 4: v = sigT_kms / M; break;
+          case 5: v = gamma; break;
+          case 6: v = kF_kms * M; break;
+          default: v = 1000.0 / (kF_kms * M); break;
+        }
+      }
+      ev[j] = v;
+    }
+    if (use_hull && (!use_zmask || c.zmask[z])) {
+      // every facet of every 2-D hull: A p + b <= tol (hull.py:9-10, 157-165)
+      for (int f = 0; f < c.n_hull_facets; ++f) {
+        double p0 = ev[c.hull_dim[2 * f]], p1 = ev[c.hull_dim[2 * f + 1]];
+        double val = c.hull_abc[3 * f] * p0 + c.hull_abc[3 * f + 1] * p1 + c.hull_abc[3 * f + 2];
+        if (!(val <= c.hull_tol)) { rej = true; break; }
+      }
+      if (rej) break;
+    }
+    double* eo = emu_in + ((int64_t)z * W + w) * C1D_MAX_EMU;
+    for (int j = 0; j < C1D_MAX_EMU; ++j) eo[j] = ev[j];
+
+    double* a = amp + ((int64_t)z * W + w) * C1D_NAMP;
+    double om = 1.0 - mF;
+    a[A_S3] = q[C1D_Q_S_SIIII];
+    a[A_S2] = q[C1D_Q_S_SIII];
+    if (c.metal_model == 0) {
+      // SiMult amplitudes (si_mult.py:242-247, 267-314)
+      double a3 = q[C1D_Q_F_SIIII] / om;
+      double a2 = c.rb3 * q[C1D_Q_F_SIII] / om;
+      double r = c.ra3_over_rb3 * q[C1D_Q_F_SIIIA_SIIII];
+      double gmm = q[C1D_Q_F_SIIIB_SIIII];
+      a[A_M0] = 1.0 + (a3 * a3 * c.c0_o1 + a2 * a2 * (r * r * c.c0_o2 + c.c0_o3c));
+      a[A_C1] = 2.0 * a3;
+      a[A_C2A] = 2.0 * a2 * r;
+      a[A_C2B] = 2.0 * a2;
+      a[A_C3A] = 2.0 * a3 * a2 * gmm * r;
+      a[A_C3B] = 2.0 * a3 * a2 * gmm;
+    } else {
+      // SiVid (si_vid_final.py:205-217)
+      a[A_M0] = 1.0;
+      a[A_C1] = q[C1D_Q_F_SIIII] / om;
+      a[A_C2A] = q[C1D_Q_F_SIII] / om;
+      a[A_C2B] = 0.0; a[A_C3A] = 0.0; a[A_C3B] = 0.0;
+    }
+    a[A_H0] = 1.0 + q[C1D_Q_HCD_CONST];  // hcd_model_rogers_class.py:116
+    a[A_HCD1 + 0] = q[C1D_Q_HCD1];
+    a[A_HCD1 + 1] = q[C1D_Q_HCD2];
+    a[A_HCD1 + 2] = q[C1D_Q_HCD3];
+    a[A_HCD1 + 3] = q[C1D_Q_HCD4];
+    a[A_AA] = q[C1D_Q_F_SIADD] * q[C1D_Q_F_SIADD];  // si_add.py:219
+    a[A_SA2] = q[C1D_Q_S_SIADD] * q[C1D_Q_S_SIADD]; // si_add.py:168-170
+    a[A_RES] = c.apply_resolution ? q[C1D_Q_RES] : 0.0;  // lya_theory.py:712-722
+  }
+  status[w] = rej ? ST_REJECTED : ST_OK;
+}
+
+int c1d_launch_stage1(c1d_ctx* ctx, const double* x, int64_t W, double* blobs_out, uint32_t flags,
+                      cudaStream_t s) {
+  int threads = 128;
+  int64_t blocks = (W + threads - 1) / threads;
+  k_stage1<<<(unsigned)blocks, threads, 0, s>>>(ctx->d, x, W, ctx->ws.status, ctx->ws.lnprior,
+                                                 blobs_out, ctx->ws.emu_in, ctx->ws.amp, flags);
+  ctx->launches++;
+  C1D_CUDA(ctx, cudaPeekAtLastError());
+  return C1D_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// stage 2a: MLP on fp64 CUDA cores.  One CTA owns a tile of 64 rows ((walker, z) pairs) and
+// chains all layers with the activations resident in shared memory (k-major, 64 rows
+// contiguous).  Warp w owns rows 8w..8w+7, lane l owns CW consecutive output columns.
+// ---------------------------------------------------------------------------------------
+#define MLP_ROWS 64
+#define MLP_MAXW 256
+#define MLP_THREADS 256
+
+template <int CW>
+__device__ __forceinline__ void mlp_layer(const double* __restrict__ Wt, const double* __restrict__ b,
+                                          int K, int N, double* act, double slope, bool activate) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = lane * CW, r0 = warp * 8;
+  double acc[8][CW];
+#pragma unroll
+  for (int c = 0; c < CW; ++c) {
+    double bv = (n0 + c < N) ? b[n0 + c] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][c] = bv;
+  }
+  if (n0 < N) {
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+      double wv[CW];
+#pragma unroll
+      for (int c = 0; c < CW; ++c) wv[c] = (n0 + c < N) ? __ldg(Wt + (size_t)k * N + n0 + c) : 0.0;
+      const double2* ap = reinterpret_cast<const double2*>(act + k * MLP_ROWS + r0);
+      double a[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double2 t = ap[i];
+        a[2 * i] = t.x;
+        a[2 * i + 1] = t.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < CW; ++c) acc[i][c] = fma(a[i], wv[c], acc[i][c]);
+    }
+  }
+  __syncthreads();  // every read of the input activations is done
+#pragma unroll
+  for (int c = 0; c < CW; ++c) {
+    if (n0 + c < N) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double v = acc[i][c];
+        if (activate) v = (v > 0.0) ? v : slope * v;  // LeakyReLU(slope)
+        act[(n0 + c) * MLP_ROWS + r0 + i] = v;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(MLP_THREADS, 1)
+k_mlp_f64(DevCtx c, const double* __restrict__ emu_in, int64_t nrows, double* __restrict__ out,
+          int out_stride) {
+  extern __shared__ __align__(16) double act[];  // [MLP_MAXW][MLP_ROWS]
+  const int64_t ntiles = (nrows + MLP_ROWS - 1) / MLP_ROWS;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * MLP_ROWS;
+    // normalised inputs: (x - lo)/(hi - lo) - 0.5
+    for (int t = threadIdx.x; t < MLP_ROWS * c.n_emu; t += blockDim.x) {
+      int r = t / c.n_emu, j = t % c.n_emu;
+      int64_t row = row0 + r;
+      double v = 0.0;
+      if (row < nrows) {
+        double xv = emu_in[row * C1D_MAX_EMU + j];
+        v = (xv - c.emu_lo[j]) / (c.emu_hi[j] - c.emu_lo[j]) - 0.5;
+      }
+      act[j * MLP_ROWS + r] = v;
+    }
+    __syncthreads();
+    size_t woff = 0, boff = 0;
+    for (int l = 0; l < c.n_layers; ++l) {
+      const int K = c.layer_dims[l], N = c.layer_dims[l + 1];
+      const bool activate = l < c.n_layers - 1;
+      const double* Wt = c.nn_w + woff;
+      const double* b = c.nn_b + boff;
+      const int cw = (N + 31) / 32;
+      switch (cw) {
+        case 1: mlp_layer<1>(Wt, b, K, N, act, c.nn_slope, activate); break;
+        case 2: mlp_layer<2>(Wt, b, K, N, act, c.nn_slope, activate); break;
+        case 3: mlp_layer<3>(Wt, b, K, N, act, c.nn_slope, activate); break;
+        case 4: mlp_layer<4>(Wt, b, K, N, act, c.nn_slope, activate); break;
+        case 5: mlp_layer<5>(Wt, b, K, N, act, c.nn_slope, activate); break;
+        case 6: mlp_layer<6>(Wt, b, K, N, act, c.nn_slope, activate); break;
+        case 7: mlp_layer<7>(Wt, b, K, N, act, c.nn_slope, activate); break;
+        default: mlp_layer<8>(Wt, b, K, N, act, c.nn_slope, activate); break;
+      }
+      woff += (size_t)K * N;
+      boff += N;
+    }
+    // polynomial coefficients of this tile
+    for (int t = threadIdx.x; t < MLP_ROWS * c.nc; t += blockDim.x) {
+      int r = t / c.nc, j = t % c.nc;
+      int64_t row = row0 + r;
+      if (row < nrows) out[row * out_stride + j] = act[j * MLP_ROWS + r];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// stage 2b: GP posterior mean, one warp per row.  m_o = sum_i k(u, U_i) alpha[i, o] with
+// an ARD squared-exponential kernel; fp64 because alpha = K^-1 y cancels heavily.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_gp_f64(DevCtx c, const double* __restrict__ emu_in, int64_t nrows, double* __restrict__ out,
+         int out_stride) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < nrows; row += nwarps) {
+    double u[C1D_MAX_EMU];
+#pragma unroll
+    for (int d = 0; d < C1D_MAX_EMU; ++d) {
+      double xv = emu_in[row * C1D_MAX_EMU + d];
+      u[d] = (d < c.n_emu) ? (xv - c.emu_lo[d]) / (c.emu_hi[d] - c.emu_lo[d]) : 0.0;
+    }
+    double acc[C1D_MAX_COEF];
+#pragma unroll
+    for (int o = 0; o < C1D_MAX_COEF; ++o) acc[o] = 0.0;
+    for (int i = lane; i < c.gp_ntrain; i += 32) {
+      double s = 0.0;
+#pragma unroll
+      for (int d = 0; d < C1D_MAX_EMU; ++d) {
+        if (d < c.n_emu) {
+          double t = (u[d] - __ldg(c.gp_x + (size_t)i * c.n_emu + d)) * c.gp_invell[d];
+          s = fma(t, t, s);
+        }
+      }
+      double kern = c.gp_sigma2 * exp(-0.5 * s);
+#pragma unroll
+      for (int o = 0; o < C1D_MAX_COEF; ++o)
+        if (o < c.nc) acc[o] = fma(kern, __ldg(c.gp_alpha + (size_t)i * c.nc + o), acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < C1D_MAX_COEF; ++o)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+    if (lane == 0) {
+      double mF = emu_in[row * C1D_MAX_EMU + c.gp_imf];
+      double lnn = 0.0;  // ln norm(mF), Horner
+      for (int j = c.gp_nnorm - 1; j >= 0; --j) lnn = lnn * mF + c.gp_norm[j];
+      for (int o = 0; o < c.nc; ++o) {
+        double y = c.gp_ymean[o] + c.gp_ystd[o] * acc[o];
+        if (o == 0) y += lnn;
+        out[row * out_stride + o] = y;
+      }
+    }
+  }
+}
+
+int c1d_launch_emulator(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out,
+                        int out_stride, uint32_t flags, cudaStream_t s) {
+  if (nrows <= 0) return C1D_OK;
+  if (ctx->cfg.emu_kind == 0) {
+    if (flags & C1D_FLAG_EMU_TC) return c1d_tc_launch(ctx, emu_in, nrows, out, out_stride, s);
+    size_t smem = (size_t)MLP_MAXW * MLP_ROWS * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+      C1D_CUDA(ctx, cudaFuncSetAttribute(k_mlp_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+      attr_set = true;
+    }
+    int64_t ntiles = (nrows + MLP_ROWS - 1) / MLP_ROWS;
+    int grid = (int)(ntiles < ctx->num_sms ? ntiles : ctx->num_sms);
+    k_mlp_f64<<<grid, MLP_THREADS, smem, s>>>(ctx->d, emu_in, nrows, out, out_stride);
+  } else {
+    int64_t warps_needed = nrows;
+    int64_t blocks = (warps_needed + 7) / 8;
+    int64_t cap = (int64_t)ctx->num_sms * 8;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    k_gp_f64<<<grid, 256, 0, s>>>(ctx->d, emu_in, nrows, out, out_stride);
+  }
+  ctx->launches++;
+  C1D_CUDA(ctx, cudaPeekAtLastError());
+  return C1D_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// stage 3: fused emulator polynomial + contaminants + rebinning + residual.
+// A CTA is bound to one redshift bin: it stages the walker-independent k tables of that z
+// in shared memory once and streams a tile of walkers through them, one walker per warp.
+// ---------------------------------------------------------------------------------------
+#define P1D_THREADS 256
+#define P1D_WARPS (P1D_THREADS / 32)
+
+__global__ void __launch_bounds__(P1D_THREADS)
+k_fused_p1d(DevCtx c, int64_t W, int walkers_per_cta, const int* __restrict__ status,
+            const double* __restrict__ amp, double* __restrict__ dvec, double* __restrict__ p_out,
+            double* __restrict__ chi2z, int nfz_max, int ndz_max) {
+  extern __shared__ __align__(16) double sm[];
+  const int z = blockIdx.y;
+  const int f0 = c.zoff_f[z], nfz = c.zoff_f[z + 1] - f0;
+  const int d0 = c.zoff_d[z], ndz = c.zoff_d[z + 1] - d0;
+  const int RW = c.rebin_width;
+  double* tab = sm;                                   // [NCOL][nfz_max]
+  double* pbuf = tab + (size_t)C1D_NCOL * nfz_max;    // [P1D_WARPS][nfz_max]
+  double* rbw = pbuf + (size_t)P1D_WARPS * nfz_max;   // [ndz_max][RW]
+  double* dat = rbw + (size_t)ndz_max * RW;           // [ndz_max]
+  double* dzb = dat + ndz_max;                        // [P1D_WARPS][ndz_max]
+  int* rbs = reinterpret_cast<int*>(dzb + (size_t)P1D_WARPS * ndz_max);  // [ndz_max]
+
+  for (int t = threadIdx.x; t < C1D_NCOL * nfz; t += blockDim.x) {
+    int col = t / nfz, i = t % nfz;
+    tab[col * nfz_max + i] = c.tab[(size_t)col * c.nf + f0 + i];
+  }
+  for (int t = threadIdx.x; t < ndz * RW; t += blockDim.x) rbw[t] = c.rb_wgt[(size_t)d0 * RW + t];
+  for (int t = threadIdx.x; t < ndz; t += blockDim.x) {
+    dat[t] = c.data[d0 + t];
+    rbs[t] = c.rb_start[d0 + t];
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* pb = pbuf + (size_t)warp * nfz_max;
+  const double* tk = tab + C1D_COL_K * nfz_max;
+  const double* tS = tab + C1D_COL_S * nfz_max;
+  const double* tT = tab + C1D_COL_T * nfz_max;
+  const double* t1 = tab + C1D_COL_T1 * nfz_max;
+  const double* t2a = tab + C1D_COL_T2A * nfz_max;
+  const double* t2bc = tab + C1D_COL_T2BC * nfz_max;
+  const double* t3a = tab + C1D_COL_T3A * nfz_max;
+  const double* t3bc = tab + C1D_COL_T3BC * nfz_max;
+  const double* tD = tab + C1D_COL_D1 * nfz_max;
+  const double* tKT = tab + C1D_COL_KT * nfz_max;
+  const double* tQ = tab + C1D_COL_Q * nfz_max;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  // per-z inverse covariance block of this z (likelihood.py:939-940), read through L1/L2
+  size_t icov_base = 0;
+  for (int zz = 0; zz < z; ++zz) {
+    size_t n = c.zoff_d[zz + 1] - c.zoff_d[zz];
+    icov_base += n * n;
+  }
+  const double* icz = c.icov_blocks + icov_base;
+  double* dz = dzb + (size_t)warp * ndz_max;
+
+  const int64_t w_begin = (int64_t)blockIdx.x * walkers_per_cta;
+  int64_t w_end = w_begin + walkers_per_cta;
+  if (w_end > W) w_end = W;
+  for (int64_t w = w_begin + warp; w < w_end; w += P1D_WARPS) {
+    const bool ok = status[w] == ST_OK;
+    if (!ok) {
+      // rejected walkers carry no model (the reference returns None)
+      for (int j = lane; j < ndz; j += 32) {
+        if (dvec) dvec[w * c.nd + d0 + j] = 0.0;
+        if (p_out) p_out[w * c.nd + d0 + j] = qnan;
+      }
+      if (chi2z && lane == 0) chi2z[w * c.nz + z] = 0.0;
+      continue;
+    }
+    const double* a = amp + ((int64_t)z * W + w) * C1D_NAMP;
+    double av = (lane < C1D_NAMP) ? a[lane] : 0.0;
+    double cf[C1D_MAX_COEF];
+#pragma unroll
+    for (int j = 0; j < C1D_MAX_COEF; ++j) cf[j] = __shfl_sync(0xffffffffu, av, A_COEF0 + j);
+    const double s3 = __shfl_sync(0xffffffffu, av, A_S3), s2 = __shfl_sync(0xffffffffu, av, A_S2);
+    const double m0 = __shfl_sync(0xffffffffu, av, A_M0), c1 = __shfl_sync(0xffffffffu, av, A_C1);
+    const double c2a = __shfl_sync(0xffffffffu, av, A_C2A), c2b = __shfl_sync(0xffffffffu, av, A_C2B);
+    const double c3a = __shfl_sync(0xffffffffu, av, A_C3A), c3b = __shfl_sync(0xffffffffu, av, A_C3B);
+    const double h0 = __shfl_sync(0xffffffffu, av, A_H0);
+    const double hA = __shfl_sync(0xffffffffu, av, A_HCD1 + 0), hB = __shfl_sync(0xffffffffu, av, A_HCD1 + 1);
+    const double hC = __shfl_sync(0xffffffffu, av, A_HCD1 + 2), hD = __shfl_sync(0xffffffffu, av, A_HCD1 + 3);
+    const double aa = __shfl_sync(0xffffffffu, av, A_AA), sa2 = __shfl_sync(0xffffffffu, av, A_SA2);
+    const double res = __shfl_sync(0xffffffffu, av, A_RES);
+
+    for (int i = lane; i < nfz; i += 32) {
+      const double k = tk[i];
+      // emulator polynomial (Horner) -> P_emu in km/s (lya_theory.py:690-701)
+      double pl = 0.0;
+      const double tt = tT[i];
+#pragma unroll
+      for (int j = C1D_MAX_COEF - 1; j >= 0; --j)
+        if (j < c.nc) pl = fma(pl, tt, cf[j]);
+      const double p_emu = tS[i] * (c.emu_kind == 0 ? exp10(pl) : exp(pl));
+      double mult;
+      if (c.metal_model == 0) {
+        // si_mult.py:212-218, 267-341
+        const double G3 = 2.0 - 2.0 / (1.0 + exp(-s3 * k));
+        const double G2 = 2.0 - 2.0 / (1.0 + exp(-s2 * k));
+        mult = m0 + (c1 * G3 * t1[i] + G2 * (c2a * t2a[i] + c2b * t2bc[i])) +
+               (c3a * t3a[i] + c3b * t3bc[i]);
+      } else {
+        // si_vid_final.py:205-219
+        mult = 1.0 + c1 * exp(s3 * k) + c2a * t1[i] * exp(-s2 * k);
+      }
+      // hcd_model_rogers_class.py:115-135 (or hcd_boss.py:5-7 through D1)
+      const double hcd = h0 + hA * tD[i] + hB * tD[nfz_max + i] + hC * tD[2 * nfz_max + i] +
+                         hD * tD[3 * nfz_max + i];
+      // si_add.py:168-219
+      const double add = aa * tKT[i] * exp(-1.0 * sa2 * (k * k));
+      // resolution_class.py:99-108
+      const double syst = 1.0 + res * tQ[i];
+      // lya_theory.py:778-784 (IC correction is folded into the S column)
+      pb[i] = (hcd * mult * p_emu + add) * syst;
+    }
+    __syncwarp();
+    // rebinning (likelihood.py:147-161) and residual (likelihood.py:939, 957)
+    for (int j = lane; j < ndz; j += 32) {
+      const int st = rbs[j];
+      double m = 0.0;
+      for (int t = 0; t < RW; ++t) {
+        int ii = st + t;
+        double pv = (ii < nfz) ? pb[ii] : 0.0;
+        m = fma(rbw[j * RW + t], pv, m);
+      }
+      const double dj = dat[j] - m;
+      if (dvec) dvec[w * c.nd + d0 + j] = dj;
+      if (p_out) p_out[w * c.nd + d0 + j] = m;
+      dz[j] = dj;
+    }
+    __syncwarp();
+    if (chi2z) {
+      // chi2_z = d^T C_z^-1 d: lane owns columns j, rows broadcast from shared memory
+      double part = 0.0;
+      for (int j = lane; j < ndz; j += 32) {
+        double acc = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < ndz; ++i) acc = fma(__ldg(icz + (size_t)i * ndz + j), dz[i], acc);
+        part = fma(acc, dz[j], part);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      if (lane == 0) chi2z[w * c.nz + z] = part;
+    }
+    __syncwarp();
+  }
+}
+
+int c1d_launch_stage3(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int want_chi2z,
+                      cudaStream_t s) {
+  const c1d_config& cfg = ctx->cfg;
+  // largest z-bin sizes were stored in reserved_i by finalize
+  int nfz_max = cfg.reserved_i[0], ndz_max = cfg.reserved_i[1];
+  size_t smem = ((size_t)C1D_NCOL * nfz_max + (size_t)P1D_WARPS * nfz_max +
+                 (size_t)ndz_max * cfg.rebin_width + ndz_max + (size_t)P1D_WARPS * ndz_max) * sizeof(double) +
+                (size_t)ndz_max * sizeof(int) + 16;
+  if (smem > 200 * 1024) {
+    snprintf(ctx->err, sizeof(ctx->err), "stage 3 needs %zu B of shared memory (z-bin too large)", smem);
+    return C1D_ERR_ARG;
+  }
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    C1D_CUDA(ctx, cudaFuncSetAttribute(k_fused_p1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  // enough CTAs per z to fill the machine about twice, at least 32 walkers each
+  int64_t target_ctas = ((int64_t)ctx->num_sms * 4 + cfg.nz - 1) / cfg.nz;
+  int64_t wpc = (W + target_ctas - 1) / target_ctas;
+  if (wpc < 32) wpc = 32;
+  wpc = (wpc + P1D_WARPS - 1) / P1D_WARPS * P1D_WARPS;
+  dim3 grid((unsigned)((W + wpc - 1) / wpc), (unsigned)cfg.nz);
+  double* dvec = want_dvec ? ctx->ws.dvec : nullptr;
+  double* chi2z = want_chi2z ? ctx->ws.chi2z : nullptr;
+  k_fused_p1d<<<grid, P1D_THREADS, smem, s>>>(ctx->d, W, (int)wpc, ctx->ws.status, ctx->ws.amp, dvec,
+                                             p_out, chi2z, nfz_max, ndz_max);
+  ctx->launches++;
+  C1D_CUDA(ctx, cudaPeekAtLastError());
+  return C1D_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// stage 4: chi2 = d^T C^-1 d with the dense inverse covariance (likelihood.py:956-960) for
+// TW walkers per CTA.  The residual tile lives in shared memory as dT[i][w]; a thread owns
+// CW columns j of C^-1 and CW x TW accumulators.  (The per-z block chi2 is fused into
+// k_fused_p1d.)
+// ---------------------------------------------------------------------------------------
+template <int TW, int CW>
+__global__ void __launch_bounds__(256)
+k_quadform(DevCtx c, int64_t W, const double* __restrict__ dvec, double* __restrict__ out) {
+  extern __shared__ __align__(16) double sm[];
+  double* dT = sm;  // [nd][TW]
+  __shared__ double wsum[8][TW];
+  const int nd = c.nd;
+  const int64_t w0 = (int64_t)blockIdx.x * TW;
+  for (int t = threadIdx.x; t < nd * TW; t += blockDim.x) {
+    int w = t / nd, i = t % nd;  // coalesced global read along i
+    double v = (w0 + w < W) ? dvec[(w0 + w) * nd + i] : 0.0;
+    dT[i * TW + w] = v;
+  }
+  __syncthreads();
+
+  double part[TW];
+#pragma unroll
+  for (int w = 0; w < TW; ++w) part[w] = 0.0;
+  const int ncg = (nd + CW - 1) / CW;
+  const double* M = c.icov_full;
+  for (int cg = threadIdx.x; cg < ncg; cg += blockDim.x) {
+    const int j0 = cg * CW;
+    double acc[CW][TW];
+#pragma unroll
+    for (int cc = 0; cc < CW; ++cc)
+#pragma unroll
+      for (int w = 0; w < TW; ++w) acc[cc][w] = 0.0;
+#pragma unroll 2
+    for (int i = 0; i < nd; ++i) {
+      double mv[CW];
+#pragma unroll
+      for (int cc = 0; cc < CW; ++cc)
+        mv[cc] = (j0 + cc < nd) ? __ldg(M + (size_t)i * nd + j0 + cc) : 0.0;
+      const double2* dp = reinterpret_cast<const double2*>(dT + i * TW);
+      double dv[TW];
+#pragma unroll
+      for (int w = 0; w < TW / 2; ++w) {
+        double2 t = dp[w];
+        dv[2 * w] = t.x;
+        dv[2 * w + 1] = t.y;
+      }
+#pragma unroll
+      for (int cc = 0; cc < CW; ++cc)
+#pragma unroll
+        for (int w = 0; w < TW; ++w) acc[cc][w] = fma(mv[cc], dv[w], acc[cc][w]);
+    }
+#pragma unroll
+    for (int cc = 0; cc < CW; ++cc)
+      if (j0 + cc < nd)
+#pragma unroll
+        for (int w = 0; w < TW; ++w) part[w] = fma(acc[cc][w], dT[(j0 + cc) * TW + w], part[w]);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int w = 0; w < TW; ++w) {
+    double v = part[w];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) wsum[warp][w] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < TW && w0 + threadIdx.x < W) {
+    double v = 0.0;
+    for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) v += wsum[ww][threadIdx.x];
+    out[w0 + threadIdx.x] = v;
+  }
+}
+
+template <int TW>
+static int launch_quadform_tw(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
+  const int nd = ctx->cfg.nd;
+  size_t smem = (size_t)nd * TW * sizeof(double);
+  unsigned grid = (unsigned)((W + TW - 1) / TW);
+  auto kern = k_quadform<TW, 4>;
+  C1D_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int ncg = (nd + 3) / 4;
+  int threads = ((ncg + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (threads < 64) threads = 64;
+  kern<<<grid, threads, smem, s>>>(ctx->d, W, ctx->ws.dvec, ctx->ws.chi2f);
+  ctx->launches++;
+  C1D_CUDA(ctx, cudaPeekAtLastError());
+  return C1D_OK;
+}
+
+int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
+  const int nd = ctx->cfg.nd;
+  if ((size_t)nd * 16 * 8 <= 200 * 1024) return launch_quadform_tw<16>(ctx, W, s);
+  if ((size_t)nd * 8 * 8 <= 200 * 1024) return launch_quadform_tw<8>(ctx, W, s);
+  if ((size_t)nd * 4 * 8 <= 200 * 1024) return launch_quadform_tw<4>(ctx, W, s);
+  snprintf(ctx->err, sizeof(ctx->err), "data vector too long for the chi2 kernel (nd=%d)", nd);
+  return C1D_ERR_ARG;
+}
+
+// ---------------------------------------------------------------------------------------
+// stage 5: regulate, add the prior, blob conventions (likelihood.py:966-1024)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_finalize(DevCtx c, int64_t W, const int* __restrict__ status, const double* __restrict__ lnprior,
+           const double* __restrict__ chi2z, const double* __restrict__ chi2f, int use_full,
+           double* __restrict__ lnp, double* __restrict__ lnl_z, double* __restrict__ blobs,
+           double* __restrict__ chi2_out, uint32_t flags) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  const int st = status[w];
+  const double ninf = __longlong_as_double(0xfff0000000000000LL);
+  double loglike = ninf;
+  if (st == ST_OK) {
+    if (use_full) {
+      loglike = -0.5 * chi2f[w];
+    } else {
+      double sum = 0.0;
+      for (int z = 0; z < c.nz; ++z) {
+        bool on = !(flags & C1D_FLAG_ZMASK) || c.zmask[z];
+        if (on) sum += -0.5 * chi2z[w * c.nz + z];
+      }
+      loglike = sum;
+    }
+    if (loglike != loglike) loglike = ninf;  // NaN -> null_out (likelihood.py:966-967)
+  }
+  const bool null_out = !(loglike > ninf);
+  if (lnl_z) {
+    for (int z = 0; z < c.nz; ++z) {
+      bool on = !(flags & C1D_FLAG_ZMASK) || c.zmask[z];
+      double v = 0.0;
+      if (null_out) v = ninf;
+      else if (on) v = -0.5 * chi2z[w * c.nz + z];
+      lnl_z[w * c.nz + z] = v;
+    }
+  }
+  if (chi2_out) chi2_out[w] = -2.0 * loglike;
+  if (st == ST_OUT_OF_CUBE) {
+    lnp[w] = c.min_log_like;  // no prior added (likelihood.py:989-994); blobs are NaN already
+    return;
+  }
+  // regulate_log_like (likelihood.py:974-980), then the prior (:1019-1024)
+  double reg = (loglike > c.min_log_like) ? loglike : c.min_log_like;
+  lnp[w] = reg + lnprior[w];
+  if (null_out && blobs) {
+    for (int i = 0; i < 6; ++i) blobs[w * 6 + i] = 0.0;  // null blob (likelihood.py:833-836)
+  }
+}
+
+int c1d_launch_finalize(c1d_ctx* ctx, int64_t W, double* lnp, double* lnl_z, double* blobs,
+                        double* chi2, uint32_t flags, cudaStream_t s) {
+  int use_full = ctx->cfg.has_full && !(flags & C1D_FLAG_ZMASK);
+  int threads = 256;
+  unsigned grid = (unsigned)((W + threads - 1) / threads);
+  k_finalize<<<grid, threads, 0, s>>>(ctx->d, W, ctx->ws.status, ctx->ws.lnprior, ctx->ws.chi2z,
+                                      ctx->ws.chi2f, use_full, lnp, lnl_z, blobs, chi2, flags);
+  ctx->launches++;
+  C1D_CUDA(ctx, cudaPeekAtLastError());
+  return C1D_OK;
+}
+
+__global__ void __launch_bounds__(256)
+k_pack7(int64_t W, const double* __restrict__ lnp, const double* __restrict__ blobs, double* __restrict__ out7) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= W * 7) return;
+  int64_t w = t / 7;
+  int j = (int)(t % 7);
+  out7[t] = (j == 0) ? lnp[w] : blobs[w * 6 + j - 1];
+}
+
+int c1d_launch_pack7(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
+  unsigned grid = (unsigned)((W * 7 + 255) / 256);
+  k_pack7<<<grid, 256, 0, s>>>(W, ctx->ws.lnp, ctx->ws.blobs, ctx->ws.out7);
+  ctx->launches++;
+  C1D_CUDA(ctx, cudaPeekAtLastError());
+  return C1D_OK;
+}

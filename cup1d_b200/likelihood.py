@@ -1,0 +1,326 @@
+"""Drop-in for the hot path of ``cup1d.likelihood.likelihood.Likelihood``.
+
+``B200Likelihood(like)`` compiles a reference-API likelihood (or a model
+spec) into a device context and exposes
+
+* the reference's scalar methods with the reference's names, argument
+  meaning and return conventions — ``get_p1d_kms``, ``get_chi2``,
+  ``get_log_like``, ``compute_log_prob``, ``log_prob``,
+  ``log_prob_and_blobs``, ``minus_log_prob`` (likelihood.py:722-1072) — so
+  ``Fitter`` / ``emcee`` / ``scipy.optimize`` hooks keep working, and
+* batched entry points over ``values[W, ndim]``:
+  ``log_prob_batch``, ``log_prob_and_blobs_batch``, ``get_log_like_batch``,
+  ``get_chi2_batch``, ``get_p1d_kms_batch`` and ``log_prob_and_blobs_vectorized``
+  (the ``[W, 7]`` array ``emcee.EnsembleSampler(..., vectorize=True)`` wants).
+
+CUDA tensors in -> CUDA tensors out, asynchronously on the current torch
+stream.  NumPy in -> NumPy out through the host-buffer C-ABI call.  There is
+no CPU implementation behind this class.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _abi
+from .compile import compile_spec
+from .spec import spec_from_likelihood, spec_sizes
+
+BLOB_NAMES = ("Delta2_star", "n_star", "alpha_star", "f_star", "g_star", "H0")
+
+
+class B200Likelihood(object):
+    def __init__(self, like, device=None, emulator_precision="fp64"):
+        """like: a reference ``Likelihood`` (any object with its attributes) or
+        a model spec dict.  emulator_precision: "fp64" (CUDA cores, exact
+        parity with an fp64 evaluation of the weights) or "3xtf32"
+        (tcgen05 tensor cores, fp32-class accuracy; NN emulators only)."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("cup1d_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.spec = like if isinstance(like, dict) else spec_from_likelihood(like)
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.nz, self.ndim, self.nd, self.nf = spec_sizes(self.spec)
+        cfg, fields = compile_spec(self.spec)
+        self.ctx = _abi.Context(cfg, fields, device=self.device.index)
+        self.n_emu = cfg["n_emu"]
+        self.has_full = bool(cfg["has_full"])
+        p = self.spec["params"]
+        self.free_param_names = list(p["names"])
+        self.pmin = np.asarray(p["min"], dtype=float)
+        self.pmax = np.asarray(p["max"], dtype=float)
+        self.min_log_like = float(p["min_log_like"])
+        self.Gauss_priors = p["gauss_sigma_cube"]
+        self.fid_cube = (np.asarray(p["value"], dtype=float) - self.pmin) / (self.pmax - self.pmin)
+        self.zs = np.asarray(self.spec["zs"], dtype=float)
+        self.zoff_d = fields["ZOFF_D"].astype(int)
+        self._zmask_key = None
+        self.set_emulator_precision(emulator_precision)
+        d = self.spec["data"]
+        # constants for ignore_log_det_cov=False (likelihood.py:950, 962)
+        self._logdet_z = np.array([np.log(np.abs(1 / np.linalg.det(c))) for c in d["icov"]])
+        self._logdet_full = None
+        if d["full_icov"] is not None:
+            sign, ld = np.linalg.slogdet(d["full_icov"])
+            self._logdet_full = -ld
+
+    # ------------------------------------------------------------------
+    def set_emulator_precision(self, mode):
+        if mode not in ("fp64", "3xtf32"):
+            raise ValueError("emulator_precision must be 'fp64' or '3xtf32'")
+        if mode == "3xtf32" and self.spec["emulator"]["kind"] != "nn":
+            raise ValueError("the tensor-core path is for NN emulators")
+        self.emulator_precision = mode
+        self._base_flags = _abi.FLAG_EMU_TC if mode == "3xtf32" else 0
+
+    def set_data(self, full_Pk_kms):
+        """Replace the data vector (mock generation)"""
+        v = np.ascontiguousarray(full_Pk_kms, dtype=float).reshape(-1)
+        if v.size != self.nd:
+            raise ValueError("data vector length")
+        self.ctx.upload("DATA", v)
+        o = 0
+        for iz, k in enumerate(self.spec["data"]["k_kms"]):
+            self.spec["data"]["Pk_kms"][iz] = v[o : o + len(k)].copy()
+            o += len(k)
+        if self.spec["data"]["full_icov"] is not None:
+            self.spec["data"]["full_Pk_kms"] = v.copy()
+
+    def get_blobs_dtype(self):
+        """lya_theory.py:500-512"""
+        return [(n, float) for n in BLOB_NAMES]
+
+    def parameters_from_sampling_point(self, values):
+        """likelihood.py:561-574 as a flat array of parameter values"""
+        values = np.asarray(values, dtype=float)
+        return self.pmin + values * (self.pmax - self.pmin)
+
+    def sampling_point_from_parameters(self):
+        """likelihood.py:552-559"""
+        return self.fid_cube.copy()
+
+    # ------------------------------------------------------------------
+    def _flags(self, zmask=None, apply_hull=True):
+        flags = self._base_flags
+        if not apply_hull:
+            flags |= _abi.FLAG_NO_HULL
+        if zmask is not None:
+            zmask = np.atleast_1d(np.asarray(zmask, dtype=float))
+            sel = np.array([int(np.any(np.abs(zmask - z) < 1e-3)) for z in self.zs], dtype=np.int32)
+            key = sel.tobytes()
+            if key != self._zmask_key:
+                self.ctx.upload("ZMASK", sel)
+                self._zmask_key = key
+            flags |= _abi.FLAG_ZMASK
+        return flags
+
+    def _as_device(self, values):
+        """-> (x [W, ndim] float64 contiguous CUDA tensor, was_numpy, was_1d)"""
+        was_numpy = not torch.is_tensor(values)
+        x = torch.as_tensor(values, dtype=torch.float64) if was_numpy else values
+        was_1d = x.dim() == 1
+        if was_1d:
+            x = x.unsqueeze(0)
+        if x.dim() != 2 or x.shape[1] != self.ndim:
+            raise ValueError("values must have shape [W, %d]" % self.ndim)
+        x = x.to(device=self.device, dtype=torch.float64).contiguous()
+        return x, was_numpy, was_1d
+
+    def _evaluate(self, values, want_z=False, want_chi2=False, zmask=None, apply_hull=True):
+        x, was_numpy, _ = self._as_device(values)
+        W = x.shape[0]
+        with torch.cuda.device(self.device):
+            lnp = torch.empty(W, dtype=torch.float64, device=self.device)
+            blobs = torch.empty((W, 6), dtype=torch.float64, device=self.device)
+            lnl_z = torch.empty((W, self.nz), dtype=torch.float64, device=self.device) if want_z else None
+            chi2 = torch.empty(W, dtype=torch.float64, device=self.device) if want_chi2 else None
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self.ctx.loglike_batch(
+                x.data_ptr(), W, lnp.data_ptr(),
+                lnl_z.data_ptr() if want_z else None, blobs.data_ptr(),
+                chi2.data_ptr() if want_chi2 else None,
+                self._flags(zmask, apply_hull), stream,
+            )
+        return lnp, blobs, lnl_z, chi2, was_numpy
+
+    @staticmethod
+    def _out(t, was_numpy):
+        return t.cpu().numpy() if was_numpy else t
+
+    # ---- batched entry points -----------------------------------------
+    def log_prob_batch(self, values, zmask=None):
+        """lnP[W] = Likelihood.log_prob for every row (likelihood.py:1026)"""
+        if zmask is None and not torch.is_tensor(values):
+            return self.log_prob_and_blobs_vectorized(values)[:, 0].copy()
+        lnp, _, _, _, was_numpy = self._evaluate(values, zmask=zmask)
+        return self._out(lnp, was_numpy)
+
+    def log_prob_and_blobs_batch(self, values, zmask=None):
+        """(lnP[W], blobs[W, 6]) = Likelihood.log_prob_and_blobs per row (:1036)"""
+        if zmask is None and not torch.is_tensor(values):
+            out = self.log_prob_and_blobs_vectorized(values)
+            return out[:, 0].copy(), out[:, 1:].copy()
+        lnp, blobs, _, _, was_numpy = self._evaluate(values, zmask=zmask)
+        return self._out(lnp, was_numpy), self._out(blobs, was_numpy)
+
+    def log_prob_and_blobs_vectorized(self, values, out=None):
+        """[W, 7] rows (lnP, *blob): what ``emcee.EnsembleSampler(...,
+        vectorize=True, blobs_dtype=get_blobs_dtype())`` expects.  NumPy in,
+        NumPy out, through the host-buffer C-ABI call (copies included)."""
+        if torch.is_tensor(values):
+            lnp, blobs, _, _, _ = self._evaluate(values)
+            return torch.cat([lnp[:, None], blobs], dim=1)
+        x = np.ascontiguousarray(values, dtype=np.float64)
+        if x.ndim == 1:
+            x = x[None, :]
+        if x.shape[1] != self.ndim:
+            raise ValueError("values must have shape [W, %d]" % self.ndim)
+        if out is None:
+            out = np.empty((x.shape[0], 7), dtype=np.float64)
+        self.ctx.loglike_batch_host(x, out, self._base_flags)
+        return out
+
+    def get_log_like_batch(self, values, ignore_log_det_cov=True, zmask=None):
+        """(lnL[W], lnL_z[W, Nz]): -inf rows where the reference returns its
+        null output (likelihood.py:822-972)"""
+        lnp, blobs, lnl_z, chi2, was_numpy = self._evaluate(values, want_z=True, want_chi2=True, zmask=zmask)
+        lnl = -0.5 * chi2
+        if not ignore_log_det_cov:
+            ldz = torch.as_tensor(self._logdet_z, device=self.device)
+            if zmask is not None:
+                sel = torch.as_tensor([bool(np.any(np.abs(np.atleast_1d(zmask) - z) < 1e-3)) for z in self.zs], device=self.device)
+                ldz = ldz * sel
+            ok = torch.isfinite(lnl)
+            lnl_z = torch.where(ok[:, None], lnl_z - 0.5 * ldz[None, :], lnl_z)
+            if self.has_full and zmask is None:
+                lnl = torch.where(ok, lnl - 0.5 * self._logdet_full, lnl)
+            else:
+                lnl = torch.where(ok, lnl_z.sum(dim=1), lnl)
+        return self._out(lnl, was_numpy), self._out(lnl_z, was_numpy)
+
+    def get_chi2_batch(self, values, zmask=None):
+        """chi2[W] (likelihood.py:787-798); +inf where the reference gives -2*(-inf)"""
+        _, _, _, chi2, was_numpy = self._evaluate(values, want_chi2=True, zmask=zmask)
+        return self._out(chi2, was_numpy)
+
+    def get_p1d_kms_batch(self, values, apply_hull=True, return_emu_params=False):
+        """P[W, N_d]: the rebinned model concatenated over z in the order of
+        ``data.full_Pk_kms`` (likelihood.py:957); NaN rows where the reference
+        returns None.  With return_emu_params also emu[W, Nz, n_emu]."""
+        x, was_numpy, _ = self._as_device(values)
+        W = x.shape[0]
+        with torch.cuda.device(self.device):
+            p = torch.empty((W, self.nd), dtype=torch.float64, device=self.device)
+            emu = torch.empty((W, self.nz, self.n_emu), dtype=torch.float64, device=self.device) if return_emu_params else None
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self.ctx.p1d_batch(x.data_ptr(), W, p.data_ptr(), emu.data_ptr() if return_emu_params else None,
+                               self._flags(None, apply_hull), stream)
+        if return_emu_params:
+            return self._out(p, was_numpy), self._out(emu, was_numpy)
+        return self._out(p, was_numpy)
+
+    # ---- scalar API with the reference's conventions ------------------
+    def _values_or_fid(self, values):
+        if values is None:
+            if (self.fid_cube > 1).any() or (self.fid_cube < 0).any():
+                raise NotImplementedError("values=None with a fiducial point outside the unit cube")
+            return self.fid_cube.copy()
+        return np.asarray(values, dtype=float)
+
+    def get_p1d_kms(self, zs=None, _k_kms=None, values=None, return_covar=False, return_blob=False,
+                    return_emu_params=False, apply_hull=True, remove=None):
+        """likelihood.py:722-785 on the data redshifts and k bins"""
+        if zs is not None or _k_kms is not None or remove is not None or return_covar:
+            raise NotImplementedError("only the data grid, all contaminant terms and no emulator covariance")
+        v = self._values_or_fid(values)
+        if values is not None and ((v > 1).any() or (v < 0).any()):
+            # the reference evaluates outside the cube here; the device path rejects
+            raise NotImplementedError("get_p1d_kms outside the unit cube")
+        p, emu = self.get_p1d_kms_batch(v[None, :], apply_hull=apply_hull, return_emu_params=True)
+        if np.isnan(p[0]).all():
+            return None
+        out = [[p[0, self.zoff_d[iz] : self.zoff_d[iz + 1]].copy() for iz in range(self.nz)]]
+        if return_blob:
+            _, blobs = self.log_prob_and_blobs_batch(v[None, :])
+            out.append(tuple(blobs[0]))
+        if return_emu_params:
+            names = self.spec["emulator"]["emu_params"]
+            out.append({n: emu[0, :, j].copy() for j, n in enumerate(names)})
+        return out
+
+    def get_log_like(self, values=None, ignore_log_det_cov=True, return_blob=False, zmask=None):
+        """likelihood.py:822-972: [log_like, log_like_all[1, Nz](, blob)]"""
+        v = self._values_or_fid(values)
+        lnp, blobs, lnl_z, chi2, _ = self._evaluate(v[None, :], want_z=True, want_chi2=True, zmask=zmask)
+        if not ignore_log_det_cov:
+            lnl, lz = self.get_log_like_batch(v[None, :], ignore_log_det_cov=False, zmask=zmask)
+            ll, llz = float(lnl[0]), lz[0]
+        else:
+            ll, llz = float(-0.5 * chi2[0]), lnl_z[0].cpu().numpy()
+        if not np.isfinite(ll):
+            out = [-np.inf, -np.inf]
+            if return_blob:
+                out.append((0, 0, 0, 0, 0, 0))
+            return out
+        out = [ll, llz[None, :].copy()]
+        if return_blob:
+            out.append(tuple(blobs[0].cpu().numpy()))
+        return out
+
+    def get_chi2(self, values=None, return_all=False, zmask=None):
+        """likelihood.py:787-798"""
+        log_like, log_like_all = self.get_log_like(values, ignore_log_det_cov=True, zmask=zmask)
+        if return_all:
+            return -2.0 * log_like, -2.0 * log_like_all
+        return -2.0 * log_like
+
+    def regulate_log_like(self, log_like):
+        """likelihood.py:974-980"""
+        if (log_like is None) or np.isnan(log_like):
+            return self.min_log_like
+        return max(self.min_log_like, log_like)
+
+    def get_log_prior(self, values):
+        """likelihood.py:1049-1064"""
+        values = np.asarray(values, dtype=float)
+        if max(values) > 1 or min(values) < 0:
+            return self.min_log_like
+        if self.Gauss_priors is None:
+            return 0
+        return -np.sum((self.fid_cube - values) ** 2 / (2 * np.asarray(self.Gauss_priors) ** 2))
+
+    def compute_log_prob(self, values, return_blob=False, ignore_log_det_cov=True, zmask=None):
+        """likelihood.py:982-1024"""
+        if not ignore_log_det_cov:
+            raise NotImplementedError("log|C| term: use get_log_like(ignore_log_det_cov=False)")
+        v = np.asarray(values, dtype=float)
+        if zmask is None:
+            row = self.log_prob_and_blobs_vectorized(v[None, :])[0]
+            lnp, blob = float(row[0]), tuple(row[1:])
+        else:
+            lnp_t, blobs_t = self.log_prob_and_blobs_batch(v[None, :], zmask=zmask)
+            lnp, blob = float(lnp_t[0]), tuple(blobs_t[0])
+        if return_blob:
+            return lnp, blob
+        return lnp
+
+    def log_prob(self, values, ignore_log_det_cov=True, zmask=None):
+        """likelihood.py:1026-1034"""
+        return self.compute_log_prob(values, False, ignore_log_det_cov, zmask)
+
+    def log_prob_and_blobs(self, values, ignore_log_det_cov=True, zmask=None):
+        """likelihood.py:1036-1047"""
+        lnprob, blob = self.compute_log_prob(values, True, ignore_log_det_cov, zmask)
+        return (lnprob, *blob)
+
+    def minus_log_prob(self, values, zmask=None, ind_fix=None, pfix=None):
+        """likelihood.py:1066-1072 (in-place fixing of values included)"""
+        if ind_fix is not None:
+            values[ind_fix] = pfix
+        return -1.0 * self.log_prob(values, zmask=zmask)
+
+    # ------------------------------------------------------------------
+    def close(self):
+        self.ctx.close()

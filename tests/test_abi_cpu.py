@@ -1,0 +1,44 @@
+"""The C-ABI library loads without a GPU and exports every symbol the header
+declares (no compute calls here)."""
+
+import os
+import re
+
+from conftest import ROOT
+from cup1d_b200 import _abi
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "cup1d_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(c1d_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_header_symbols():
+    if not os.path.exists(_abi.LIB_PATH):
+        import __graft_entry__ as g
+
+        g.build()
+    lib = _abi.load_library()
+    syms = _header_symbols()
+    assert set(syms) == set(_abi.SYMBOLS), (syms, _abi.SYMBOLS)
+    for s in syms:
+        assert getattr(lib, s) is not None
+    assert lib.c1d_abi_version() == _abi.ABI_VERSION
+
+
+def test_config_struct_matches_header():
+    """field order of the ctypes mirror == order in the C struct"""
+    txt = open(os.path.join(ROOT, "include", "cup1d_b200.h")).read()
+    start = txt.index("typedef struct c1d_config {") + len("typedef struct c1d_config {")
+    body = txt[start : txt.index("} c1d_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        m = re.match(r"(int32_t|double)\s+(.*)", decl, flags=re.S)
+        if not m:
+            continue
+        for part in m.group(2).split(","):
+            names.append(re.sub(r"\[.*", "", part.strip()))
+    assert names == [f[0] for f in _abi.Config._fields_]

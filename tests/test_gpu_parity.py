@@ -1,0 +1,205 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's own
+outputs (goldens) and with the oracle on synthetic full-size configurations.
+
+Tolerances are those of BASELINE.json:north_star: model P1D within 1e-5
+relative, log-like within 1e-4 absolute (here: emulator in fp64 mode)."""
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_NAMES
+
+pytestmark = pytest.mark.gpu
+
+RTOL_P1D = 1e-5
+ATOL_LOGLIKE = 1e-4
+
+
+def _like(spec, **kw):
+    from cup1d_b200.likelihood import B200Likelihood
+
+    return B200Likelihood(spec, device=0, **kw)
+
+
+def _tol(v):
+    # 1e-4 absolute; far-from-fit walkers have |lnL| ~ 1e5..1e14 where one ulp exceeds it
+    return ATOL_LOGLIKE + 1e-11 * np.abs(v)
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_golden_reference_outputs(golden, name):
+    spec, ref = golden(name)
+    like = _like(spec)
+    x = ref["x"]
+    exp = ref["lnprob_blobs"]
+    bad = exp[:, 0] <= -1e99
+
+    got = like.log_prob_and_blobs_vectorized(x)  # host-buffer C-ABI call
+    np.testing.assert_array_equal(got[bad, 0], exp[bad, 0])
+    np.testing.assert_array_equal(np.isnan(got[bad, 1:]), np.isnan(exp[bad, 1:]))
+    np.testing.assert_array_equal(np.nan_to_num(got[bad, 1:]), np.nan_to_num(exp[bad, 1:]))
+    assert np.all(np.abs(got[~bad, 0] - exp[~bad, 0]) <= _tol(exp[~bad, 0]))
+    np.testing.assert_allclose(got[~bad, 1:], exp[~bad, 1:], rtol=1e-12)
+
+    # device-tensor entry points
+    import torch
+
+    xd = torch.as_tensor(x, device="cuda:0")
+    lnp, blobs = like.log_prob_and_blobs_batch(xd)
+    np.testing.assert_array_equal(lnp.cpu().numpy(), got[:, 0])
+    np.testing.assert_array_equal(np.nan_to_num(blobs.cpu().numpy()), np.nan_to_num(got[:, 1:]))
+    np.testing.assert_array_equal(like.log_prob_batch(x), got[:, 0])
+
+    # model P1D, emulator inputs
+    incube = ~((x > 1).any(axis=1) | (x < 0).any(axis=1))
+    p, emu = like.get_p1d_kms_batch(x[incube], return_emu_params=True)
+    refp = ref["p1d"][incube]
+    none = np.isnan(refp).all(axis=1)
+    assert np.isnan(p[none]).all()
+    assert np.max(np.abs(p[~none] / refp[~none] - 1)) <= RTOL_P1D
+    np.testing.assert_allclose(emu[~none], ref["emu_call"][incube][~none], rtol=1e-12)
+
+    # log-like, per-z log-like, chi2
+    lnl, lnl_z = like.get_log_like_batch(x)
+    rl = ref["loglike"]
+    inf = np.isinf(rl)
+    np.testing.assert_array_equal(lnl[inf], rl[inf])
+    assert np.all(np.abs(lnl[~inf] - rl[~inf]) <= _tol(rl[~inf]))
+    assert np.all(np.abs(lnl_z[~inf] - ref["loglike_all"][~inf]) <= _tol(ref["loglike_all"][~inf]))
+    chi2 = like.get_chi2_batch(x)
+    assert np.all(np.abs(chi2[~inf] - ref["chi2"][~inf]) <= 2 * _tol(ref["chi2"][~inf]))
+    assert np.all(np.isinf(chi2[inf]))
+
+    # zmask (the reference itself fails for zmask + IC correction: NaN in the fixture)
+    if not np.isnan(ref["lnprob_zmask"]).any():
+        gz = like.log_prob_batch(x, zmask=ref["zmask"])
+        ez = ref["lnprob_zmask"]
+        badz = ez <= -1e99
+        np.testing.assert_array_equal(gz[badz], ez[badz])
+        assert np.all(np.abs(gz[~badz] - ez[~badz]) <= _tol(ez[~badz]))
+    like.close()
+
+
+def test_scalar_api_conventions(golden):
+    """same names / return conventions as likelihood.py:722-1072"""
+    spec, ref = golden("nyx_gp_priors")
+    like = _like(spec)
+    x = ref["x"]
+    exp = ref["lnprob_blobs"]
+    for i in [0, 5, len(x) - 1, int(np.argmin(exp[:, 0]))]:
+        v = x[i].copy()
+        out = like.log_prob_and_blobs(v)
+        assert len(out) == 7
+        if exp[i, 0] <= -1e99:
+            assert out[0] == exp[i, 0]
+        else:
+            assert abs(out[0] - exp[i, 0]) <= _tol(exp[i, 0])
+        assert like.log_prob(v) == out[0]
+        assert like.minus_log_prob(v) == -out[0]
+        ll = like.get_log_like(v, return_blob=True)
+        if np.isinf(ref["loglike"][i]):
+            assert ll[0] == -np.inf and ll[1] == -np.inf and ll[2] == (0, 0, 0, 0, 0, 0)
+            assert like.get_chi2(v) == np.inf
+            incube = not ((v > 1).any() or (v < 0).any())
+            if incube:
+                assert like.get_p1d_kms(values=v) is None
+        else:
+            assert ll[1].shape == (1, len(spec["zs"]))
+            assert abs(ll[0] - ref["loglike"][i]) <= _tol(ref["loglike"][i])
+            chi2, chi2_all = like.get_chi2(v, return_all=True)
+            assert abs(chi2 - ref["chi2"][i]) <= 2 * _tol(ref["chi2"][i])
+            res = like.get_p1d_kms(values=v, return_blob=True, return_emu_params=True)
+            assert len(res) == 3 and len(res[0]) == len(spec["zs"])
+            assert np.max(np.abs(np.concatenate(res[0]) / ref["p1d"][i] - 1)) <= RTOL_P1D
+    # ind_fix / pfix of minus_log_prob (likelihood.py:1069-1070) acts in place
+    v = x[0].copy()
+    like.minus_log_prob(v, ind_fix=3, pfix=0.5)
+    assert v[3] == 0.5
+    assert like.get_blobs_dtype()[0] == ("Delta2_star", float)
+    like.close()
+
+
+def _synthetic(kind):
+    from cup1d_b200 import synth
+
+    if kind == "c1":  # sam_sim-style mock: NN emulator, Chabanier grid, block-diagonal cov
+        emu = synth.synth_nn_emulator(seed=11)
+        spec = synth.build_spec(emu, grid="chab", rebin_k=1, full_cov=False, seed=14)
+    elif kind == "c2":  # GP emulator, DR1 grid, full covariance
+        emu = synth.synth_gp_emulator(seed=12, n_train=330)
+        spec = synth.build_spec(emu, grid="dr1", rebin_k=8, full_cov=True, seed=14)
+    elif kind == "c4":  # DR1-like: NN emulator, rebin 8, dense 681^2 inverse covariance
+        emu = synth.synth_nn_emulator(seed=11)
+        spec = synth.build_spec(emu, grid="dr1", rebin_k=8, full_cov=True, seed=14)
+    else:  # nyx-like full nuisance set: 7 inputs, nrun free, HCD_const free
+        emu = synth.synth_nn_emulator(seed=13, suite="nyx", ndeg=6)
+        spec = synth.build_spec(emu, grid="dr1", rebin_k=8, full_cov=True, vary_nrun=True, nz_igm=6, hcd_const=True, gauss_priors=True, seed=14)
+    like = _like(spec)
+    p_truth = like.get_p1d_kms_batch(synth.truth_point(spec)[None, :])[0]
+    synth.attach_mock_data(spec, p_truth, add_noise=(kind != "c1"))
+    like.close()
+    return spec
+
+
+@pytest.mark.parametrize("kind", ["c1", "c2", "c4", "c3"])
+def test_synthetic_full_size_vs_oracle(kind):
+    from cup1d_b200 import synth
+    from oracle.model import OracleLikelihood
+
+    spec = _synthetic(kind)
+    like = _like(spec)
+    ora = OracleLikelihood(spec)
+    x = np.concatenate([synth.walkers_ball(spec, 40, seed=0), synth.walkers_sweep(spec, 88, seed=16, frac_out=0.05)])
+    got = like.log_prob_and_blobs_vectorized(x)
+    exp = ora.log_prob_and_blobs_many(x)
+    bad = exp[:, 0] <= -1e99
+    np.testing.assert_array_equal(got[bad, 0], exp[bad, 0])
+    assert np.all(np.abs(got[~bad, 0] - exp[~bad, 0]) <= _tol(exp[~bad, 0])), np.max(np.abs(got[~bad, 0] - exp[~bad, 0]))
+    np.testing.assert_allclose(got[~bad, 1:], exp[~bad, 1:], rtol=1e-12)
+    p = like.get_p1d_kms_batch(x[~bad][:32])
+    for i, v in enumerate(x[~bad][:32]):
+        po = np.concatenate(ora.get_p1d_kms(values=v)[0])
+        assert np.max(np.abs(p[i] / po - 1)) <= RTOL_P1D
+    like.close()
+
+
+def test_full_size_properties():
+    """size-independent properties at the benchmark size (C4, 65 536 walkers)"""
+    import torch
+
+    from cup1d_b200 import synth
+
+    spec = _synthetic("c4")
+    # (a) block-diagonal full covariance: the dense chi2 kernel must equal the sum of the
+    #     per-z chi2 computed inside the fused kernel
+    from scipy.linalg import block_diag
+
+    spec_bd = dict(spec)
+    spec_bd["data"] = dict(spec["data"])
+    spec_bd["data"]["full_icov"] = block_diag(*spec["data"]["icov"])
+    like = _like(spec_bd)
+    W = 65536
+    x = synth.walkers_sweep(spec, W, seed=16)
+    xd = torch.as_tensor(x, device="cuda:0")
+    lnl, lnl_z = like.get_log_like_batch(xd)
+    ok = torch.isfinite(lnl)
+    assert int((~ok).sum()) == int(round(0.01 * W))  # the rows put outside the cube
+    rel = (lnl[ok] - lnl_z[ok].sum(dim=1)).abs() / lnl[ok].abs().clamp(min=1.0)
+    assert float(rel.max()) < 1e-11
+    assert bool((lnl[ok] <= 0).all())
+    # (b) row independence: any batch split gives bit-identical results
+    lnp_all = like.log_prob_batch(xd)
+    lnp_a = like.log_prob_batch(xd[:1000])
+    lnp_b = like.log_prob_batch(xd[1000:1777])
+    assert torch.equal(lnp_all[:1000], lnp_a) and torch.equal(lnp_all[1000:1777], lnp_b)
+    # (c) permutation equivariance
+    perm = torch.randperm(4096, device="cuda:0", generator=torch.Generator(device="cuda:0").manual_seed(1))
+    assert torch.equal(like.log_prob_batch(xd[:4096][perm]), lnp_all[:4096][perm])
+    like.close()
+    # (d) noise-free mock: chi2 at the truth is zero (mock generation round trip)
+    like = _like(spec)
+    xt = synth.truth_point(spec)
+    p_truth = like.get_p1d_kms_batch(xt[None, :])[0]
+    like.set_data(p_truth)
+    assert abs(like.get_chi2(xt)) < 1e-18 * 681
+    like.close()
