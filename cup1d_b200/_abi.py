@@ -25,7 +25,7 @@ FLAG_EMU_TC = 4
 SYMBOLS = (
     "c1d_abi_version", "c1d_ctx_create", "c1d_ctx_upload", "c1d_ctx_finalize",
     "c1d_loglike_batch", "c1d_p1d_batch", "c1d_emulator_only", "c1d_loglike_batch_host",
-    "c1d_launch_count", "c1d_set_timing", "c1d_get_timing", "c1d_ctx_destroy", "c1d_last_error",
+    "c1d_launch_count", "c1d_set_timing", "c1d_get_timing", "c1d_tc_selftest", "c1d_ctx_destroy", "c1d_last_error",
 )
 
 
@@ -82,6 +82,8 @@ def load_library(path=None):
     lib.c1d_launch_count.restype = i64
     lib.c1d_set_timing.argtypes = [vp, C.c_int]
     lib.c1d_get_timing.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.c1d_tc_selftest.argtypes = [C.c_int, vp, vp, vp, C.c_int, C.c_int]
+    lib.c1d_tc_selftest.restype = C.c_int
     lib.c1d_ctx_destroy.argtypes = [vp]
     lib.c1d_last_error.argtypes = [vp]
     lib.c1d_last_error.restype = C.c_char_p

@@ -1,11 +1,627 @@
-// Tensor-core (tcgen05, 3xTF32) emulator path — placeholder until the kernel lands.
+// Stage 2 on the 5th-generation tensor cores: the LaCE-style MLP as a chain of
+// tcgen05.mma (kind::tf32) GEMMs over a 128-row tile of (walker, z) pairs, in 3xTF32
+// (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulation in TMEM).
+//
+// One persistent CTA per SM, 6 warps:
+//   warps 0-3  one thread per row / TMEM lane: first layer on CUDA cores (fp64), per-layer
+//              epilogue TMEM -> registers -> bias + LeakyReLU -> hi/lo split -> next A operand,
+//              last layer (-> polynomial coefficients) on CUDA cores in fp64
+//   warp 4     TMEM allocation; lane 0 issues every tcgen05.mma and tcgen05.commit
+//   warp 5     lane 0 streams the pre-swizzled weight images with cp.async.bulk (TMA bulk copy)
+//              through a 3-stage mbarrier ring
+//
+// Operand placement (227 KB of shared memory cannot hold hi and lo of a 128 x 256 tile):
+//   A_hi   shared memory, K-major SWIZZLE_128B, 8 chunks of 32 k            (SS form)
+//   A_lo   tensor memory columns [256, 512), lane = row, column = k         (TS form)
+//   B_hi, B_lo  shared memory ring, one (layer, n-block<=128, k-chunk) unit per stage
+//   D      tensor memory columns [0, 256)
+#include <math.h>
+
+#include <vector>
+
 #include "c1d_internal.h"
 
-int c1d_tc_prepare(c1d_ctx* ctx) { (void)ctx; return C1D_OK; }
+namespace {
 
-int c1d_tc_launch(c1d_ctx* ctx, const double*, int64_t, double*, int, cudaStream_t) {
-  snprintf(ctx->err, sizeof(ctx->err), "tensor-core emulator path not built");
-  return C1D_ERR_STATE;
+constexpr int TC_ROWS = 128;
+constexpr int TC_KCH = 32;                         // tf32 elements per 128-byte swizzle row
+constexpr int TC_A_CHUNK_BYTES = TC_ROWS * 128;    // 16 KB
+constexpr int TC_MAX_KCHUNKS = 8;                  // K <= 256
+constexpr int TC_A_BYTES = TC_MAX_KCHUNKS * TC_A_CHUNK_BYTES;
+constexpr int TC_STAGE_BYTES = 32768;              // 128 rows x 128 B x (hi, lo)
+constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_UNITS = 64;
+constexpr int TC_MAX_TL = C1D_MAX_LAYERS;
+constexpr uint32_t TC_ALO_COL = 256;
+constexpr int TC_BAR_BYTES = 128;
+constexpr size_t TC_SMEM = 1024 + TC_A_BYTES + TC_STAGES * TC_STAGE_BYTES + TC_BAR_BYTES + TC_MAX_UNITS * 16;
+static_assert(TC_SMEM <= 232448, "shared memory budget");
+
+struct TcUnit {
+  uint32_t w_off;      // byte offset of the unit in the weight image
+  uint16_t rows;       // rows of the n-block (multiple of 16, <= 128)
+  uint16_t dcol;       // first D column of the n-block
+  uint8_t layer;       // tensor-layer index
+  uint8_t kchunk;      // which 32-wide k chunk of A
+  uint8_t ksteps;      // k-steps of 8 issued in this chunk
+  uint8_t flags;       // 1 = first unit of its (layer, n-block), 2 = last unit of its layer
+  uint32_t pad;
+};
+static_assert(sizeof(TcUnit) == 16, "TcUnit layout");
+
+struct TcParams {
+  const uint8_t* wimg;
+  const TcUnit* units;
+  const float* bias;        // tensor layers, padded, concatenated
+  const double *w_first, *b_first, *w_last, *b_last;
+  const double *emu_lo, *emu_hi;
+  int n_units, n_tl;
+  int n_in, first_out, last_in, last_out;
+  int tl_npad[TC_MAX_TL];
+  int tl_bias_off[TC_MAX_TL];
+  int tl_unit_begin[TC_MAX_TL + 1];
+  double slope;
+};
+
+struct TcState {
+  TcParams p;
+  void *d_wimg, *d_units, *d_bias, *d_wfirst, *d_bfirst, *d_wlast, *d_blast;
+  bool ready;
+};
+
+// ------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-void c1d_tc_destroy(c1d_ctx* ctx) { (void)ctx; }
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: tf32 x tf32 -> f32, A and B K-major, M = 128
+__device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// byte offset of (row, 16-byte group g of k) inside one 128-row x 32-k SWIZZLE_128B chunk
+__device__ __host__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t g) {
+  return (row >> 3) * 1024u + (row & 7u) * 128u + ((g ^ (row & 7u)) << 4);
+}
+
+// split 16 fp32 activations into tf32 hi (to shared memory, swizzled) and lo (to TMEM)
+__device__ __forceinline__ void store_act16(uint32_t a_smem, uint32_t tmem_lane_base, uint32_t row, int col0, const float* v) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    uint32_t b = __float_as_uint(v[i]);
+    hi[i] = b & 0xffffe000u;
+    lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+  }
+  const uint32_t chunk = (uint32_t)col0 >> 5, g0 = ((uint32_t)col0 & 31u) >> 2;
+  const uint32_t cbase = a_smem + chunk * TC_A_CHUNK_BYTES;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t addr = cbase + sw128_off(row, g0 + q);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hi[4 * q]), "r"(hi[4 * q + 1]), "r"(hi[4 * q + 2]),
+                 "r"(hi[4 * q + 3])
+                 : "memory");
+  }
+  tmem_st16(tmem_lane_base + TC_ALO_COL + (uint32_t)col0, lo);
+}
+
+// ------------------------------------------------------------------------------------
+// the MLP kernel
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* __restrict__ out, int out_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_smem = base;
+  const uint32_t b_smem = base + TC_A_BYTES;
+  const uint32_t bar0 = b_smem + TC_STAGES * TC_STAGE_BYTES;
+  // barriers: b_full[s] at +0, b_empty[s] at +8*TC_STAGES, d_full, a_ready, then the TMEM pointer
+  const uint32_t bar_bfull = bar0, bar_bempty = bar0 + 8 * TC_STAGES;
+  const uint32_t bar_dfull = bar0 + 16 * TC_STAGES, bar_aready = bar_dfull + 8;
+  const uint32_t tmem_slot = bar_aready + 8;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+  TcUnit* units = reinterpret_cast<TcUnit*>(gen_base + (bar0 + TC_BAR_BYTES - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < p.n_units; i += TC_THREADS) units[i] = p.units[i];
+  if (tid == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar_bfull + 8 * s, 1);
+      mbar_init(bar_bempty + 8 * s, 1);
+    }
+    mbar_init(bar_dfull, 1);
+    mbar_init(bar_aready, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_p;
+
+  const int64_t ntiles = (nrows + TC_ROWS - 1) / TC_ROWS;
+  const float slope = (float)p.slope;
+
+  if (warp < 4) {
+    // ============================ row owners / epilogue ============================
+    const uint32_t row = (uint32_t)tid;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t d_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t grow = tile * TC_ROWS + row;
+      // ---- first layer on CUDA cores, fp64 ----
+      double xin[C1D_MAX_EMU];
+#pragma unroll
+      for (int j = 0; j < C1D_MAX_EMU; ++j) {
+        double xv = (grow < nrows && j < p.n_in) ? emu_in[grow * C1D_MAX_EMU + j] : 0.0;
+        xin[j] = (j < p.n_in) ? (xv - p.emu_lo[j]) / (p.emu_hi[j] - p.emu_lo[j]) - 0.5 : 0.0;
+      }
+      const int fo_pad = (p.first_out + 15) & ~15;
+      for (int col0 = 0; col0 < fo_pad; col0 += 16) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          int n = col0 + i;
+          double acc = 0.0;
+          if (n < p.first_out) {
+            acc = __ldg(p.b_first + n);
+#pragma unroll
+            for (int j = 0; j < C1D_MAX_EMU; ++j)
+              if (j < p.n_in) acc = fma(__ldg(p.w_first + n * p.n_in + j), xin[j], acc);
+            acc = (acc > 0.0) ? acc : p.slope * acc;
+          }
+          v[i] = (float)acc;
+        }
+        store_act16(a_smem, tmem_lane, row, col0, v);
+      }
+      fence_async_smem();
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_aready);
+
+      for (int tl = 0; tl < p.n_tl; ++tl) {
+        mbar_wait(bar_dfull, d_phase);
+        d_phase ^= 1;
+        tc_fence_after();
+        const int npad = p.tl_npad[tl];
+        const float* bias = p.bias + p.tl_bias_off[tl];
+        if (tl < p.n_tl - 1) {
+          for (int col0 = 0; col0 < npad; col0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_lane + (uint32_t)col0, r);
+            tc_wait_ld();
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float t = __uint_as_float(r[i]) + __ldg(bias + col0 + i);
+              v[i] = (t > 0.f) ? t : slope * t;
+            }
+            store_act16(a_smem, tmem_lane, row, col0, v);
+          }
+          fence_async_smem();
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(bar_aready);
+        } else {
+          // ---- last tensor layer: activation, then the output layer on CUDA cores (fp64) ----
+          double acc[C1D_MAX_COEF];
+#pragma unroll
+          for (int o = 0; o < C1D_MAX_COEF; ++o) acc[o] = (o < p.last_out) ? __ldg(p.b_last + o) : 0.0;
+          for (int col0 = 0; col0 < npad; col0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_lane + (uint32_t)col0, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              int k = col0 + i;
+              if (k < p.last_in) {
+                float t = __uint_as_float(r[i]) + __ldg(bias + k);
+                double a = (double)((t > 0.f) ? t : slope * t);
+#pragma unroll
+                for (int o = 0; o < C1D_MAX_COEF; ++o)
+                  if (o < p.last_out) acc[o] = fma(__ldg(p.w_last + o * p.last_in + k), a, acc[o]);
+              }
+            }
+          }
+          if (grow < nrows) {
+#pragma unroll
+            for (int o = 0; o < C1D_MAX_COEF; ++o)
+              if (o < p.last_out) out[grow * out_stride + o] = acc[o];
+          }
+          tc_fence_before();
+        }
+      }
+    }
+  } else if (tid == 128) {
+    // ================================ MMA issuer ================================
+    uint32_t a_phase = 0, stage = 0, b_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tl = 0; tl < p.n_tl; ++tl) {
+        mbar_wait(bar_aready, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+        for (int u = p.tl_unit_begin[tl]; u < p.tl_unit_begin[tl + 1]; ++u) {
+          const TcUnit un = units[u];
+          mbar_wait(bar_bfull + 8 * stage, b_phase);
+          tc_fence_after();
+          const uint32_t sb = b_smem + stage * TC_STAGE_BYTES;
+          const uint32_t idesc = make_idesc_tf32(un.rows);
+          const uint32_t d_tmem = tmem_base + un.dcol;
+          for (uint32_t ks = 0; ks < un.ksteps; ++ks) {
+            const uint64_t a_hi = make_desc_sw128(a_smem + un.kchunk * TC_A_CHUNK_BYTES + ks * 32u);
+            const uint64_t b_hi = make_desc_sw128(sb + ks * 32u);
+            const uint64_t b_lo = make_desc_sw128(sb + (uint32_t)un.rows * 128u + ks * 32u);
+            const uint32_t a_lo = tmem_base + TC_ALO_COL + (uint32_t)un.kchunk * TC_KCH + ks * 8u;
+            const uint32_t acc0 = ((un.flags & 1) && ks == 0) ? 0u : 1u;
+            mma_ts(d_tmem, a_lo, b_hi, idesc, acc0);  // small terms first
+            mma_ss(d_tmem, a_hi, b_lo, idesc, 1u);
+            mma_ss(d_tmem, a_hi, b_hi, idesc, 1u);
+          }
+          tc_commit(bar_bempty + 8 * stage);
+          if (un.flags & 2) tc_commit(bar_dfull);
+          if (++stage == TC_STAGES) { stage = 0; b_phase ^= 1; }
+        }
+      }
+    }
+  } else if (tid == 160) {
+    // ============================== weight streamer ==============================
+    uint32_t stage = 0, phase = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int u = 0; u < p.n_units; ++u) {
+        const TcUnit un = units[u];
+        mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
+        const uint32_t bytes = (uint32_t)un.rows * 256u;
+        mbar_expect_tx(bar_bfull + 8 * stage, bytes);
+        bulk_g2s(b_smem + stage * TC_STAGE_BYTES, p.wimg + un.w_off, bytes, bar_bfull + 8 * stage);
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// self test: D[128, N] = A[128, 32] . B[N, 32]^T with one tcgen05.mma chain (4 k-steps)
+//   mode 0: A from shared memory (SS), mode 1: A from tensor memory (TS)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160, 1)
+k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_smem = base, b_smem = base + TC_A_CHUNK_BYTES, bar = b_smem + 256 * 128, tmem_slot = bar + 8;
+  volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_p;
+  if (warp < 4) {
+    const uint32_t row = tid;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float v[16];
+    for (int col0 = 0; col0 < 32; col0 += 16) {
+      for (int i = 0; i < 16; ++i) v[i] = A[row * 32 + col0 + i];
+      // hi to shared memory, and the same hi values to TMEM columns [256, 288) for the TS test
+      uint32_t hi[16];
+      for (int i = 0; i < 16; ++i) hi[i] = __float_as_uint(v[i]) & 0xffffe000u;
+      for (int q = 0; q < 4; ++q) {
+        uint32_t addr = a_smem + sw128_off(row, (col0 >> 2) + q);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hi[4 * q]), "r"(hi[4 * q + 1]),
+                     "r"(hi[4 * q + 2]), "r"(hi[4 * q + 3])
+                     : "memory");
+      }
+      tmem_st16(tmem_lane + TC_ALO_COL + col0, hi);
+    }
+    for (int n = row; n < N; n += 128)
+      for (int g = 0; g < 8; ++g) {
+        uint32_t w[4];
+        for (int i = 0; i < 4; ++i) w[i] = __float_as_uint(B[n * 32 + 4 * g + i]) & 0xffffe000u;
+        uint32_t addr = b_smem + sw128_off(n, g);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+      }
+    fence_async_smem();
+    tc_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 128) {
+    const uint32_t idesc = make_idesc_tf32(N);
+    for (uint32_t ks = 0; ks < 4; ++ks) {
+      const uint64_t bd = make_desc_sw128(b_smem + ks * 32u);
+      if (mode == 0)
+        mma_ss(tmem_base, make_desc_sw128(a_smem + ks * 32u), bd, idesc, ks ? 1u : 0u);
+      else
+        mma_ts(tmem_base, tmem_base + TC_ALO_COL + ks * 8u, bd, idesc, ks ? 1u : 0u);
+    }
+    tc_commit(bar);
+  }
+  if (warp < 4) {
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int col0 = 0; col0 < N; col0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_lane + col0, r);
+      tc_wait_ld();
+      for (int i = 0; i < 16; ++i) D[tid * N + col0 + i] = __uint_as_float(r[i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+static inline float tf32_trunc(float x) {
+  uint32_t b;
+  memcpy(&b, &x, 4);
+  b &= 0xffffe000u;
+  memcpy(&x, &b, 4);
+  return x;
+}
+
+int c1d_tc_prepare(c1d_ctx* ctx) {
+  const c1d_config& c = ctx->cfg;
+  if (ctx->tc_state) { c1d_tc_destroy(ctx); }
+  // needs a CUDA-core first layer, >= 1 tensor layer and a CUDA-core output layer
+  if (c.emu_kind != 0 || c.n_layers < 3) return C1D_OK;
+  TcState* st = new TcState();
+  memset(st, 0, sizeof(*st));
+  ctx->tc_state = st;
+  const int L = c.n_layers;
+  size_t nw = 0, nb = 0;
+  std::vector<size_t> woff(L), boff(L);
+  for (int l = 0; l < L; ++l) {
+    woff[l] = nw;
+    boff[l] = nb;
+    nw += (size_t)c.layer_dims[l] * c.layer_dims[l + 1];
+    nb += c.layer_dims[l + 1];
+  }
+  std::vector<double> W(nw), Bv(nb);
+  C1D_CUDA(ctx, cudaMemcpy(W.data(), ctx->dev[C1D_F_NN_W], nw * sizeof(double), cudaMemcpyDeviceToHost));
+  C1D_CUDA(ctx, cudaMemcpy(Bv.data(), ctx->dev[C1D_F_NN_B], nb * sizeof(double), cudaMemcpyDeviceToHost));
+  // weights are stored in-major: Wt[k * N + n]
+  auto wat = [&](int l, int n, int k) { return W[woff[l] + (size_t)k * c.layer_dims[l + 1] + n]; };
+
+  TcParams& p = st->p;
+  p.n_in = c.layer_dims[0];
+  p.first_out = c.layer_dims[1];
+  p.last_in = c.layer_dims[L - 1];
+  p.last_out = c.layer_dims[L];
+  p.n_tl = L - 2;
+  p.slope = c.nn_slope;
+  std::vector<TcUnit> units;
+  std::vector<uint8_t> img;
+  std::vector<float> bias;
+  for (int tl = 0; tl < p.n_tl; ++tl) {
+    const int l = tl + 1;
+    const int K = c.layer_dims[l], N = c.layer_dims[l + 1];
+    const int npad = (N + 15) & ~15;
+    p.tl_npad[tl] = npad;
+    p.tl_bias_off[tl] = (int)bias.size();
+    for (int n = 0; n < npad; ++n) bias.push_back(n < N ? (float)Bv[boff[l] + n] : 0.f);
+    p.tl_unit_begin[tl] = (int)units.size();
+    const int nkc = (K + TC_KCH - 1) / TC_KCH;
+    int blocks[2], nblk = 1;
+    if (npad <= 128) blocks[0] = npad;
+    else { blocks[0] = ((npad / 2) + 15) & ~15; blocks[1] = npad - blocks[0]; nblk = 2; }
+    int n0 = 0;
+    for (int b = 0; b < nblk; ++b) {
+      const int rows = blocks[b];
+      for (int kc = 0; kc < nkc; ++kc) {
+        TcUnit u;
+        memset(&u, 0, sizeof(u));
+        u.w_off = (uint32_t)img.size();
+        u.rows = (uint16_t)rows;
+        u.dcol = (uint16_t)n0;
+        u.layer = (uint8_t)tl;
+        u.kchunk = (uint8_t)kc;
+        int kleft = K - kc * TC_KCH;
+        if (kleft > TC_KCH) kleft = TC_KCH;
+        u.ksteps = (uint8_t)((kleft + 7) / 8);
+        u.flags = (uint8_t)((kc == 0 ? 1 : 0) | ((b == nblk - 1 && kc == nkc - 1) ? 2 : 0));
+        units.push_back(u);
+        size_t o = img.size();
+        img.resize(o + (size_t)rows * 256, 0);
+        for (int n = 0; n < rows; ++n)
+          for (int k = 0; k < TC_KCH; ++k) {
+            int gn = n0 + n, gk = kc * TC_KCH + k;
+            double w = (gn < N && gk < K) ? wat(l, gn, gk) : 0.0;
+            float hi = tf32_trunc((float)w);
+            float lo = (float)(w - (double)hi);
+            uint32_t off = sw128_off((uint32_t)n, (uint32_t)k >> 2) + ((uint32_t)k & 3u) * 4u;
+            memcpy(&img[o + off], &hi, 4);
+            memcpy(&img[o + (size_t)rows * 128 + off], &lo, 4);
+          }
+      }
+      n0 += rows;
+    }
+  }
+  p.tl_unit_begin[p.n_tl] = (int)units.size();
+  p.n_units = (int)units.size();
+  if (p.n_units > TC_MAX_UNITS) {
+    snprintf(ctx->err, sizeof(ctx->err), "tensor-core MLP: too many weight units (%d)", p.n_units);
+    return C1D_ERR_ARG;
+  }
+  // first / last layers as row-major [out][in] doubles
+  std::vector<double> wf((size_t)p.first_out * p.n_in), wl((size_t)p.last_out * p.last_in);
+  for (int n = 0; n < p.first_out; ++n)
+    for (int k = 0; k < p.n_in; ++k) wf[(size_t)n * p.n_in + k] = wat(0, n, k);
+  for (int n = 0; n < p.last_out; ++n)
+    for (int k = 0; k < p.last_in; ++k) wl[(size_t)n * p.last_in + k] = wat(L - 1, n, k);
+#define UP(dst, src, bytes)                                                   \
+  do {                                                                        \
+    C1D_CUDA(ctx, cudaMalloc(&(dst), (bytes) ? (bytes) : 16));                \
+    C1D_CUDA(ctx, cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice)); \
+  } while (0)
+  UP(st->d_wimg, img.data(), img.size());
+  UP(st->d_units, units.data(), units.size() * sizeof(TcUnit));
+  UP(st->d_bias, bias.data(), bias.size() * sizeof(float));
+  UP(st->d_wfirst, wf.data(), wf.size() * sizeof(double));
+  UP(st->d_bfirst, &Bv[boff[0]], (size_t)p.first_out * sizeof(double));
+  UP(st->d_wlast, wl.data(), wl.size() * sizeof(double));
+  UP(st->d_blast, &Bv[boff[L - 1]], (size_t)p.last_out * sizeof(double));
+#undef UP
+  p.wimg = (const uint8_t*)st->d_wimg;
+  p.units = (const TcUnit*)st->d_units;
+  p.bias = (const float*)st->d_bias;
+  p.w_first = (const double*)st->d_wfirst;
+  p.b_first = (const double*)st->d_bfirst;
+  p.w_last = (const double*)st->d_wlast;
+  p.b_last = (const double*)st->d_blast;
+  p.emu_lo = ctx->d.emu_lo;
+  p.emu_hi = ctx->d.emu_hi;
+  C1D_CUDA(ctx, cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+  st->ready = true;
+  return C1D_OK;
+}
+
+int c1d_tc_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out, int out_stride, cudaStream_t s) {
+  TcState* st = (TcState*)ctx->tc_state;
+  if (!st || !st->ready) {
+    snprintf(ctx->err, sizeof(ctx->err),
+             "tensor-core emulator path unavailable (needs an NN emulator with >= 3 layers)");
+    return C1D_ERR_STATE;
+  }
+  int64_t ntiles = (nrows + TC_ROWS - 1) / TC_ROWS;
+  int grid = (int)(ntiles < ctx->num_sms ? ntiles : ctx->num_sms);
+  k_mlp_tc<<<grid, TC_THREADS, TC_SMEM, s>>>(st->p, emu_in, nrows, out, out_stride);
+  ctx->launches++;
+  C1D_CUDA(ctx, cudaPeekAtLastError());
+  return C1D_OK;
+}
+
+void c1d_tc_destroy(c1d_ctx* ctx) {
+  TcState* st = (TcState*)ctx->tc_state;
+  if (!st) return;
+  cudaFree(st->d_wimg); cudaFree(st->d_units); cudaFree(st->d_bias); cudaFree(st->d_wfirst);
+  cudaFree(st->d_bfirst); cudaFree(st->d_wlast); cudaFree(st->d_blast);
+  delete st;
+  ctx->tc_state = nullptr;
+}
+
+// D[128, N] = tf32(A[128, 32]) . tf32(B[N, 32])^T through one tcgen05.mma chain; host pointers.
+extern "C" int c1d_tc_selftest(int device, const float* A_host, const float* B_host, float* D_host, int N, int mode) {
+  if (!A_host || !B_host || !D_host || N < 16 || N > 256 || (N % 16) || (mode != 0 && mode != 1)) return C1D_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return C1D_ERR_CUDA;
+  float *dA = nullptr, *dB = nullptr, *dD = nullptr;
+  int rc = C1D_OK;
+  size_t smem = 1024 + TC_A_CHUNK_BYTES + 256 * 128 + 64;
+  if (cudaMalloc(&dA, 128 * 32 * 4) || cudaMalloc(&dB, (size_t)N * 32 * 4) || cudaMalloc(&dD, (size_t)128 * N * 4)) rc = C1D_ERR_CUDA;
+  if (!rc && (cudaMemcpy(dA, A_host, 128 * 32 * 4, cudaMemcpyHostToDevice) ||
+              cudaMemcpy(dB, B_host, (size_t)N * 32 * 4, cudaMemcpyHostToDevice)))
+    rc = C1D_ERR_CUDA;
+  if (!rc && cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) rc = C1D_ERR_CUDA;
+  if (!rc) {
+    k_tc_selftest<<<1, 160, smem>>>(dA, dB, dD, N, mode);
+    if (cudaDeviceSynchronize() != cudaSuccess) rc = C1D_ERR_CUDA;
+  }
+  if (!rc && cudaMemcpy(D_host, dD, (size_t)128 * N * 4, cudaMemcpyDeviceToHost)) rc = C1D_ERR_CUDA;
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  return rc;
+}

@@ -204,6 +204,10 @@ int64_t c1d_launch_count(const c1d_ctx* ctx);
 int c1d_set_timing(c1d_ctx* ctx, int enable);
 int c1d_get_timing(c1d_ctx* ctx, double* ms_out /* [8] */);
 
+/* diagnostic: D[128, N] = tf32(A[128, 32]) . tf32(B[N, 32])^T through one tcgen05.mma
+ * chain (host pointers); mode 0 = A from shared memory, 1 = A from tensor memory */
+int c1d_tc_selftest(int device, const float* A_host, const float* B_host, float* D_host, int N, int mode);
+
 int c1d_ctx_destroy(c1d_ctx* ctx);
 const char* c1d_last_error(const c1d_ctx* ctx);
 
