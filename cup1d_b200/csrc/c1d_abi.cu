@@ -159,6 +159,7 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
   }
   DevCtx& d = ctx->d;
   d.nz = c.nz; d.ndim = c.ndim; d.n_emu = c.n_emu; d.nd = c.nd; d.nf = c.nf;
+  d.ldd = (c.nd + 63) / 64 * 64;
   d.ell_width = c.ell_width; d.rebin_width = c.rebin_width; d.emu_kind = c.emu_kind; d.nc = c.nc;
   d.n_layers = c.n_layers;
   for (int l = 0; l <= C1D_MAX_LAYERS; ++l) d.layer_dims[l] = c.layer_dims[l];
@@ -184,6 +185,15 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
   DP(gp_ymean, C1D_F_GP_YMEAN); DP(gp_ystd, C1D_F_GP_YSTD); DP(gp_norm, C1D_F_GP_NORM); IP(zmask, C1D_F_ZMASK);
 #undef DP
 #undef IP
+  if (ctx->icov_pad) { cudaFree(ctx->icov_pad); ctx->icov_pad = nullptr; }
+  if (c.has_full) {
+    // zero-padded [ldd x ldd] copy for the tiled chi2 GEMM
+    const size_t ldd = d.ldd;
+    C1D_CUDA(ctx, cudaMalloc(&ctx->icov_pad, ldd * ldd * sizeof(double)));
+    C1D_CUDA(ctx, cudaMemset(ctx->icov_pad, 0, ldd * ldd * sizeof(double)));
+    C1D_CUDA(ctx, cudaMemcpy2D(ctx->icov_pad, ldd * sizeof(double), ctx->dev[C1D_F_ICOV_FULL], (size_t)c.nd * sizeof(double),
+                               (size_t)c.nd * sizeof(double), c.nd, cudaMemcpyDeviceToDevice));
+  }
   ctx->finalized = 1;
   if (c.emu_kind == 0) {
     int rc = c1d_tc_prepare(ctx);  // builds the tensor-core weight images (no-op when unsupported)
@@ -195,7 +205,7 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
 static void ws_free(c1d_ctx* ctx) {
   Workspace& w = ctx->ws;
   cudaFree(w.status); cudaFree(w.lnprior); cudaFree(w.blobs); cudaFree(w.emu_in); cudaFree(w.amp);
-  cudaFree(w.dvec); cudaFree(w.chi2z); cudaFree(w.chi2f); cudaFree(w.lnp); cudaFree(w.xdev); cudaFree(w.out7);
+  cudaFree(w.dvec); cudaFree(w.chi2z); cudaFree(w.chi2p); cudaFree(w.lnp); cudaFree(w.xdev); cudaFree(w.out7);
   memset(&w, 0, sizeof(w));
 }
 
@@ -211,9 +221,10 @@ static int ws_reserve(c1d_ctx* ctx, int64_t W) {
   C1D_CUDA(ctx, cudaMalloc(&w.blobs, cap * 6 * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.emu_in, (size_t)cap * c.nz * C1D_MAX_EMU * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.amp, (size_t)cap * c.nz * C1D_NAMP * sizeof(double)));
-  C1D_CUDA(ctx, cudaMalloc(&w.dvec, (size_t)cap * c.nd * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.dvec, (size_t)cap * ctx->d.ldd * sizeof(double)));
+  C1D_CUDA(ctx, cudaMemset(w.dvec, 0, (size_t)cap * ctx->d.ldd * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.chi2z, (size_t)cap * c.nz * sizeof(double)));
-  C1D_CUDA(ctx, cudaMalloc(&w.chi2f, cap * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.chi2p, (size_t)cap * ((ctx->d.ldd / 64 + 1) / 2) * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.lnp, cap * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.xdev, (size_t)cap * c.ndim * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.out7, (size_t)cap * 7 * sizeof(double)));
@@ -374,6 +385,7 @@ extern "C" int c1d_ctx_destroy(c1d_ctx* ctx) {
   cudaDeviceSynchronize();
   c1d_tc_destroy(ctx);
   ws_free(ctx);
+  if (ctx->icov_pad) cudaFree(ctx->icov_pad);
   for (int f = 0; f < C1D_F_COUNT; ++f)
     if (ctx->dev[f]) cudaFree(ctx->dev[f]);
   for (int i = 0; i < 9; ++i)

@@ -30,6 +30,7 @@ enum { ST_OK = 0, ST_OUT_OF_CUBE = 1, ST_REJECTED = 2 };
 
 struct DevCtx {
   int nz, ndim, n_emu, nd, nf, ell_width, rebin_width, emu_kind, nc, n_layers;
+  int ldd;  // row stride of the residual buffer = nd rounded up to a multiple of 64 (zero padded)
   int layer_dims[C1D_MAX_LAYERS + 1];
   int gp_ntrain, gp_nnorm, gp_imf;
   int metal_model, apply_resolution, has_full, has_gauss, n_hull_facets;
@@ -61,9 +62,9 @@ struct Workspace {
   double* blobs;   // [cap*6]
   double* emu_in;  // [nz*cap*C1D_MAX_EMU]
   double* amp;     // [nz*cap*C1D_NAMP]
-  double* dvec;    // [cap*nd]
+  double* dvec;    // [cap*ldd], pad columns stay zero
   double* chi2z;   // [cap*nz]
-  double* chi2f;   // [cap]
+  double* chi2p;   // [cap*npairs] partial dense chi2 per column-tile pair
   double* lnp;     // [cap]   (host-variant staging on the device)
   double* xdev;    // [cap*ndim]
   double* out7;    // [cap*7] packed (lnP, blob[6]) rows for the host variant
@@ -81,6 +82,7 @@ struct c1d_ctx {
   int timing;
   cudaEvent_t ev[9];
   double last_ms[8];
+  double* icov_pad;  // [ldd*ldd] zero-padded copy of the dense inverse covariance
   // tensor-core emulator path (c1d_mlp_tc.cu)
   void* tc_state;
   char err[512];

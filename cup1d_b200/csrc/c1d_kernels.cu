@@ -6,8 +6,8 @@
 //                k_gp_f64      GP posterior mean = batched kernel-vector product
 //   stage 3      k_fused_p1d   emulator polynomial -> contaminant templates -> rebin ->
 //                              residual, tables staged in shared memory per z
-//   stage 4      k_quadform    chi2 = d^T C^-1 d, register-tiled fp64 with the residual
-//                              tile in shared memory
+//   stage 4      k_chi2_dmma   chi2 = d^T C^-1 d: tiled fp64 tensor-core GEMM (DMMA), symmetric,
+//                              row-dot fused into the epilogue
 //   stage 5      k_finalize    regulate + prior, blobs conventions
 //
 // Reference lines are cited next to each formula.
@@ -416,7 +416,7 @@ k_fused_p1d(DevCtx c, int64_t W, int walkers_per_cta, const int* __restrict__ st
     if (!ok) {
       // rejected walkers carry no model (the reference returns None)
       for (int j = lane; j < ndz; j += 32) {
-        if (dvec) dvec[w * c.nd + d0 + j] = 0.0;
+        if (dvec) dvec[w * c.ldd + d0 + j] = 0.0;
         if (p_out) p_out[w * c.nd + d0 + j] = qnan;
       }
       if (chi2z && lane == 0) chi2z[w * c.nz + z] = 0.0;
@@ -478,7 +478,7 @@ k_fused_p1d(DevCtx c, int64_t W, int walkers_per_cta, const int* __restrict__ st
         m = fma(rbw[j * RW + t], pv, m);
       }
       const double dj = dat[j] - m;
-      if (dvec) dvec[w * c.nd + d0 + j] = dj;
+      if (dvec) dvec[w * c.ldd + d0 + j] = dj;
       if (p_out) p_out[w * c.nd + d0 + j] = m;
       dz[j] = dj;
     }
@@ -533,103 +533,149 @@ int c1d_launch_stage3(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int
 }
 
 // ---------------------------------------------------------------------------------------
-// stage 4: chi2 = d^T C^-1 d with the dense inverse covariance (likelihood.py:956-960) for
-// TW walkers per CTA.  The residual tile lives in shared memory as dT[i][w]; a thread owns
-// CW columns j of C^-1 and CW x TW accumulators.  (The per-z block chi2 is fused into
-// k_fused_p1d.)
+// stage 4: chi2 = d^T C^-1 d with the dense inverse covariance (likelihood.py:956-960) as a
+// tiled fp64 GEMM on the tensor cores (mma.sync m8n8k4 f64) with the row-dot fused into the
+// epilogue.  CTA tile = 128 walkers x 64 columns j; the K loop runs over rows i of C^-1 in
+// chunks of 16 staged with cp.async (double buffered).  C^-1 is symmetric: for column tile
+// jt only i < (jt+1)*64 is visited, the strictly-lower part counted twice; column tiles are
+// paired (jt, ntj-1-jt) so that every CTA does the same amount of work.  Both operands are
+// zero-padded to ndp = multiple of 64, so there is no edge handling.
 // ---------------------------------------------------------------------------------------
-template <int TW, int CW>
-__global__ void __launch_bounds__(256)
-k_quadform(DevCtx c, int64_t W, const double* __restrict__ dvec, double* __restrict__ out) {
-  extern __shared__ __align__(16) double sm[];
-  double* dT = sm;  // [nd][TW]
-  __shared__ double wsum[8][TW];
-  const int nd = c.nd;
-  const int64_t w0 = (int64_t)blockIdx.x * TW;
-  for (int t = threadIdx.x; t < nd * TW; t += blockDim.x) {
-    int w = t / nd, i = t % nd;  // coalesced global read along i
-    double v = (w0 + w < W) ? dvec[(w0 + w) * nd + i] : 0.0;
-    dT[i * TW + w] = v;
-  }
-  __syncthreads();
+#define Q_TW 128
+#define Q_TJ 64
+#define Q_KC 16
+#define Q_ASTR 20   // doubles per A row in shared memory (16 + 4: conflict-free fragment loads)
+#define Q_BSTR 68   // doubles per B row (64 + 4)
 
-  double part[TW];
-#pragma unroll
-  for (int w = 0; w < TW; ++w) part[w] = 0.0;
-  const int ncg = (nd + CW - 1) / CW;
-  const double* M = c.icov_full;
-  for (int cg = threadIdx.x; cg < ncg; cg += blockDim.x) {
-    const int j0 = cg * CW;
-    double acc[CW][TW];
-#pragma unroll
-    for (int cc = 0; cc < CW; ++cc)
-#pragma unroll
-      for (int w = 0; w < TW; ++w) acc[cc][w] = 0.0;
-#pragma unroll 2
-    for (int i = 0; i < nd; ++i) {
-      double mv[CW];
-#pragma unroll
-      for (int cc = 0; cc < CW; ++cc)
-        mv[cc] = (j0 + cc < nd) ? __ldg(M + (size_t)i * nd + j0 + cc) : 0.0;
-      const double2* dp = reinterpret_cast<const double2*>(dT + i * TW);
-      double dv[TW];
-#pragma unroll
-      for (int w = 0; w < TW / 2; ++w) {
-        double2 t = dp[w];
-        dv[2 * w] = t.x;
-        dv[2 * w + 1] = t.y;
-      }
-#pragma unroll
-      for (int cc = 0; cc < CW; ++cc)
-#pragma unroll
-        for (int w = 0; w < TW; ++w) acc[cc][w] = fma(mv[cc], dv[w], acc[cc][w]);
-    }
-#pragma unroll
-    for (int cc = 0; cc < CW; ++cc)
-      if (j0 + cc < nd)
-#pragma unroll
-        for (int w = 0; w < TW; ++w) part[w] = fma(acc[cc][w], dT[(j0 + cc) * TW + w], part[w]);
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int w = 0; w < TW; ++w) {
-    double v = part[w];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0) wsum[warp][w] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < TW && w0 + threadIdx.x < W) {
-    double v = 0.0;
-    for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) v += wsum[ww][threadIdx.x];
-    out[w0 + threadIdx.x] = v;
-  }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
 }
 
-template <int TW>
-static int launch_quadform_tw(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
-  const int nd = ctx->cfg.nd;
-  size_t smem = (size_t)nd * TW * sizeof(double);
-  unsigned grid = (unsigned)((W + TW - 1) / TW);
-  auto kern = k_quadform<TW, 4>;
-  C1D_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int ncg = (nd + 3) / 4;
-  int threads = ((ncg + 31) / 32) * 32;
-  if (threads > 256) threads = 256;
-  if (threads < 64) threads = 64;
-  kern<<<grid, threads, smem, s>>>(ctx->d, W, ctx->ws.dvec, ctx->ws.chi2f);
-  ctx->launches++;
-  C1D_CUDA(ctx, cudaPeekAtLastError());
-  return C1D_OK;
+__global__ void __launch_bounds__(256)
+k_chi2_dmma(int64_t W, int ndp, const double* __restrict__ dvec, const double* __restrict__ Cp,
+            double* __restrict__ partial, int npairs) {
+  extern __shared__ __align__(16) double qsm[];
+  double (*As)[Q_TW][Q_ASTR] = reinterpret_cast<double (*)[Q_TW][Q_ASTR]>(qsm);
+  double (*Bs)[Q_KC][Q_BSTR] = reinterpret_cast<double (*)[Q_KC][Q_BSTR]>(qsm + 2 * Q_TW * Q_ASTR);
+  double (*red)[Q_TW] = reinterpret_cast<double (*)[Q_TW]>(qsm + 2 * Q_TW * Q_ASTR + 2 * Q_KC * Q_BSTR);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int64_t w0 = (int64_t)blockIdx.x * Q_TW;
+  const int ntj = ndp / Q_TJ;
+  const int pair = blockIdx.y;
+  double tot = 0.0;  // thread r < 128 owns walker w0 + r
+
+  for (int half = 0; half < 2; ++half) {
+    const int jt = half == 0 ? pair : ntj - 1 - pair;
+    if (half == 1 && jt == pair) break;  // the middle tile pairs with itself
+    const int j0 = jt * Q_TJ;
+    const int nk = (jt + 1) * (Q_TJ / Q_KC);
+    const int kdiag = jt * (Q_TJ / Q_KC);
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    auto load_chunk = [&](int kc, int buf) {
+      const int i0 = kc * Q_KC;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {  // A: 128 rows x 8 pieces of 16 B
+        int piece = tid + t * 256;
+        int r = piece >> 3, cc = piece & 7;
+        int64_t wr = w0 + r;
+        if (wr >= W) wr = W - 1;
+        cp_async16(&As[buf][r][cc * 2], dvec + wr * ndp + i0 + cc * 2);
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {  // B: 16 rows x 32 pieces
+        int piece = tid + t * 256;
+        int r = piece >> 5, cc = piece & 31;
+        cp_async16(&Bs[buf][r][cc * 2], Cp + (size_t)(i0 + r) * ndp + j0 + cc * 2);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    load_chunk(0, 0);
+    for (int kc = 0; kc < nk; ++kc) {
+      const int buf = kc & 1;
+      if (kc + 1 < nk) {
+        load_chunk(kc + 1, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      if (kc == kdiag) {
+        // everything accumulated so far is strictly below the diagonal block: count it twice
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) { acc[a][b][0] *= 2.0; acc[a][b][1] *= 2.0; }
+      }
+#pragma unroll
+      for (int ks = 0; ks < Q_KC / 4; ++ks) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) af[a] = As[buf][32 * wm + 8 * a + (lane >> 2)][4 * ks + (lane & 3)];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf[b] = Bs[buf][4 * ks + (lane & 3)][32 * wn + 8 * b + (lane >> 2)];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+      }
+      __syncthreads();
+    }
+    // epilogue: sum_j Q[w][j] d[w][j] over this column tile
+    double ps[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int64_t wr = w0 + 32 * wm + 8 * a + (lane >> 2);
+      if (wr >= W) wr = W - 1;
+      double sum = 0.0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double2 dv = *reinterpret_cast<const double2*>(dvec + wr * ndp + j0 + 32 * wn + 8 * b + 2 * (lane & 3));
+        sum = fma(acc[a][b][0], dv.x, sum);
+        sum = fma(acc[a][b][1], dv.y, sum);
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      ps[a] = sum;
+    }
+    if ((lane & 3) == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) red[wn][32 * wm + 8 * a + (lane >> 2)] = ps[a];
+    }
+    __syncthreads();
+    if (tid < Q_TW) tot += red[0][tid] + red[1][tid];
+    __syncthreads();
+  }
+  if (tid < Q_TW && w0 + tid < W) partial[(w0 + tid) * npairs + pair] = tot;
 }
 
 int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
-  const int nd = ctx->cfg.nd;
-  if ((size_t)nd * 16 * 8 <= 200 * 1024) return launch_quadform_tw<16>(ctx, W, s);
-  if ((size_t)nd * 8 * 8 <= 200 * 1024) return launch_quadform_tw<8>(ctx, W, s);
-  if ((size_t)nd * 4 * 8 <= 200 * 1024) return launch_quadform_tw<4>(ctx, W, s);
-  snprintf(ctx->err, sizeof(ctx->err), "data vector too long for the chi2 kernel (nd=%d)", nd);
-  return C1D_ERR_ARG;
+  const int ndp = ctx->d.ldd;
+  const int ntj = ndp / Q_TJ;
+  const int npairs = (ntj + 1) / 2;
+  dim3 grid((unsigned)((W + Q_TW - 1) / Q_TW), (unsigned)npairs);
+  const size_t smem = (size_t)(2 * Q_TW * Q_ASTR + 2 * Q_KC * Q_BSTR + 2 * Q_TW) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    C1D_CUDA(ctx, cudaFuncSetAttribute(k_chi2_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  k_chi2_dmma<<<grid, 256, smem, s>>>(W, ndp, ctx->ws.dvec, ctx->icov_pad, ctx->ws.chi2p, npairs);
+  ctx->launches++;
+  C1D_CUDA(ctx, cudaPeekAtLastError());
+  return C1D_OK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -637,7 +683,7 @@ int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_finalize(DevCtx c, int64_t W, const int* __restrict__ status, const double* __restrict__ lnprior,
-           const double* __restrict__ chi2z, const double* __restrict__ chi2f, int use_full,
+           const double* __restrict__ chi2z, const double* __restrict__ chi2p, int npairs, int use_full,
            double* __restrict__ lnp, double* __restrict__ lnl_z, double* __restrict__ blobs,
            double* __restrict__ chi2_out, uint32_t flags) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -647,7 +693,9 @@ k_finalize(DevCtx c, int64_t W, const int* __restrict__ status, const double* __
   double loglike = ninf;
   if (st == ST_OK) {
     if (use_full) {
-      loglike = -0.5 * chi2f[w];
+      double chi2 = 0.0;  // fixed summation order over the column-tile pairs
+      for (int p = 0; p < npairs; ++p) chi2 += chi2p[w * npairs + p];
+      loglike = -0.5 * chi2;
     } else {
       double sum = 0.0;
       for (int z = 0; z < c.nz; ++z) {
@@ -686,8 +734,9 @@ int c1d_launch_finalize(c1d_ctx* ctx, int64_t W, double* lnp, double* lnl_z, dou
   int use_full = ctx->cfg.has_full && !(flags & C1D_FLAG_ZMASK);
   int threads = 256;
   unsigned grid = (unsigned)((W + threads - 1) / threads);
+  const int npairs = (ctx->d.ldd / Q_TJ + 1) / 2;
   k_finalize<<<grid, threads, 0, s>>>(ctx->d, W, ctx->ws.status, ctx->ws.lnprior, ctx->ws.chi2z,
-                                      ctx->ws.chi2f, use_full, lnp, lnl_z, blobs, chi2, flags);
+                                      ctx->ws.chi2p, npairs, use_full, lnp, lnl_z, blobs, chi2, flags);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return C1D_OK;
