@@ -316,7 +316,19 @@ def compile_spec(spec):
     else:
         fields["ICOV_FULL"] = np.zeros(0)
 
+    # evenly spaced model grids allow exp(-s k) by recurrence on the device
+    uniform = True
+    for k in kgrid:
+        k = np.asarray(k, dtype=float)
+        if len(k) < 3:
+            uniform = False
+            break
+        lin = k[0] + np.arange(len(k)) * ((k[-1] - k[0]) / (len(k) - 1))
+        if np.max(np.abs(k - lin)) > 1e-13 * np.abs(k[-1]):
+            uniform = False
+            break
     cfg = {
+        "uniform_k": int(uniform),
         "nz": nz, "ndim": ndim, "n_emu": n_emu, "nd": nd, "nf": nf,
         "ell_width": int(ell), "rebin_width": int(rwidth),
         "n_layers": 0, "layer_dims": [0] * (MAX_LAYERS + 1),

@@ -33,7 +33,7 @@ struct DevCtx {
   int ldd;  // row stride of the residual buffer = nd rounded up to a multiple of 64 (zero padded)
   int layer_dims[C1D_MAX_LAYERS + 1];
   int gp_ntrain, gp_nnorm, gp_imf;
-  int metal_model, apply_resolution, has_full, has_gauss, n_hull_facets;
+  int metal_model, apply_resolution, has_full, has_gauss, n_hull_facets, uniform_k;
   int idx_As, idx_ns, idx_nrun;
   int emu_code[C1D_MAX_EMU];
   double As_fid, ns_fid, nrun_fid, L_emu, L_star;
@@ -78,6 +78,7 @@ struct c1d_ctx {
   Workspace ws;
   int finalized;
   int num_sms;
+  int nfz_max, ndz_max;  // largest z-bin of the model grid / data vector
   int64_t launches;
   int timing;
   cudaEvent_t ev[9];

@@ -2,7 +2,7 @@
 //
 //   stage 0/1/5  k_stage1      cube -> parameters -> per-z emulator inputs, contaminant
 //                              amplitudes, blobs, Gaussian prior, star box, hull
-//   stage 2      k_mlp_f64     LaCE-style MLP on fp64 CUDA cores (exact-parity mode)
+//   stage 2      k_mlp_f64     LaCE-style MLP on the fp64 tensor cores (DMMA, exact-parity mode)
 //                k_gp_f64      GP posterior mean = batched kernel-vector product
 //   stage 3      k_fused_p1d   emulator polynomial -> contaminant templates -> rebin ->
 //                              residual, tables staged in shared memory per z
@@ -168,57 +168,70 @@ int c1d_launch_stage1(c1d_ctx* ctx, const double* x, int64_t W, double* blobs_ou
 }
 
 // ---------------------------------------------------------------------------------------
-// stage 2a: MLP on fp64 CUDA cores.  One CTA owns a tile of 64 rows ((walker, z) pairs) and
-// chains all layers with the activations resident in shared memory (k-major, 64 rows
-// contiguous).  Warp w owns rows 8w..8w+7, lane l owns CW consecutive output columns.
+// stage 2a: the MLP in fp64 (exact-parity mode) on the fp64 tensor cores (mma.sync m8n8k4).
+// One CTA owns a tile of 64 rows ((walker, z) pairs) and chains all layers with the
+// activations resident in shared memory (k-major, padded row stride).  Warp (wm, wn) owns
+// rows 32 wm .. +31 and a slab of 8*NB output columns; weights stream through L1/L2.
 // ---------------------------------------------------------------------------------------
 #define MLP_ROWS 64
 #define MLP_MAXW 256
 #define MLP_THREADS 256
+#define MLP_STR 68  // doubles per k-row of the activation tile (64 + 4: conflict-free fragments)
 
-template <int CW>
+__device__ __forceinline__ void dmma8(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int NB>
 __device__ __forceinline__ void mlp_layer(const double* __restrict__ Wt, const double* __restrict__ b,
                                           int K, int N, double* act, double slope, bool activate) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n0 = lane * CW, r0 = warp * 8;
-  double acc[8][CW];
+  const int wm = warp & 1, wn = warp >> 1;
+  const int n0 = wn * (8 * NB), r0 = 32 * wm;
+  const int kq = lane & 3, g = lane >> 2;
+  double acc[4][NB][2];
 #pragma unroll
-  for (int c = 0; c < CW; ++c) {
-    double bv = (n0 + c < N) ? b[n0 + c] : 0.0;
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i][c] = bv;
-  }
+    for (int nb = 0; nb < NB; ++nb) acc[a][nb][0] = acc[a][nb][1] = 0.0;
   if (n0 < N) {
 #pragma unroll 2
-    for (int k = 0; k < K; ++k) {
-      double wv[CW];
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      const int k = k0 + kq;
+      const bool kin = k < K;
+      double af[4], bf[NB];
 #pragma unroll
-      for (int c = 0; c < CW; ++c) wv[c] = (n0 + c < N) ? __ldg(Wt + (size_t)k * N + n0 + c) : 0.0;
-      const double2* ap = reinterpret_cast<const double2*>(act + k * MLP_ROWS + r0);
-      double a[8];
+      for (int a = 0; a < 4; ++a) af[a] = kin ? act[k * MLP_STR + r0 + 8 * a + g] : 0.0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        double2 t = ap[i];
-        a[2 * i] = t.x;
-        a[2 * i + 1] = t.y;
+      for (int nb = 0; nb < NB; ++nb) {
+        const int n = n0 + 8 * nb + g;
+        bf[nb] = (kin && n < N) ? __ldg(Wt + (size_t)k * N + n) : 0.0;
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int c = 0; c < CW; ++c) acc[i][c] = fma(a[i], wv[c], acc[i][c]);
+        for (int nb = 0; nb < NB; ++nb) dmma8(acc[a][nb][0], acc[a][nb][1], af[a], bf[nb]);
     }
   }
   __syncthreads();  // every read of the input activations is done
+  if (n0 < N) {
 #pragma unroll
-  for (int c = 0; c < CW; ++c) {
-    if (n0 + c < N) {
+    for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        double v = acc[i][c];
-        if (activate) v = (v > 0.0) ? v : slope * v;  // LeakyReLU(slope)
-        act[(n0 + c) * MLP_ROWS + r0 + i] = v;
+      for (int e = 0; e < 2; ++e) {
+        const int n = n0 + 8 * nb + 2 * kq + e;
+        if (n < N) {
+          const double bv = b[n];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            double v = acc[a][nb][e] + bv;
+            if (activate) v = (v > 0.0) ? v : slope * v;  // LeakyReLU(slope)
+            act[n * MLP_STR + r0 + 8 * a + g] = v;
+          }
+        }
       }
-    }
   }
   __syncthreads();
 }
@@ -226,7 +239,7 @@ __device__ __forceinline__ void mlp_layer(const double* __restrict__ Wt, const d
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 k_mlp_f64(DevCtx c, const double* __restrict__ emu_in, int64_t nrows, double* __restrict__ out,
           int out_stride) {
-  extern __shared__ __align__(16) double act[];  // [MLP_MAXW][MLP_ROWS]
+  extern __shared__ __align__(16) double act[];  // [MLP_MAXW][MLP_STR]
   const int64_t ntiles = (nrows + MLP_ROWS - 1) / MLP_ROWS;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * MLP_ROWS;
@@ -239,7 +252,7 @@ k_mlp_f64(DevCtx c, const double* __restrict__ emu_in, int64_t nrows, double* __
         double xv = emu_in[row * C1D_MAX_EMU + j];
         v = (xv - c.emu_lo[j]) / (c.emu_hi[j] - c.emu_lo[j]) - 0.5;
       }
-      act[j * MLP_ROWS + r] = v;
+      act[j * MLP_STR + r] = v;
     }
     __syncthreads();
     size_t woff = 0, boff = 0;
@@ -248,8 +261,8 @@ k_mlp_f64(DevCtx c, const double* __restrict__ emu_in, int64_t nrows, double* __
       const bool activate = l < c.n_layers - 1;
       const double* Wt = c.nn_w + woff;
       const double* b = c.nn_b + boff;
-      const int cw = (N + 31) / 32;
-      switch (cw) {
+      const int nb = (N + 31) / 32;  // 8-column blocks per warp slab (4 slabs)
+      switch (nb) {
         case 1: mlp_layer<1>(Wt, b, K, N, act, c.nn_slope, activate); break;
         case 2: mlp_layer<2>(Wt, b, K, N, act, c.nn_slope, activate); break;
         case 3: mlp_layer<3>(Wt, b, K, N, act, c.nn_slope, activate); break;
@@ -266,7 +279,7 @@ k_mlp_f64(DevCtx c, const double* __restrict__ emu_in, int64_t nrows, double* __
     for (int t = threadIdx.x; t < MLP_ROWS * c.nc; t += blockDim.x) {
       int r = t / c.nc, j = t % c.nc;
       int64_t row = row0 + r;
-      if (row < nrows) out[row * out_stride + j] = act[j * MLP_ROWS + r];
+      if (row < nrows) out[row * out_stride + j] = act[j * MLP_STR + r];
     }
     __syncthreads();
   }
@@ -328,7 +341,7 @@ int c1d_launch_emulator(c1d_ctx* ctx, const double* emu_in, int64_t nrows, doubl
   if (nrows <= 0) return C1D_OK;
   if (ctx->cfg.emu_kind == 0) {
     if (flags & C1D_FLAG_EMU_TC) return c1d_tc_launch(ctx, emu_in, nrows, out, out_stride, s);
-    size_t smem = (size_t)MLP_MAXW * MLP_ROWS * sizeof(double);
+    size_t smem = (size_t)MLP_MAXW * MLP_STR * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
       C1D_CUDA(ctx, cudaFuncSetAttribute(k_mlp_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -437,8 +450,29 @@ k_fused_p1d(DevCtx c, int64_t W, int walkers_per_cta, const int* __restrict__ st
     const double aa = __shfl_sync(0xffffffffu, av, A_AA), sa2 = __shfl_sync(0xffffffffu, av, A_SA2);
     const double res = __shfl_sync(0xffffffffu, av, A_RES);
 
+    // exp(-s k) and exp(-s^2 k^2) on an evenly spaced grid advance by constant ratios:
+    // one exp per term and lane instead of one per point
+    const bool uni = c.uniform_k && nfz >= 2;
+    const double sg3 = (c.metal_model == 0) ? -s3 : s3;  // SiVid grows with k (si_vid_final.py:208)
+    double E3 = 0.0, R3 = 0.0, E2 = 0.0, R2 = 0.0, gg = 0.0, grho = 0.0, gq = 0.0;
+    if (uni) {
+      const double dk32 = 32.0 * ((tk[nfz - 1] - tk[0]) / (double)(nfz - 1));
+      const double kl = tk[lane < nfz ? lane : 0];
+      E3 = exp(sg3 * kl);
+      R3 = exp(sg3 * dk32);
+      E2 = exp(-s2 * kl);
+      R2 = exp(-s2 * dk32);
+      gg = exp(-1.0 * sa2 * (kl * kl));
+      grho = exp(-1.0 * sa2 * (2.0 * kl * dk32 + dk32 * dk32));
+      gq = exp(-2.0 * sa2 * (dk32 * dk32));
+    }
     for (int i = lane; i < nfz; i += 32) {
       const double k = tk[i];
+      if (!uni) {
+        E3 = exp(sg3 * k);
+        E2 = exp(-s2 * k);
+        gg = exp(-1.0 * sa2 * (k * k));
+      }
       // emulator polynomial (Horner) -> P_emu in km/s (lya_theory.py:690-701)
       double pl = 0.0;
       const double tt = tT[i];
@@ -448,24 +482,30 @@ k_fused_p1d(DevCtx c, int64_t W, int walkers_per_cta, const int* __restrict__ st
       const double p_emu = tS[i] * (c.emu_kind == 0 ? exp10(pl) : exp(pl));
       double mult;
       if (c.metal_model == 0) {
-        // si_mult.py:212-218, 267-341
-        const double G3 = 2.0 - 2.0 / (1.0 + exp(-s3 * k));
-        const double G2 = 2.0 - 2.0 / (1.0 + exp(-s2 * k));
+        // si_mult.py:212-218, 267-341; 2/(1+E) = 2 * rn(1/(1+E)) exactly
+        const double G3 = fma(-2.0, __drcp_rn(1.0 + E3), 2.0);
+        const double G2 = fma(-2.0, __drcp_rn(1.0 + E2), 2.0);
         mult = m0 + (c1 * G3 * t1[i] + G2 * (c2a * t2a[i] + c2b * t2bc[i])) +
                (c3a * t3a[i] + c3b * t3bc[i]);
       } else {
         // si_vid_final.py:205-219
-        mult = 1.0 + c1 * exp(s3 * k) + c2a * t1[i] * exp(-s2 * k);
+        mult = 1.0 + c1 * E3 + c2a * t1[i] * E2;
       }
       // hcd_model_rogers_class.py:115-135 (or hcd_boss.py:5-7 through D1)
       const double hcd = h0 + hA * tD[i] + hB * tD[nfz_max + i] + hC * tD[2 * nfz_max + i] +
                          hD * tD[3 * nfz_max + i];
       // si_add.py:168-219
-      const double add = aa * tKT[i] * exp(-1.0 * sa2 * (k * k));
+      const double add = aa * tKT[i] * gg;
       // resolution_class.py:99-108
       const double syst = 1.0 + res * tQ[i];
       // lya_theory.py:778-784 (IC correction is folded into the S column)
       pb[i] = (hcd * mult * p_emu + add) * syst;
+      if (uni) {
+        E3 *= R3;
+        E2 *= R2;
+        gg *= grho;
+        grho *= gq;
+      }
     }
     __syncwarp();
     // rebinning (likelihood.py:147-161) and residual (likelihood.py:939, 957)
@@ -503,8 +543,7 @@ k_fused_p1d(DevCtx c, int64_t W, int walkers_per_cta, const int* __restrict__ st
 int c1d_launch_stage3(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int want_chi2z,
                       cudaStream_t s) {
   const c1d_config& cfg = ctx->cfg;
-  // largest z-bin sizes were stored in reserved_i by finalize
-  int nfz_max = cfg.reserved_i[0], ndz_max = cfg.reserved_i[1];
+  int nfz_max = ctx->nfz_max, ndz_max = ctx->ndz_max;
   size_t smem = ((size_t)C1D_NCOL * nfz_max + (size_t)P1D_WARPS * nfz_max +
                  (size_t)ndz_max * cfg.rebin_width + ndz_max + (size_t)P1D_WARPS * ndz_max) * sizeof(double) +
                 (size_t)ndz_max * sizeof(int) + 16;

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define C1D_ABI_VERSION 3
+#define C1D_ABI_VERSION 4
 #define C1D_MAX_LAYERS 12
 #define C1D_MAX_EMU 8     /* emulator inputs */
 #define C1D_MAX_COEF 8    /* polynomial coefficients the emulator returns */
@@ -131,7 +131,8 @@ typedef struct c1d_config {
   int32_t idx_As, idx_ns, idx_nrun; /* parameter indices or -1 */
   int32_t emu_code[C1D_MAX_EMU]; /* 0 Delta2_p 1 n_p 2 alpha_p 3 mF 4 sigT_Mpc 5 gamma 6 kF_Mpc 7 lambda_P */
   int32_t device;             /* CUDA device ordinal */
-  int32_t reserved_i[7];
+  int32_t uniform_k;          /* 1 = the model k grid of every z is evenly spaced (linspace, likelihood.py:90-94) */
+  int32_t reserved_i[6];
   double As_fid, ns_fid, nrun_fid;
   double L_emu;               /* ln(kp_emu / ks)   lya_theory.py:299 */
   double L_star;              /* ln(kp_star / ks)  lya_theory.py:565 */
