@@ -368,175 +368,230 @@ int c1d_launch_emulator(c1d_ctx* ctx, const double* emu_in, int64_t nrows, doubl
 // A CTA is bound to one redshift bin: it stages the walker-independent k tables of that z
 // in shared memory once and streams a tile of walkers through them, one walker per warp.
 // ---------------------------------------------------------------------------------------
-#define P1D_THREADS 256
+#define P1D_THREADS 512
 #define P1D_WARPS (P1D_THREADS / 32)
+#define P1D_CHUNK 32   // walkers per work item
+#define P1D_NPAIR (C1D_NCOL / 2)
 
-__global__ void __launch_bounds__(P1D_THREADS)
-k_fused_p1d(DevCtx c, int64_t W, int walkers_per_cta, const int* __restrict__ status,
-            const double* __restrict__ amp, double* __restrict__ dvec, double* __restrict__ p_out,
-            double* __restrict__ chi2z, int nfz_max, int ndz_max) {
+// 10^x for the emulator polynomial: 2^(x log2 10) with a two-term constant and a degree-12
+// polynomial for 2^r on |r| <= 1/2 (relative error ~2e-16); outside the safe exponent range
+// the library function is used.
+__device__ __forceinline__ double exp10_poly(double x) {
+  if (!(fabs(x) < 280.0)) return exp10(x);
+  const double L2_10_HI = 3.321928094887362, L2_10_LO = 1.661617516973592e-16;
+  const int ni = __double2int_rn(x * L2_10_HI);
+  const double n = (double)ni;
+  double r = fma(x, L2_10_HI, -n);
+  r = fma(x, L2_10_LO, r);
+  double p = 1.3691488853904124e-12;  // ln2^k / k!, k = 13 .. 0
+  p = fma(p, r, 2.5678435993488196e-11);
+  p = fma(p, r, 4.44553827187081e-10);
+  p = fma(p, r, 7.054911620801121e-09);
+  p = fma(p, r, 1.0178086009239696e-07);
+  p = fma(p, r, 1.3215486790144305e-06);
+  p = fma(p, r, 1.5252733804059838e-05);
+  p = fma(p, r, 0.00015403530393381606);
+  p = fma(p, r, 0.0013333558146428441);
+  p = fma(p, r, 0.009618129107628477);
+  p = fma(p, r, 0.055504108664821576);
+  p = fma(p, r, 0.2402265069591007);
+  p = fma(p, r, 0.6931471805599453);
+  p = fma(p, r, 1.0);
+  return p * __longlong_as_double((long long)(ni + 1023) << 52);
+}
+
+// reciprocal to ~1 ulp: hardware seed + two Newton steps
+__device__ __forceinline__ double rcp_fast(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+// A persistent CTA streams work items (z, chunk of 32 walkers) that are contiguous in a
+// z-major order and balanced by cost (fine points per z), so the grid is exactly one wave.
+__global__ void __launch_bounds__(P1D_THREADS, 1)
+k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* __restrict__ amp,
+            double* __restrict__ dvec, double* __restrict__ p_out, double* __restrict__ chi2z,
+            int nfz_max, int ndz_max) {
   extern __shared__ __align__(16) double sm[];
-  const int z = blockIdx.y;
-  const int f0 = c.zoff_f[z], nfz = c.zoff_f[z + 1] - f0;
-  const int d0 = c.zoff_d[z], ndz = c.zoff_d[z + 1] - d0;
-  const int RW = c.rebin_width;
-  double* tab = sm;                                   // [NCOL][nfz_max]
-  double* pbuf = tab + (size_t)C1D_NCOL * nfz_max;    // [P1D_WARPS][nfz_max]
-  double* rbw = pbuf + (size_t)P1D_WARPS * nfz_max;   // [ndz_max][RW]
-  double* dat = rbw + (size_t)ndz_max * RW;           // [ndz_max]
-  double* dzb = dat + ndz_max;                        // [P1D_WARPS][ndz_max]
+  const int RW = c.rebin_width, RWP = RW | 1;        // odd row stride: conflict-free
+  const int pb_len = nfz_max + (nfz_max >> 3) + 2;   // P(i) lives at i + i/8
+  double2* tab2 = reinterpret_cast<double2*>(sm);    // [P1D_NPAIR][nfz_max] column pairs
+  double* pbuf = sm + (size_t)2 * P1D_NPAIR * nfz_max;   // [P1D_WARPS][pb_len]
+  double* rbw = pbuf + (size_t)P1D_WARPS * pb_len;   // [ndz_max][RWP]
+  double* dat = rbw + (size_t)ndz_max * RWP;         // [ndz_max]
+  double* dzb = dat + ndz_max;                       // [P1D_WARPS][ndz_max]
   int* rbs = reinterpret_cast<int*>(dzb + (size_t)P1D_WARPS * ndz_max);  // [ndz_max]
 
-  for (int t = threadIdx.x; t < C1D_NCOL * nfz; t += blockDim.x) {
-    int col = t / nfz, i = t % nfz;
-    tab[col * nfz_max + i] = c.tab[(size_t)col * c.nf + f0 + i];
-  }
-  for (int t = threadIdx.x; t < ndz * RW; t += blockDim.x) rbw[t] = c.rb_wgt[(size_t)d0 * RW + t];
-  for (int t = threadIdx.x; t < ndz; t += blockDim.x) {
-    dat[t] = c.data[d0 + t];
-    rbs[t] = c.rb_start[d0 + t];
-  }
-  __syncthreads();
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* pb = pbuf + (size_t)warp * nfz_max;
-  const double* tk = tab + C1D_COL_K * nfz_max;
-  const double* tS = tab + C1D_COL_S * nfz_max;
-  const double* tT = tab + C1D_COL_T * nfz_max;
-  const double* t1 = tab + C1D_COL_T1 * nfz_max;
-  const double* t2a = tab + C1D_COL_T2A * nfz_max;
-  const double* t2bc = tab + C1D_COL_T2BC * nfz_max;
-  const double* t3a = tab + C1D_COL_T3A * nfz_max;
-  const double* t3bc = tab + C1D_COL_T3BC * nfz_max;
-  const double* tD = tab + C1D_COL_D1 * nfz_max;
-  const double* tKT = tab + C1D_COL_KT * nfz_max;
-  const double* tQ = tab + C1D_COL_Q * nfz_max;
-  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-  // per-z inverse covariance block of this z (likelihood.py:939-940), read through L1/L2
-  size_t icov_base = 0;
-  for (int zz = 0; zz < z; ++zz) {
-    size_t n = c.zoff_d[zz + 1] - c.zoff_d[zz];
-    icov_base += n * n;
-  }
-  const double* icz = c.icov_blocks + icov_base;
+  double* pb = pbuf + (size_t)warp * pb_len;
   double* dz = dzb + (size_t)warp * ndz_max;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-  const int64_t w_begin = (int64_t)blockIdx.x * walkers_per_cta;
-  int64_t w_end = w_begin + walkers_per_cta;
-  if (w_end > W) w_end = W;
-  for (int64_t w = w_begin + warp; w < w_end; w += P1D_WARPS) {
-    const bool ok = status[w] == ST_OK;
-    if (!ok) {
-      // rejected walkers carry no model (the reference returns None)
-      for (int j = lane; j < ndz; j += 32) {
-        if (dvec) dvec[w * c.ldd + d0 + j] = 0.0;
-        if (p_out) p_out[w * c.nd + d0 + j] = qnan;
-      }
-      if (chi2z && lane == 0) chi2z[w * c.nz + z] = 0.0;
-      continue;
-    }
-    const double* a = amp + ((int64_t)z * W + w) * C1D_NAMP;
-    double av = (lane < C1D_NAMP) ? a[lane] : 0.0;
-    double cf[C1D_MAX_COEF];
-#pragma unroll
-    for (int j = 0; j < C1D_MAX_COEF; ++j) cf[j] = __shfl_sync(0xffffffffu, av, A_COEF0 + j);
-    const double s3 = __shfl_sync(0xffffffffu, av, A_S3), s2 = __shfl_sync(0xffffffffu, av, A_S2);
-    const double m0 = __shfl_sync(0xffffffffu, av, A_M0), c1 = __shfl_sync(0xffffffffu, av, A_C1);
-    const double c2a = __shfl_sync(0xffffffffu, av, A_C2A), c2b = __shfl_sync(0xffffffffu, av, A_C2B);
-    const double c3a = __shfl_sync(0xffffffffu, av, A_C3A), c3b = __shfl_sync(0xffffffffu, av, A_C3B);
-    const double h0 = __shfl_sync(0xffffffffu, av, A_H0);
-    const double hA = __shfl_sync(0xffffffffu, av, A_HCD1 + 0), hB = __shfl_sync(0xffffffffu, av, A_HCD1 + 1);
-    const double hC = __shfl_sync(0xffffffffu, av, A_HCD1 + 2), hD = __shfl_sync(0xffffffffu, av, A_HCD1 + 3);
-    const double aa = __shfl_sync(0xffffffffu, av, A_AA), sa2 = __shfl_sync(0xffffffffu, av, A_SA2);
-    const double res = __shfl_sync(0xffffffffu, av, A_RES);
+  // cost-balanced contiguous range of this CTA: [t0, t1) in units of (fine points + 2 data bins)
+  const int64_t nchunks = (W + P1D_CHUNK - 1) / P1D_CHUNK;
+  int64_t total = 0;
+  for (int z = 0; z < c.nz; ++z)
+    total += nchunks * (int64_t)((c.zoff_f[z + 1] - c.zoff_f[z]) + 2 * (c.zoff_d[z + 1] - c.zoff_d[z]));
+  const int64_t t0 = total * blockIdx.x / gridDim.x, t1 = total * (blockIdx.x + 1) / gridDim.x;
 
-    // exp(-s k) and exp(-s^2 k^2) on an evenly spaced grid advance by constant ratios:
-    // one exp per term and lane instead of one per point
-    const bool uni = c.uniform_k && nfz >= 2;
-    const double sg3 = (c.metal_model == 0) ? -s3 : s3;  // SiVid grows with k (si_vid_final.py:208)
-    double E3 = 0.0, R3 = 0.0, E2 = 0.0, R2 = 0.0, gg = 0.0, grho = 0.0, gq = 0.0;
-    if (uni) {
-      const double dk32 = 32.0 * ((tk[nfz - 1] - tk[0]) / (double)(nfz - 1));
-      const double kl = tk[lane < nfz ? lane : 0];
-      E3 = exp(sg3 * kl);
-      R3 = exp(sg3 * dk32);
-      E2 = exp(-s2 * kl);
-      R2 = exp(-s2 * dk32);
-      gg = exp(-1.0 * sa2 * (kl * kl));
-      grho = exp(-1.0 * sa2 * (2.0 * kl * dk32 + dk32 * dk32));
-      gq = exp(-2.0 * sa2 * (dk32 * dk32));
+  int64_t cum = 0;
+  size_t icov_base = 0;
+  for (int z = 0; z < c.nz; ++z) {
+    const int f0 = c.zoff_f[z], nfz = c.zoff_f[z + 1] - f0;
+    const int d0 = c.zoff_d[z], ndz = c.zoff_d[z + 1] - d0;
+    const int64_t cost = nfz + 2 * ndz;
+    const int64_t zend = cum + nchunks * cost;
+    // chunks of this z whose start cost falls in [t0, t1)
+    int64_t c_lo = (t0 > cum) ? (t0 - cum + cost - 1) / cost : 0;
+    int64_t c_hi = (t1 < zend) ? ((t1 > cum) ? (t1 - cum + cost - 1) / cost : 0) : nchunks;
+    const double* icz = c.icov_blocks + icov_base;
+    icov_base += (size_t)ndz * ndz;
+    cum = zend;
+    if (c_lo >= c_hi) continue;
+
+    __syncthreads();  // previous z fully processed before its tables are overwritten
+    for (int t = threadIdx.x; t < P1D_NPAIR * nfz; t += blockDim.x) {
+      int pr = t / nfz, i = t % nfz;
+      tab2[pr * nfz_max + i] = make_double2(c.tab[(size_t)(2 * pr) * c.nf + f0 + i],
+                                            c.tab[(size_t)(2 * pr + 1) * c.nf + f0 + i]);
     }
-    for (int i = lane; i < nfz; i += 32) {
-      const double k = tk[i];
-      if (!uni) {
-        E3 = exp(sg3 * k);
-        E2 = exp(-s2 * k);
-        gg = exp(-1.0 * sa2 * (k * k));
+    for (int t = threadIdx.x; t < ndz * RW; t += blockDim.x)
+      rbw[(t / RW) * RWP + (t % RW)] = c.rb_wgt[(size_t)d0 * RW + t];
+    for (int t = threadIdx.x; t < ndz; t += blockDim.x) {
+      dat[t] = c.data[d0 + t];
+      rbs[t] = c.rb_start[d0 + t];
+    }
+    __syncthreads();
+    const double2* tKS = tab2 + (C1D_COL_K / 2) * nfz_max;      // (k, S)
+    const double2* tTT1 = tab2 + (C1D_COL_T / 2) * nfz_max;     // (t, T1)
+    const double2* t2 = tab2 + (C1D_COL_T2A / 2) * nfz_max;     // (T2A, T2BC)
+    const double2* t3 = tab2 + (C1D_COL_T3A / 2) * nfz_max;     // (T3A, T3BC)
+    const double2* tD12 = tab2 + (C1D_COL_D1 / 2) * nfz_max;    // (D1, D2)
+    const double2* tD34 = tab2 + (C1D_COL_D3 / 2) * nfz_max;    // (D3, D4)
+    const double2* tKQ = tab2 + (C1D_COL_KT / 2) * nfz_max;     // (KT, Q)
+
+    const int64_t w_begin = c_lo * P1D_CHUNK;
+    int64_t w_end = c_hi * P1D_CHUNK;
+    if (w_end > W) w_end = W;
+    for (int64_t w = w_begin + warp; w < w_end; w += P1D_WARPS) {
+      const bool ok = status[w] == ST_OK;
+      if (!ok) {
+        // rejected walkers carry no model (the reference returns None)
+        for (int j = lane; j < ndz; j += 32) {
+          if (dvec) dvec[w * c.ldd + d0 + j] = 0.0;
+          if (p_out) p_out[w * c.nd + d0 + j] = qnan;
+        }
+        if (chi2z && lane == 0) chi2z[w * c.nz + z] = 0.0;
+        continue;
       }
-      // emulator polynomial (Horner) -> P_emu in km/s (lya_theory.py:690-701)
-      double pl = 0.0;
-      const double tt = tT[i];
+      const double* a = amp + ((int64_t)z * W + w) * C1D_NAMP;
+      double av = (lane < C1D_NAMP) ? a[lane] : 0.0;
+      double cf[C1D_MAX_COEF];
 #pragma unroll
-      for (int j = C1D_MAX_COEF - 1; j >= 0; --j)
-        if (j < c.nc) pl = fma(pl, tt, cf[j]);
-      const double p_emu = tS[i] * (c.emu_kind == 0 ? exp10(pl) : exp(pl));
-      double mult;
-      if (c.metal_model == 0) {
-        // si_mult.py:212-218, 267-341; 2/(1+E) = 2 * rn(1/(1+E)) exactly
-        const double G3 = fma(-2.0, __drcp_rn(1.0 + E3), 2.0);
-        const double G2 = fma(-2.0, __drcp_rn(1.0 + E2), 2.0);
-        mult = m0 + (c1 * G3 * t1[i] + G2 * (c2a * t2a[i] + c2b * t2bc[i])) +
-               (c3a * t3a[i] + c3b * t3bc[i]);
-      } else {
-        // si_vid_final.py:205-219
-        mult = 1.0 + c1 * E3 + c2a * t1[i] * E2;
-      }
-      // hcd_model_rogers_class.py:115-135 (or hcd_boss.py:5-7 through D1)
-      const double hcd = h0 + hA * tD[i] + hB * tD[nfz_max + i] + hC * tD[2 * nfz_max + i] +
-                         hD * tD[3 * nfz_max + i];
-      // si_add.py:168-219
-      const double add = aa * tKT[i] * gg;
-      // resolution_class.py:99-108
-      const double syst = 1.0 + res * tQ[i];
-      // lya_theory.py:778-784 (IC correction is folded into the S column)
-      pb[i] = (hcd * mult * p_emu + add) * syst;
+      for (int j = 0; j < C1D_MAX_COEF; ++j) cf[j] = __shfl_sync(0xffffffffu, av, A_COEF0 + j);
+      const double s3 = __shfl_sync(0xffffffffu, av, A_S3), s2 = __shfl_sync(0xffffffffu, av, A_S2);
+      const double m0 = __shfl_sync(0xffffffffu, av, A_M0), c1 = __shfl_sync(0xffffffffu, av, A_C1);
+      const double c2a = __shfl_sync(0xffffffffu, av, A_C2A), c2b = __shfl_sync(0xffffffffu, av, A_C2B);
+      const double c3a = __shfl_sync(0xffffffffu, av, A_C3A), c3b = __shfl_sync(0xffffffffu, av, A_C3B);
+      const double h0 = __shfl_sync(0xffffffffu, av, A_H0);
+      const double hA = __shfl_sync(0xffffffffu, av, A_HCD1 + 0), hB = __shfl_sync(0xffffffffu, av, A_HCD1 + 1);
+      const double hC = __shfl_sync(0xffffffffu, av, A_HCD1 + 2), hD = __shfl_sync(0xffffffffu, av, A_HCD1 + 3);
+      const double aa = __shfl_sync(0xffffffffu, av, A_AA), sa2 = __shfl_sync(0xffffffffu, av, A_SA2);
+      const double res = __shfl_sync(0xffffffffu, av, A_RES);
+
+      // exp(-s k) and exp(-s^2 k^2) on an evenly spaced grid advance by constant ratios:
+      // one exp per term and lane instead of one per point
+      const bool uni = c.uniform_k && nfz >= 2;
+      const double sg3 = (c.metal_model == 0) ? -s3 : s3;  // SiVid grows with k (si_vid_final.py:208)
+      double E3 = 0.0, R3 = 0.0, E2 = 0.0, R2 = 0.0, gg = 0.0, grho = 0.0, gq = 0.0;
       if (uni) {
-        E3 *= R3;
-        E2 *= R2;
-        gg *= grho;
-        grho *= gq;
+        const double dk32 = 32.0 * ((tKS[nfz - 1].x - tKS[0].x) / (double)(nfz - 1));
+        const double kl = tKS[lane < nfz ? lane : 0].x;
+        E3 = exp(sg3 * kl);
+        R3 = exp(sg3 * dk32);
+        E2 = exp(-s2 * kl);
+        R2 = exp(-s2 * dk32);
+        gg = exp(-1.0 * sa2 * (kl * kl));
+        grho = exp(-1.0 * sa2 * (2.0 * kl * dk32 + dk32 * dk32));
+        gq = exp(-2.0 * sa2 * (dk32 * dk32));
       }
-    }
-    __syncwarp();
-    // rebinning (likelihood.py:147-161) and residual (likelihood.py:939, 957)
-    for (int j = lane; j < ndz; j += 32) {
-      const int st = rbs[j];
-      double m = 0.0;
-      for (int t = 0; t < RW; ++t) {
-        int ii = st + t;
-        double pv = (ii < nfz) ? pb[ii] : 0.0;
-        m = fma(rbw[j * RW + t], pv, m);
-      }
-      const double dj = dat[j] - m;
-      if (dvec) dvec[w * c.ldd + d0 + j] = dj;
-      if (p_out) p_out[w * c.nd + d0 + j] = m;
-      dz[j] = dj;
-    }
-    __syncwarp();
-    if (chi2z) {
-      // chi2_z = d^T C_z^-1 d: lane owns columns j, rows broadcast from shared memory
-      double part = 0.0;
-      for (int j = lane; j < ndz; j += 32) {
-        double acc = 0.0;
-#pragma unroll 4
-        for (int i = 0; i < ndz; ++i) acc = fma(__ldg(icz + (size_t)i * ndz + j), dz[i], acc);
-        part = fma(acc, dz[j], part);
-      }
+      for (int i = lane; i < nfz; i += 32) {
+        const double2 ks = tKS[i], tt1 = tTT1[i];
+        const double k = ks.x;
+        if (!uni) {
+          E3 = exp(sg3 * k);
+          E2 = exp(-s2 * k);
+          gg = exp(-1.0 * sa2 * (k * k));
+        }
+        // emulator polynomial (Horner) -> P_emu in km/s (lya_theory.py:690-701)
+        double pl = 0.0;
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-      if (lane == 0) chi2z[w * c.nz + z] = part;
+        for (int j = C1D_MAX_COEF - 1; j >= 0; --j)
+          if (j < c.nc) pl = fma(pl, tt1.x, cf[j]);
+        const double p_emu = ks.y * (c.emu_kind == 0 ? exp10_poly(pl) : exp(pl));
+        double mult;
+        if (c.metal_model == 0) {
+          // si_mult.py:212-218, 267-341:  G = 2 - 2/(1 + E)
+          const double2 v2 = t2[i], v3 = t3[i];
+          const double G3 = fma(-2.0, rcp_fast(1.0 + E3), 2.0);
+          const double G2 = fma(-2.0, rcp_fast(1.0 + E2), 2.0);
+          mult = m0 + (c1 * G3 * tt1.y + G2 * (c2a * v2.x + c2b * v2.y)) + (c3a * v3.x + c3b * v3.y);
+        } else {
+          // si_vid_final.py:205-219
+          mult = 1.0 + c1 * E3 + c2a * tt1.y * E2;
+        }
+        // hcd_model_rogers_class.py:115-135 (or hcd_boss.py:5-7 through D1)
+        const double2 d12 = tD12[i], d34 = tD34[i], kq = tKQ[i];
+        const double hcd = h0 + hA * d12.x + hB * d12.y + hC * d34.x + hD * d34.y;
+        // si_add.py:168-219
+        const double add = aa * kq.x * gg;
+        // resolution_class.py:99-108
+        const double syst = 1.0 + res * kq.y;
+        // lya_theory.py:778-784 (IC correction is folded into the S column)
+        pb[i + (i >> 3)] = (hcd * mult * p_emu + add) * syst;
+        if (uni) {
+          E3 *= R3;
+          E2 *= R2;
+          gg *= grho;
+          grho *= gq;
+        }
+      }
+      __syncwarp();
+      // rebinning (likelihood.py:147-161) and residual (likelihood.py:939, 957)
+      for (int j = lane; j < ndz; j += 32) {
+        const int st = rbs[j];
+        double m = 0.0;
+        for (int t = 0; t < RW; ++t) {
+          int ii = st + t;
+          double pv = (ii < nfz) ? pb[ii + (ii >> 3)] : 0.0;
+          m = fma(rbw[j * RWP + t], pv, m);
+        }
+        const double dj = dat[j] - m;
+        if (dvec) dvec[w * c.ldd + d0 + j] = dj;
+        if (p_out) p_out[w * c.nd + d0 + j] = m;
+        dz[j] = dj;
+      }
+      __syncwarp();
+      if (chi2z) {
+        // chi2_z = d^T C_z^-1 d (likelihood.py:939-940): lane owns columns j, rows broadcast
+        double part = 0.0;
+        for (int j = lane; j < ndz; j += 32) {
+          double acc = 0.0;
+#pragma unroll 4
+          for (int i = 0; i < ndz; ++i) acc = fma(__ldg(icz + (size_t)i * ndz + j), dz[i], acc);
+          part = fma(acc, dz[j], part);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        if (lane == 0) chi2z[w * c.nz + z] = part;
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -544,10 +599,11 @@ int c1d_launch_stage3(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int
                       cudaStream_t s) {
   const c1d_config& cfg = ctx->cfg;
   int nfz_max = ctx->nfz_max, ndz_max = ctx->ndz_max;
-  size_t smem = ((size_t)C1D_NCOL * nfz_max + (size_t)P1D_WARPS * nfz_max +
-                 (size_t)ndz_max * cfg.rebin_width + ndz_max + (size_t)P1D_WARPS * ndz_max) * sizeof(double) +
-                (size_t)ndz_max * sizeof(int) + 16;
-  if (smem > 200 * 1024) {
+  const int RWP = cfg.rebin_width | 1;
+  const int pb_len = nfz_max + (nfz_max >> 3) + 2;
+  size_t smem = ((size_t)C1D_NCOL * nfz_max + (size_t)P1D_WARPS * pb_len + (size_t)ndz_max * RWP + ndz_max +
+                 (size_t)P1D_WARPS * ndz_max) * sizeof(double) + (size_t)ndz_max * sizeof(int) + 16;
+  if (smem > 227 * 1024) {
     snprintf(ctx->err, sizeof(ctx->err), "stage 3 needs %zu B of shared memory (z-bin too large)", smem);
     return C1D_ERR_ARG;
   }
@@ -556,16 +612,14 @@ int c1d_launch_stage3(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int
     C1D_CUDA(ctx, cudaFuncSetAttribute(k_fused_p1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  // enough CTAs per z to fill the machine about twice, at least 32 walkers each
-  int64_t target_ctas = ((int64_t)ctx->num_sms * 4 + cfg.nz - 1) / cfg.nz;
-  int64_t wpc = (W + target_ctas - 1) / target_ctas;
-  if (wpc < 32) wpc = 32;
-  wpc = (wpc + P1D_WARPS - 1) / P1D_WARPS * P1D_WARPS;
-  dim3 grid((unsigned)((W + wpc - 1) / wpc), (unsigned)cfg.nz);
+  // exactly one wave: one 16-warp CTA per SM (the tables are shared by all its warps)
+  int64_t items = ((W + P1D_CHUNK - 1) / P1D_CHUNK) * cfg.nz;
+  int64_t grid = (int64_t)ctx->num_sms;
+  if (grid > items) grid = items;
   double* dvec = want_dvec ? ctx->ws.dvec : nullptr;
   double* chi2z = want_chi2z ? ctx->ws.chi2z : nullptr;
-  k_fused_p1d<<<grid, P1D_THREADS, smem, s>>>(ctx->d, W, (int)wpc, ctx->ws.status, ctx->ws.amp, dvec,
-                                             p_out, chi2z, nfz_max, ndz_max);
+  k_fused_p1d<<<(unsigned)grid, P1D_THREADS, smem, s>>>(ctx->d, W, ctx->ws.status, ctx->ws.amp, dvec, p_out, chi2z,
+                                                     nfz_max, ndz_max);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return C1D_OK;
