@@ -413,6 +413,10 @@ __device__ __forceinline__ double rcp_fast(double x) {
 
 // A persistent CTA streams work items (z, chunk of 32 walkers) that are contiguous in a
 // z-major order and balanced by cost (fine points per z), so the grid is exactly one wave.
+// Compile-time specialisation: NC = emulator coefficients (0 = run-time count), KIND = emulator
+// kind (0: 10^poly(log10 k), 1: exp(poly(k/kmax))), METAL = 0 SiMult / 1 SiVid, UNI = evenly
+// spaced k grid (exp recurrences).
+template <int NC, int KIND, int METAL, bool UNI>
 __global__ void __launch_bounds__(P1D_THREADS, 1)
 k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* __restrict__ amp,
             double* __restrict__ dvec, double* __restrict__ p_out, double* __restrict__ chi2z,
@@ -506,8 +510,8 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
 
       // exp(-s k) and exp(-s^2 k^2) on an evenly spaced grid advance by constant ratios:
       // one exp per term and lane instead of one per point
-      const bool uni = c.uniform_k && nfz >= 2;
-      const double sg3 = (c.metal_model == 0) ? -s3 : s3;  // SiVid grows with k (si_vid_final.py:208)
+      constexpr bool uni = UNI;
+      const double sg3 = (METAL == 0) ? -s3 : s3;  // SiVid grows with k (si_vid_final.py:208)
       double E3 = 0.0, R3 = 0.0, E2 = 0.0, R2 = 0.0, gg = 0.0, grho = 0.0, gq = 0.0;
       if (uni) {
         const double dk32 = 32.0 * ((tKS[nfz - 1].x - tKS[0].x) / (double)(nfz - 1));
@@ -530,12 +534,17 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
         }
         // emulator polynomial (Horner) -> P_emu in km/s (lya_theory.py:690-701)
         double pl = 0.0;
+        if (NC > 0) {
 #pragma unroll
-        for (int j = C1D_MAX_COEF - 1; j >= 0; --j)
-          if (j < c.nc) pl = fma(pl, tt1.x, cf[j]);
-        const double p_emu = ks.y * (c.emu_kind == 0 ? exp10_poly(pl) : exp(pl));
+          for (int j = NC - 1; j >= 0; --j) pl = fma(pl, tt1.x, cf[j]);
+        } else {
+#pragma unroll
+          for (int j = C1D_MAX_COEF - 1; j >= 0; --j)
+            if (j < c.nc) pl = fma(pl, tt1.x, cf[j]);
+        }
+        const double p_emu = ks.y * (KIND == 0 ? exp10_poly(pl) : exp(pl));
         double mult;
-        if (c.metal_model == 0) {
+        if (METAL == 0) {
           // si_mult.py:212-218, 267-341:  G = 2 - 2/(1 + E)
           const double2 v2 = t2[i], v3 = t3[i];
           const double G3 = fma(-2.0, rcp_fast(1.0 + E3), 2.0);
@@ -607,19 +616,39 @@ int c1d_launch_stage3(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int
     snprintf(ctx->err, sizeof(ctx->err), "stage 3 needs %zu B of shared memory (z-bin too large)", smem);
     return C1D_ERR_ARG;
   }
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    C1D_CUDA(ctx, cudaFuncSetAttribute(k_fused_p1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  typedef void (*kern_t)(DevCtx, int64_t, const int*, const double*, double*, double*, double*, int, int);
+  kern_t kern = nullptr;
+  const int nc = (cfg.nc >= 5 && cfg.nc <= 7) ? cfg.nc : 0;
+  const int sel = ((nc ? nc - 4 : 0) << 3) | (cfg.emu_kind << 2) | (cfg.metal_model << 1) | (cfg.uniform_k ? 1 : 0);
+#define P1D_CASE(NCI, NCV)                                                                              \
+  case ((NCI) << 3) | 0: kern = k_fused_p1d<NCV, 0, 0, false>; break;                                   \
+  case ((NCI) << 3) | 1: kern = k_fused_p1d<NCV, 0, 0, true>; break;                                    \
+  case ((NCI) << 3) | 2: kern = k_fused_p1d<NCV, 0, 1, false>; break;                                   \
+  case ((NCI) << 3) | 3: kern = k_fused_p1d<NCV, 0, 1, true>; break;                                    \
+  case ((NCI) << 3) | 4: kern = k_fused_p1d<NCV, 1, 0, false>; break;                                   \
+  case ((NCI) << 3) | 5: kern = k_fused_p1d<NCV, 1, 0, true>; break;                                    \
+  case ((NCI) << 3) | 6: kern = k_fused_p1d<NCV, 1, 1, false>; break;                                   \
+  case ((NCI) << 3) | 7: kern = k_fused_p1d<NCV, 1, 1, true>; break;
+  switch (sel) {
+    P1D_CASE(0, 0)
+    P1D_CASE(1, 5)
+    P1D_CASE(2, 6)
+    P1D_CASE(3, 7)
   }
+#undef P1D_CASE
+  if (!kern) {
+    snprintf(ctx->err, sizeof(ctx->err), "no stage-3 kernel for this configuration");
+    return C1D_ERR_ARG;
+  }
+  C1D_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // exactly one wave: one 16-warp CTA per SM (the tables are shared by all its warps)
   int64_t items = ((W + P1D_CHUNK - 1) / P1D_CHUNK) * cfg.nz;
   int64_t grid = (int64_t)ctx->num_sms;
   if (grid > items) grid = items;
   double* dvec = want_dvec ? ctx->ws.dvec : nullptr;
   double* chi2z = want_chi2z ? ctx->ws.chi2z : nullptr;
-  k_fused_p1d<<<(unsigned)grid, P1D_THREADS, smem, s>>>(ctx->d, W, ctx->ws.status, ctx->ws.amp, dvec, p_out, chi2z,
-                                                     nfz_max, ndz_max);
+  kern<<<(unsigned)grid, P1D_THREADS, smem, s>>>(ctx->d, W, ctx->ws.status, ctx->ws.amp, dvec, p_out, chi2z, nfz_max,
+                                                  ndz_max);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return C1D_OK;
