@@ -205,7 +205,7 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
 static void ws_free(c1d_ctx* ctx) {
   Workspace& w = ctx->ws;
   cudaFree(w.status); cudaFree(w.lnprior); cudaFree(w.blobs); cudaFree(w.emu_in); cudaFree(w.amp);
-  cudaFree(w.dvec); cudaFree(w.chi2z); cudaFree(w.chi2p); cudaFree(w.lnp); cudaFree(w.xdev); cudaFree(w.out7);
+  cudaFree(w.dvec); cudaFree(w.chi2z); cudaFree(w.chi2p); cudaFree(w.lnp); cudaFree(w.xdev); cudaFree(w.out7); cudaFree(w.factors); cudaFree(w.blobs_q);
   memset(&w, 0, sizeof(w));
 }
 
@@ -228,11 +228,27 @@ static int ws_reserve(c1d_ctx* ctx, int64_t W) {
   C1D_CUDA(ctx, cudaMalloc(&w.lnp, cap * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.xdev, (size_t)cap * c.ndim * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.out7, (size_t)cap * 7 * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.factors, cap * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.blobs_q, (size_t)cap * 6 * sizeof(double)));
   // rows of rejected walkers are never written by stage 1: keep them finite
   C1D_CUDA(ctx, cudaMemset(w.emu_in, 0, (size_t)cap * c.nz * C1D_MAX_EMU * sizeof(double)));
   C1D_CUDA(ctx, cudaMemset(w.amp, 0, (size_t)cap * c.nz * C1D_NAMP * sizeof(double)));
   w.cap = cap;
   return C1D_OK;
+}
+
+// the sampler keeps proposals in the workspace across likelihood calls: size it once up front
+int c1d_sampler_reserve(c1d_ctx* ctx, int64_t W) {
+  if (!ctx->finalized) {
+    snprintf(ctx->err, sizeof(ctx->err), "context not finalised");
+    return C1D_ERR_STATE;
+  }
+  if (W > CHUNK_MAX) {
+    snprintf(ctx->err, sizeof(ctx->err), "device sampler supports at most %lld walkers per half-ensemble", (long long)CHUNK_MAX);
+    return C1D_ERR_ARG;
+  }
+  C1D_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  return ws_reserve(ctx, W);
 }
 
 static int check_ready(c1d_ctx* ctx, uint32_t flags) {

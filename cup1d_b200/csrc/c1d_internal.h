@@ -68,6 +68,8 @@ struct Workspace {
   double* lnp;     // [cap]   (host-variant staging on the device)
   double* xdev;    // [cap*ndim]
   double* out7;    // [cap*7] packed (lnP, blob[6]) rows for the host variant
+  double* factors; // [cap] (n-1) ln z of the stretch-move proposals
+  double* blobs_q; // [cap*6] blobs of the proposals
 };
 
 struct c1d_ctx {

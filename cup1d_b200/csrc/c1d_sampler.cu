@@ -1,0 +1,140 @@
+// Affine-invariant ensemble sampler on the device: the stretch move of
+// Goodman & Weare (2010) in its two-half parallel form — what emcee's StretchMove does around
+// the reference's per-walker likelihood calls (cup1d/likelihood/fitter.py:187-235) — with the
+// proposal, the batched likelihood of the proposed half and the accept/reject all enqueued on
+// one stream and no host round trip per step.  Random numbers: Philox4x32-10, counter
+// (step, half, walker, 0), key = seed, so a chain is reproducible from (seed, step).
+#include "c1d_internal.h"
+
+namespace {
+
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0;
+    k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// uniform in (0, 1) from 32 random bits + 21 bits of a second word (53-bit mantissa)
+__host__ __device__ inline double u01(uint32_t a, uint32_t b) {
+  const uint64_t v = ((uint64_t)a << 21) ^ (uint64_t)(b >> 11);
+  return ((double)(v & ((1ull << 53) - 1)) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// one warp per walker s of the active half: q = c_j - (c_j - x_s) z
+__global__ void __launch_bounds__(256)
+k_stretch_propose(const double* __restrict__ x, int64_t W, int ndim, int half, int64_t step, uint64_t seed,
+                  double a, double* __restrict__ q, double* __restrict__ factors) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nh = W / 2;
+  if (s >= nh) return;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)half << 31), (uint32_t)s, 0u, (uint32_t)seed,
+                (uint32_t)(seed >> 32), r);
+  const double z = (a - 1.0) * u01(r[0], r[1]) + 1.0;
+  const double zz = z * z / a;
+  int64_t j = (int64_t)(u01(r[2], r[3]) * (double)nh);
+  if (j >= nh) j = nh - 1;
+  const double* xs = x + (half * nh + s) * ndim;
+  const double* xc = x + ((1 - half) * nh + j) * ndim;
+  for (int d = lane; d < ndim; d += 32) q[s * ndim + d] = xc[d] - (xc[d] - xs[d]) * zz;
+  if (lane == 0) factors[s] = (ndim - 1.0) * log(zz);
+}
+
+// accept with probability min(1, z^(n-1) p(q)/p(x)); one warp per walker copies the row
+__global__ void __launch_bounds__(256)
+k_stretch_accept(double* __restrict__ x, double* __restrict__ lnp, double* __restrict__ blobs, int64_t W, int ndim,
+                 int half, int64_t step, uint64_t seed, const double* __restrict__ q,
+                 const double* __restrict__ factors, const double* __restrict__ lnp_q,
+                 const double* __restrict__ blobs_q, long long* __restrict__ naccept) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nh = W / 2;
+  if (s >= nh) return;
+  const int64_t w = half * nh + s;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)half << 31), (uint32_t)s, 1u, (uint32_t)seed,
+                (uint32_t)(seed >> 32), r);
+  const double lnu = log(u01(r[0], r[1]));
+  const bool acc = lnu < factors[s] + lnp_q[s] - lnp[w];
+  if (!acc) return;
+  for (int d = lane; d < ndim; d += 32) x[w * ndim + d] = q[s * ndim + d];
+  if (lane < 6) blobs[w * 6 + lane] = blobs_q[s * 6 + lane];
+  if (lane == 0) {
+    lnp[w] = lnp_q[s];
+    if (naccept) naccept[w] += 1;
+  }
+}
+
+}  // namespace
+
+// host-callable copy of the generator for tests (numpy replay of a chain)
+extern "C" int c1d_philox_u01(uint64_t seed, int64_t step, int half, int64_t walker, int which, double* out2) {
+  if (!out2) return C1D_ERR_ARG;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)half << 31), (uint32_t)walker, (uint32_t)which,
+                (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  out2[0] = u01(r[0], r[1]);
+  out2[1] = u01(r[2], r[3]);
+  return C1D_OK;
+}
+
+int c1d_sampler_reserve(c1d_ctx* ctx, int64_t W);  // c1d_abi.cu
+
+extern "C" int c1d_sampler_run(c1d_ctx* ctx, double* x_dev, double* lnp_dev, double* blobs_dev, int64_t W,
+                               int64_t nsteps, int64_t step0, uint64_t seed, double a, int init, int thin,
+                               double* chain_dev, double* lnp_chain_dev, double* blobs_chain_dev,
+                               long long* naccept_dev, uint32_t flags, void* cuda_stream) {
+  if (!ctx) return C1D_ERR_ARG;
+  if (!x_dev || !lnp_dev || !blobs_dev || W < 2 || (W % 2) || nsteps < 0 || thin < 1 || !(a > 1.0)) {
+    snprintf(ctx->err, sizeof(ctx->err), "bad arguments to c1d_sampler_run (W must be even, a > 1)");
+    return C1D_ERR_ARG;
+  }
+  const int ndim = ctx->cfg.ndim;
+  const int64_t nh = W / 2;
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  int rc = c1d_sampler_reserve(ctx, nh);
+  if (rc) return rc;
+  if (init) {
+    rc = c1d_loglike_batch(ctx, x_dev, W, lnp_dev, nullptr, blobs_dev, nullptr, flags, cuda_stream);
+    if (rc) return rc;
+  }
+  const unsigned grid = (unsigned)((nh * 32 + 255) / 256);
+  int64_t stored = 0;
+  for (int64_t it = 0; it < nsteps; ++it) {
+    const int64_t step = step0 + it;
+    for (int half = 0; half < 2; ++half) {
+      k_stretch_propose<<<grid, 256, 0, s>>>(x_dev, W, ndim, half, step, seed, a, ctx->ws.xdev, ctx->ws.factors);
+      ctx->launches++;
+      C1D_CUDA(ctx, cudaPeekAtLastError());
+      rc = c1d_loglike_batch(ctx, ctx->ws.xdev, nh, ctx->ws.lnp, nullptr, ctx->ws.blobs_q, nullptr, flags, cuda_stream);
+      if (rc) return rc;
+      k_stretch_accept<<<grid, 256, 0, s>>>(x_dev, lnp_dev, blobs_dev, W, ndim, half, step, seed, ctx->ws.xdev,
+                                            ctx->ws.factors, ctx->ws.lnp, ctx->ws.blobs_q, naccept_dev);
+      ctx->launches++;
+      C1D_CUDA(ctx, cudaPeekAtLastError());
+    }
+    if ((it + 1) % thin == 0) {
+      if (chain_dev)
+        C1D_CUDA(ctx, cudaMemcpyAsync(chain_dev + stored * W * ndim, x_dev, (size_t)W * ndim * sizeof(double),
+                                      cudaMemcpyDeviceToDevice, s));
+      if (lnp_chain_dev)
+        C1D_CUDA(ctx, cudaMemcpyAsync(lnp_chain_dev + stored * W, lnp_dev, (size_t)W * sizeof(double),
+                                      cudaMemcpyDeviceToDevice, s));
+      if (blobs_chain_dev)
+        C1D_CUDA(ctx, cudaMemcpyAsync(blobs_chain_dev + stored * W * 6, blobs_dev, (size_t)W * 6 * sizeof(double),
+                                      cudaMemcpyDeviceToDevice, s));
+      ++stored;
+    }
+  }
+  return C1D_OK;
+}

@@ -221,6 +221,45 @@ class B200Likelihood(object):
             return self._out(p, was_numpy), self._out(emu, was_numpy)
         return self._out(p, was_numpy)
 
+    # ---- on-device ensemble sampler --------------------
+    def run_sampler_device(self, p0, nsteps, nburn=0, thin=1, seed=0, a=2.0, zmask=None, to_numpy=True):
+        """Stretch-move MCMC entirely on the GPU (c1d_sampler_run): ``p0[W, ndim]``
+        initial walkers (W even), ``nburn`` discarded steps, then ``nsteps`` steps of
+        which every ``thin``-th is kept.  Returns the same products as
+        Fitter.run_sampler keeps (fitter.py:238-246): dict(chain[S, W, ndim],
+        lnprob[S, W], blobs[S, W] structured, acceptance_fraction[W])."""
+        x, _, _ = self._as_device(np.array(p0, dtype=float) if not torch.is_tensor(p0) else p0.clone())
+        x = x.clone()
+        W = x.shape[0]
+        if W % 2:
+            raise ValueError("the device sampler needs an even number of walkers")
+        nkeep = nsteps // thin
+        flags = self._flags(zmask, True)
+        with torch.cuda.device(self.device):
+            dev = self.device
+            lnp = torch.empty(W, dtype=torch.float64, device=dev)
+            blobs = torch.empty((W, 6), dtype=torch.float64, device=dev)
+            chain = torch.empty((nkeep, W, self.ndim), dtype=torch.float64, device=dev)
+            lchain = torch.empty((nkeep, W), dtype=torch.float64, device=dev)
+            bchain = torch.empty((nkeep, W, 6), dtype=torch.float64, device=dev)
+            nacc = torch.zeros(W, dtype=torch.int64, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            if nburn > 0:
+                self.ctx.sampler_run(x.data_ptr(), lnp.data_ptr(), blobs.data_ptr(), W, nburn, 0, seed, a, True, 1,
+                                     None, None, None, None, flags, stream)
+            nacc.zero_()
+            self.ctx.sampler_run(x.data_ptr(), lnp.data_ptr(), blobs.data_ptr(), W, nsteps, nburn, seed, a, nburn == 0, thin,
+                                 chain.data_ptr(), lchain.data_ptr(), bchain.data_ptr(), nacc.data_ptr(), flags, stream)
+        out = {"chain": chain, "lnprob": lchain, "blobs": bchain, "acceptance_fraction": nacc.double() / max(1, nsteps),
+               "last_state": x, "last_lnprob": lnp}
+        if to_numpy:
+            out = {k: v.cpu().numpy() for k, v in out.items()}
+            b = np.zeros(out["blobs"].shape[:-1], dtype=self.get_blobs_dtype())
+            for i, nme in enumerate(BLOB_NAMES):
+                b[nme] = out["blobs"][..., i]
+            out["blobs"] = b
+        return out
+
     # ---- scalar API with the reference's conventions ------------------
     def _values_or_fid(self, values):
         if values is None:

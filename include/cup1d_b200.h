@@ -197,6 +197,25 @@ int c1d_emulator_only(c1d_ctx* ctx, const double* emu_in_dev, int64_t nrows,
 int c1d_loglike_batch_host(c1d_ctx* ctx, const double* x_host, int64_t W,
                            double* out_host, uint32_t flags);
 
+/* Affine-invariant stretch move on the device (what emcee does around the reference's
+ * per-walker calls, fitter.py:187-235).  The ensemble is split in two fixed
+ * halves; each iteration updates both halves (proposal kernel, batched likelihood of the
+ * proposed half, accept kernel), everything enqueued on cuda_stream without host round trips.
+ *   x_dev [W, ndim], lnp_dev [W], blobs_dev [W, 6]: state, in/out (W even).  init != 0
+ *     evaluates lnp/blobs of the initial positions first.
+ *   step0, seed: Philox4x32-10 counters, so (seed, step) reproduces a chain.
+ *   a: stretch scale (emcee default 2).  thin: every thin-th state is stored in
+ *   chain_dev [nsteps/thin, W, ndim], lnp_chain_dev [nsteps/thin, W], blobs_chain_dev
+ *   [nsteps/thin, W, 6] (each may be NULL).  naccept_dev [W] int64 counters or NULL. */
+int c1d_sampler_run(c1d_ctx* ctx, double* x_dev, double* lnp_dev, double* blobs_dev, int64_t W,
+                    int64_t nsteps, int64_t step0, uint64_t seed, double a, int init, int thin,
+                    double* chain_dev, double* lnp_chain_dev, double* blobs_chain_dev,
+                    long long* naccept_dev, uint32_t flags, void* cuda_stream);
+
+/* the sampler's random numbers on the host (tests replay a chain with them):
+ * out2 = two uniforms in (0,1) of counter (step, half, walker, which) */
+int c1d_philox_u01(uint64_t seed, int64_t step, int half, int64_t walker, int which, double* out2);
+
 /* number of kernels launched by this context since creation */
 int64_t c1d_launch_count(const c1d_ctx* ctx);
 
