@@ -18,8 +18,8 @@ from .spec import model_k_grid, spec_sizes
 C_KMS = 2.99792458e5
 LYA_AA = 1215.67
 
-NQ = 19
-NCOL = 14
+NQ = 20
+NCOL = 16
 MAX_EMU = 8
 MAX_COEF = 8
 MAX_LAYERS = 12
@@ -31,10 +31,10 @@ QUANTITIES = [
     "f_SiIIa_SiIII", "f_SiIIb_SiIII",
     "f_SiIIa_SiIIb", "s_SiIIa_SiIIb",
     "HCD_damp1", "HCD_damp2", "HCD_damp3", "HCD_damp4", "HCD_const",
-    "R_coeff", "ln_AGN",
+    "R_coeff", "ln_AGN", "ln_AGN_const",
 ]
 (COL_K, COL_S, COL_T, COL_T1, COL_T2A, COL_T2BC, COL_T3A, COL_T3BC,
- COL_D1, COL_D2, COL_D3, COL_D4, COL_KT, COL_Q) = range(NCOL)
+ COL_D1, COL_D2, COL_D3, COL_D4, COL_KT, COL_Q, COL_AGN, COL_SPARE) = range(NCOL)
 
 EMU_CODES = {"Delta2_p": 0, "n_p": 1, "alpha_p": 2, "mF": 3, "sigT_Mpc": 4, "gamma": 5, "kF_Mpc": 6, "lambda_P": 7}
 
@@ -105,7 +105,16 @@ def compile_z_functions(spec):
     rows = []
     ell = 1
     for q in QUANTITIES:
-        if q in fams:
+        if q == "ln_AGN" and q in fams:
+            # AGN_Model nulls on the constant coefficient, not on the value (AGN_model.py:85-86)
+            fam = dict(fams[q])
+            fam["null"] = np.nan
+        elif q == "ln_AGN_const" and "ln_AGN" in fams:
+            src = fams["ln_AGN"]
+            fam = dict(src)
+            fam.update(ztype="pivot", znodes=np.zeros(0), coeffs=np.asarray(src["coeffs"], dtype=float)[-1:],
+                       param_idx=np.asarray(src["param_idx"])[-1:], zmax=np.nan, otype="exp")
+        elif q in fams:
             fam = fams[q]
         elif q in ("tau_eff", "sigT_kms", "gamma", "kF_kms"):
             raise ValueError("missing IGM family " + q)
@@ -209,7 +218,27 @@ def compile_tables(spec):
         tab[COL_KT, s] = kt
         Rz = C_KMS * 0.8 / (1 + z) / LYA_AA  # resolution_class.py:26-34
         tab[COL_Q, s] = 2 * Rz**2 * k**2
+        if cont.get("agn") is not None:
+            tab[COL_AGN, s] = agn_delta(cont["agn"], z, k)
     return tab
+
+
+def agn_delta(agn, z, k):
+    """delta(z, k) of the AGN feedback template: a + b exp(-c k) tabulated at 9 redshifts,
+    linear in z between them and extrapolated from the first two rows above the table
+    (AGN_model.py:99-116; table data/nuisance/AGN_corr.dat)"""
+    az = np.asarray(agn["z"], dtype=float)
+    ex = np.asarray(agn["expansion"], dtype=float)
+    if z <= np.max(az):
+        yy = ex[:, 0][None, :] + ex[:, 1][None, :] * np.exp(-ex[:, 2][None, :] * k[:, None])
+        order = np.argsort(az)
+        out = np.zeros(len(k))
+        for i in range(len(k)):
+            out[i] = np.interp(z, az[order], yy[i, order])
+        return out
+    up = ex[0, 0] + ex[0, 1] * np.exp(-ex[0, 2] * k)
+    lo = ex[1, 0] + ex[1, 1] * np.exp(-ex[1, 2] * k)
+    return (up - lo) / (az[0] - az[1]) * (z - az[0]) + up
 
 
 def compile_rebin(spec):
@@ -329,6 +358,7 @@ def compile_spec(spec):
             break
     cfg = {
         "uniform_k": int(uniform),
+        "has_agn": int(cont.get("agn") is not None and "ln_AGN" in spec["families"]),
         "nz": nz, "ndim": ndim, "n_emu": n_emu, "nd": nd, "nf": nf,
         "ell_width": int(ell), "rebin_width": int(rwidth),
         "n_layers": 0, "layer_dims": [0] * (MAX_LAYERS + 1),

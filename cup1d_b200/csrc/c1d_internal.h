@@ -22,7 +22,8 @@ enum {
   A_HCD1 = 17,   // .. A_HCD1 + 3
   A_AA = 21,     // f_SiIIa_SiIIb^2
   A_SA2 = 22,    // s_SiIIa_SiIIb^2
-  A_RES = 23     // R_coeff(z) (0 when the resolution term is not applied)
+  A_RES = 23,    // R_coeff(z) (0 when the resolution term is not applied)
+  A_AGN = 24     // f_AGN(z) (0 when absent or nulled)
 };
 
 // walker status written by stage 1
@@ -33,7 +34,7 @@ struct DevCtx {
   int ldd;  // row stride of the residual buffer = nd rounded up to a multiple of 64 (zero padded)
   int layer_dims[C1D_MAX_LAYERS + 1];
   int gp_ntrain, gp_nnorm, gp_imf;
-  int metal_model, apply_resolution, has_full, has_gauss, n_hull_facets, uniform_k;
+  int metal_model, apply_resolution, has_full, has_gauss, n_hull_facets, uniform_k, has_agn;
   int idx_As, idx_ns, idx_nrun;
   int emu_code[C1D_MAX_EMU];
   double As_fid, ns_fid, nrun_fid, L_emu, L_star;

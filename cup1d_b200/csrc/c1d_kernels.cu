@@ -152,6 +152,7 @@ k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ st
     a[A_AA] = q[C1D_Q_F_SIADD] * q[C1D_Q_F_SIADD];  // si_add.py:219
     a[A_SA2] = q[C1D_Q_S_SIADD] * q[C1D_Q_S_SIADD]; // si_add.py:168-170
     a[A_RES] = c.apply_resolution ? q[C1D_Q_RES] : 0.0;  // lya_theory.py:712-722
+    a[A_AGN] = (q[C1D_Q_AGN_CONST] > 0.0) ? q[C1D_Q_AGN] : 0.0;  // AGN_model.py:81-91
   }
   status[w] = rej ? ST_REJECTED : ST_OK;
 }
@@ -478,6 +479,7 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
     const double2* tD12 = tab2 + (C1D_COL_D1 / 2) * nfz_max;    // (D1, D2)
     const double2* tD34 = tab2 + (C1D_COL_D3 / 2) * nfz_max;    // (D3, D4)
     const double2* tKQ = tab2 + (C1D_COL_KT / 2) * nfz_max;     // (KT, Q)
+    const double2* tAG = tab2 + (C1D_COL_AGN / 2) * nfz_max;    // (AGN delta, spare)
 
     const int64_t w_begin = c_lo * P1D_CHUNK;
     int64_t w_end = c_hi * P1D_CHUNK;
@@ -507,6 +509,7 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
       const double hC = __shfl_sync(0xffffffffu, av, A_HCD1 + 2), hD = __shfl_sync(0xffffffffu, av, A_HCD1 + 3);
       const double aa = __shfl_sync(0xffffffffu, av, A_AA), sa2 = __shfl_sync(0xffffffffu, av, A_SA2);
       const double res = __shfl_sync(0xffffffffu, av, A_RES);
+      const double fagn = __shfl_sync(0xffffffffu, av, A_AGN);
 
       // exp(-s k) and exp(-s^2 k^2) on an evenly spaced grid advance by constant ratios:
       // one exp per term and lane instead of one per point
@@ -554,6 +557,7 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
           // si_vid_final.py:205-219
           mult = 1.0 + c1 * E3 + c2a * tt1.y * E2;
         }
+        if (c.has_agn) mult *= fma(fagn, tAG[i].x, 1.0);  // AGN_model.py:116-120: 1 + f_AGN delta
         // hcd_model_rogers_class.py:115-135 (or hcd_boss.py:5-7 through D1)
         const double2 d12 = tD12[i], d34 = tD34[i], kq = tKQ[i];
         const double hcd = h0 + hA * d12.x + hB * d12.y + hC * d34.x + hD * d34.y;

@@ -370,6 +370,23 @@ def spec_from_likelihood(like):
             "off": _plain(si_add.off),
         },
     }
+    agn_model = getattr(mc, "agn_model", None)
+    cont["agn"] = None
+    if agn_model is not None:
+        # AGN_Model is not a Contaminant: pivot polynomial in ln_AGN_i with parameter i
+        # feeding coefficient [n-1-i] (AGN_model.py:52-72, 137-167)
+        coeffs = np.array(agn_model.ln_AGN_coeff, dtype=float)
+        n = len(coeffs)
+        pidx = np.full(n, -1, dtype=np.int64)
+        for i in range(n):
+            nm = "ln_AGN_" + str(i)
+            if nm in free_names:
+                pidx[n - 1 - i] = free_names.index(nm)
+        families["ln_AGN"] = {
+            "ztype": "pivot", "otype": "exp", "znodes": np.zeros(0), "coeffs": coeffs, "param_idx": pidx,
+            "z0": float(agn_model.z_0), "null": float(agn_model.null_value), "zmax": np.nan,
+        }
+        cont["agn"] = {"z": np.array(agn_model.AGN_z, dtype=float), "expansion": np.array(agn_model.AGN_expansion, dtype=float)}
     if hcd_model == "rogers":
         cont["rogers"] = {
             "a0": np.array(hcd.a_0, dtype=float),

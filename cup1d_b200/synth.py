@@ -83,6 +83,20 @@ ROGERS = {
     "z0": 3.0,
 }
 
+# AGN feedback correction table of Chabanier et al. 2020 (rows: z, a, b, c with
+# delta = a + b exp(-c k)); same numbers as the reference's data/nuisance/AGN_corr.dat
+AGN_TABLE = np.array([
+    [4.254242298971526, 0.001948707260760598, -0.005113025363647983, 297.76336326532356],
+    [3.7399508480460177, -0.002395192935503769, -0.014496865270097973, 189.05445743949753],
+    [3.33497418318008, -0.0015888346971373486, -0.0280564876368884, 166.29319089261327],
+    [3.0053240496893006, -0.0066211056484300895, -0.03933342912116104, 159.0177616872931],
+    [2.7310610558920296, -0.007901357724366368, -0.04622024793203778, 153.92538415800533],
+    [2.4979310724428525, -0.011606137378406078, -0.05222578599582309, 151.0360486518846],
+    [2.29696817249267, -0.01397956154253014, -0.058065380798205515, 138.5389744852627],
+    [2.1217615536671572, -0.019499510059870485, -0.061213371048927705, 124.88130335751495],
+    [1.966806396137914, -0.025420244243385796, -0.06663923678784489, 120.3535253491937],
+])
+
 EMU_RANGES = {
     "Delta2_p": (0.10, 1.00),
     "n_p": (-2.60, -2.00),
@@ -296,6 +310,7 @@ def build_spec(
     hcd_const=False,
     ic_correction=False,
     gauss_priors=False,
+    agn=False,
     seed=14,
     snr=36.0,
     nk=None,
@@ -355,6 +370,10 @@ def build_spec(
         fam["R_coeff"] = _interp_family(zs, 0.0, -0.1, 0.1, names, pmin, pmax, pval, "R_coeff", "const", rng=rng, jitter=0.01)
     else:
         fam["R_coeff"] = _fixed_pivot(0.0, "const")
+
+    if agn:
+        # optional AGN feedback amplitude, one pivot parameter (AGN_model.py:52-72: prior [-5, 1])
+        fam["ln_AGN"] = _interp_family([3.0], -1.5, -5.0, 1.0, names, pmin, pmax, pval, "ln_AGN", "exp", null=-5.5)
 
     ndim = len(names)
     M = hubble_over_1pz(zs)
@@ -417,6 +436,7 @@ def build_spec(
             "si_mult": si_mult,
             "si_add": si_add,
             "rogers": {k: (v.copy() if hasattr(v, "copy") else v) for k, v in ROGERS.items()},
+            "agn": ({"z": AGN_TABLE[:, 0].copy(), "expansion": AGN_TABLE[:, 1:].copy()} if agn else None),
         },
         "data": {
             "k_kms": k_kms,

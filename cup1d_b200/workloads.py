@@ -11,7 +11,7 @@ WORKLOADS = {
     # C2 GP emulator, 4096 walkers on one GPU
     "c2": dict(desc="C2 GP emulator (1320 training points), DR1 grid 11 z / 681 k, rebin 8, dense 681^2 icov", walkers=4096),
     # C3 nyx-like full nuisance set, 65k walkers over 8 GPUs
-    "c3": dict(desc="C3 nyx-like NN (7 inputs, ndeg 6), As/ns/nrun + 6 IGM nodes + HCD_const, Gaussian priors, DR1 grid, dense icov", walkers=8192),
+    "c3": dict(desc="C3 nyx-like NN (7 inputs, ndeg 6), As/ns/nrun + 6 IGM nodes + HCD_const + AGN, Gaussian priors, DR1 grid, dense icov", walkers=8192),
     # C4 DESI-DR1-like: NN emulator, rebin 8 (5448 fine k), dense 681^2 inverse covariance, As/ns/nrun
     "c4": dict(desc="C4 DESI-DR1-like mock: Cabayol23+-shaped NN (6-10-70-130-190-250-50-6), 11 z, 681 k, rebin 8 (5448 fine k), dense 681^2 icov, 54 params (As, ns, nrun, IGM, Si, HCD, resolution)", walkers=65536),
 }
@@ -28,7 +28,7 @@ def build_workload_spec(name):
     if name == "c3":
         emu = synth.synth_nn_emulator(seed=13, suite="nyx", ndeg=6)
         return synth.build_spec(emu, grid="dr1", rebin_k=8, full_cov=True, vary_nrun=True, nz_igm=6,
-                                hcd_const=True, gauss_priors=True, seed=14)
+                                hcd_const=True, gauss_priors=True, agn=True, seed=14)
     if name == "c4":
         emu = synth.synth_nn_emulator(seed=11)
         return synth.build_spec(emu, grid="dr1", rebin_k=8, full_cov=True, vary_nrun=True, seed=14)

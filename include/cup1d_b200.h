@@ -32,13 +32,13 @@
 extern "C" {
 #endif
 
-#define C1D_ABI_VERSION 4
+#define C1D_ABI_VERSION 5
 #define C1D_MAX_LAYERS 12
 #define C1D_MAX_EMU 8     /* emulator inputs */
 #define C1D_MAX_COEF 8    /* polynomial coefficients the emulator returns */
-#define C1D_NQ 19         /* z-dependent model quantities, see c1d_quantity */
-#define C1D_NCOL 14       /* walker-independent k tables, see c1d_column */
-#define C1D_NAMP 24       /* per-(walker,z) amplitudes handed from stage 1/2 to stage 3 */
+#define C1D_NQ 20         /* z-dependent model quantities, see c1d_quantity */
+#define C1D_NCOL 16       /* walker-independent k tables, see c1d_column */
+#define C1D_NAMP 26       /* per-(walker,z) amplitudes handed from stage 1/2 to stage 3 */
 
 typedef enum c1d_status {
   C1D_OK = 0,
@@ -56,7 +56,9 @@ typedef enum c1d_quantity {
   C1D_Q_F_SIIIA_SIIII, C1D_Q_F_SIIIB_SIIII,
   C1D_Q_F_SIADD, C1D_Q_S_SIADD,
   C1D_Q_HCD1, C1D_Q_HCD2, C1D_Q_HCD3, C1D_Q_HCD4, C1D_Q_HCD_CONST,
-  C1D_Q_RES, C1D_Q_AGN
+  C1D_Q_RES,
+  C1D_Q_AGN,        /* f_AGN(z) = exp(poly(ln_AGN))           AGN_model.py:81-91 */
+  C1D_Q_AGN_CONST   /* exp(constant coefficient): zero when it is <= the null value (:85-86) */
 } c1d_quantity;
 
 /* walker-independent tables over the packed model k grid (fine grid when
@@ -72,7 +74,9 @@ typedef enum c1d_column {
   C1D_COL_T3BC,      /* off*cos(dv(SiIII-SiIIb)k) + off*(rc3/rb3)cos(dv(SiIII-SiIIc)k) */
   C1D_COL_D1, C1D_COL_D2, C1D_COL_D3, C1D_COL_D4, /* HCD profiles  hcd_model_rogers_class.py:5-6 */
   C1D_COL_KT,        /* SiAdd ktot(k)                                  si_add.py:207-217 */
-  C1D_COL_Q          /* 2 R_z^2 k^2                                    resolution_class.py:99-108 */
+  C1D_COL_Q,         /* 2 R_z^2 k^2                                    resolution_class.py:99-108 */
+  C1D_COL_AGN,       /* delta(z, k) of the AGN feedback template       AGN_model.py:99-116 */
+  C1D_COL_SPARE
 } c1d_column;
 
 /* constant fields uploaded once with c1d_ctx_upload (float64 unless noted) */
@@ -132,7 +136,8 @@ typedef struct c1d_config {
   int32_t emu_code[C1D_MAX_EMU]; /* 0 Delta2_p 1 n_p 2 alpha_p 3 mF 4 sigT_Mpc 5 gamma 6 kF_Mpc 7 lambda_P */
   int32_t device;             /* CUDA device ordinal */
   int32_t uniform_k;          /* 1 = the model k grid of every z is evenly spaced (linspace, likelihood.py:90-94) */
-  int32_t reserved_i[6];
+  int32_t has_agn;            /* AGN feedback term present (off in the reference: model_contaminants.py:138-154) */
+  int32_t reserved_i[5];
   double As_fid, ns_fid, nrun_fid;
   double L_emu;               /* ln(kp_emu / ks)   lya_theory.py:299 */
   double L_star;              /* ln(kp_star / ks)  lya_theory.py:565 */

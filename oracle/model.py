@@ -275,6 +275,37 @@ def nyx_ic_correction(zs, k_kms):
     return out
 
 
+def agn_delta(agn, z, k):
+    """AGN feedback shape delta(z, k) (AGN_model.py:99-116): a + b exp(-c k) tabulated at the
+    redshifts of data/nuisance/AGN_corr.dat, interpolated linearly in z, extrapolated from the
+    first two rows above the table"""
+    from scipy.interpolate import interp1d
+
+    az, ex = np.asarray(agn["z"], dtype=float), np.asarray(agn["expansion"], dtype=float)
+    if z <= np.max(az):
+        yy = ex[:, 0][None, :] + ex[:, 1][None, :] * np.exp(-ex[:, 2][None, :] * k[:, None])
+        return interp1d(az, yy)(z)
+    upper = ex[0, 0] + ex[0, 1] * np.exp(-ex[0, 2] * k)
+    lower = ex[1, 0] + ex[1, 1] * np.exp(-ex[1, 2] * k)
+    return (upper - lower) / (az[0] - az[1]) * (z - az[0]) + upper
+
+
+def agn_contamination(agn, fam, zs, k_kms, pvalues):
+    """1 + f_AGN(z) delta(z, k) (AGN_model.py:81-120).  The whole term is switched off when
+    the constant coefficient is <= the null value (:85-86).  Disabled in the reference
+    (model_contaminants.py:138-154, 242-252); here an optional term."""
+    coeff = family_coeffs(fam, pvalues)
+    out = []
+    for iz in range(len(k_kms)):
+        if coeff[-1] <= fam["null"]:
+            out.append(np.ones_like(k_kms[iz]))
+            continue
+        xz = np.log((1 + zs[iz]) / (1 + fam["z0"]))
+        f_agn = np.exp(np.polyval(coeff, xz))
+        out.append(1 + agn_delta(agn, zs[iz], k_kms[iz]) * f_agn)
+    return out
+
+
 # ---------------------------------------------------------------------------
 # Theory (stages 1, 2 call, 3, 5a/5b)
 # ---------------------------------------------------------------------------
@@ -432,10 +463,16 @@ class OracleTheory(object):
         else:
             ic = np.ones(nz)
 
+        if cont.get("agn") is not None and "ln_AGN" in fam:
+            agn = agn_contamination(cont["agn"], fam["ln_AGN"], z, k_kms, pvalues)
+        else:
+            agn = np.ones(nz)
+
         out = []
         for iz in range(nz):
-            # lya_theory.py:778-784
-            out.append((hcd[iz] * mul[iz] * ic[iz] * p_emu[iz] + add[iz]) * syst[iz])
+            # lya_theory.py:778-784 (with the multiplicative AGN term of the older
+            # mult_cont_total = metals * HCD * SN * AGN * IC, model_contaminants.py:259-262)
+            out.append((hcd[iz] * mul[iz] * agn[iz] * ic[iz] * p_emu[iz] + add[iz]) * syst[iz])
         if parts:
             return out, blob, call, {"p_emu": p_emu, "mul": mul, "add": add, "hcd": hcd, "syst": syst}
         return out, blob, call

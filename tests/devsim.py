@@ -111,6 +111,8 @@ def simulate(cfg, F, x, zmask=None, apply_hull=True):
                     2 * a3 * a2 * gmm * r * tab[cc.COL_T3A, s] + 2 * a3 * a2 * gmm * tab[cc.COL_T3BC, s])
             else:
                 mult = 1 + q[4] / om * np.exp(q[5] * k) + q[6] / om * tab[cc.COL_T1, s] * np.exp(-q[7] * k)
+            if cfg.get("has_agn"):
+                mult = mult * (1 + (q[18] if q[19] > 0 else 0.0) * tab[cc.COL_AGN, s])
             hcd = (1 + q[16]) + q[12] * tab[cc.COL_D1, s] + q[13] * tab[cc.COL_D2, s] + q[14] * tab[cc.COL_D3, s] + q[15] * tab[cc.COL_D4, s]
             add = q[10] ** 2 * tab[cc.COL_KT, s] * np.exp(-q[11] ** 2 * k * k)
             res = 1 + (q[17] if cfg["apply_resolution"] else 0.0) * tab[cc.COL_Q, s]

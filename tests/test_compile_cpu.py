@@ -39,3 +39,35 @@ def test_compiled_tables_reproduce_reference(golden, name):
         for i in range(len(x)):
             e = ref["lnprob_zmask"][i]
             assert abs(simz["lnp"][i] - e) <= ATOL_LOGLIKE + 1e-11 * abs(e)
+
+
+def test_synthetic_c3_with_agn_compiles_to_the_oracle():
+    """full nuisance set incl. the optional AGN term: compiled tables (NumPy mirror) vs oracle"""
+    from cup1d_b200 import synth
+    from oracle.model import OracleLikelihood
+
+    emu = synth.synth_nn_emulator(seed=13, suite="nyx", ndeg=6, nhidden=3, max_neurons=24, head=12)
+    spec = synth.build_spec(emu, grid="dr1", rebin_k=4, full_cov=True, vary_nrun=True, nz_igm=6, hcd_const=True,
+                            gauss_priors=True, agn=True, seed=14, nz=5, nk=20)
+    ora = OracleLikelihood(spec)
+    xt = synth.truth_point(spec)
+    synth.attach_mock_data(spec, np.concatenate(ora.get_p1d_kms(values=xt)[0]))
+    ora = OracleLikelihood(spec)
+    cfg, F = compile_spec(spec)
+    assert cfg["has_agn"] == 1 and cfg["uniform_k"] == 1
+    x = np.concatenate([synth.walkers_ball(spec, 4, seed=0), synth.walkers_sweep(spec, 12, seed=3, frac_out=0.1)])
+    # switch the AGN term off for some walkers through its null rule (constant coefficient <= -5.5)
+    ia = spec["params"]["names"].index("ln_AGN_0")
+    x[5, ia] = 0.0
+    sim = simulate(cfg, F, x)
+    exp = ora.log_prob_and_blobs_many(x)
+    ok = exp[:, 0] > -1e99
+    assert np.array_equal(sim["lnp"][~ok], exp[~ok, 0])
+    assert np.max(np.abs(sim["lnp"][ok] - exp[ok, 0]) / np.maximum(1.0, np.abs(exp[ok, 0]))) < 1e-11
+    # the AGN term matters: removing it changes the model
+    spec2 = dict(spec)
+    spec2["cont"] = dict(spec["cont"])
+    spec2["cont"]["agn"] = None
+    p_with = np.concatenate(ora.get_p1d_kms(values=x[0])[0])
+    p_without = np.concatenate(OracleLikelihood(spec2).get_p1d_kms(values=x[0])[0])
+    assert np.max(np.abs(p_with / p_without - 1)) > 1e-4

@@ -58,3 +58,20 @@ def test_fig6_hcd_rogers():
         vals["HCD_const"] = om.nulled_value(fam_c, z, None)
         got = om.hcd_rogers_contamination(ROGERS, vals, z, [k])[0]
         assert np.max(np.abs(got - ref["y%d" % ii])) <= 4e-16
+
+
+def test_agn_template_against_reference_model():
+    """the reference's own AGN_Model.get_contamination (tools/make_golden.py agn_kat)"""
+    from cup1d_b200.synth import AGN_TABLE
+
+    ref = np.load(os.path.join(GOLDEN_DIR, "agn_kat.npz"))
+    np.testing.assert_array_equal(ref["agn_z"], AGN_TABLE[:, 0])
+    np.testing.assert_array_equal(ref["agn_expansion"], AGN_TABLE[:, 1:])
+    agn = {"z": ref["agn_z"], "expansion": ref["agn_expansion"]}
+    k = ref["k"]
+    for case, exp in zip(ref["cases"], ref["out"]):
+        z, n = case[0], int(case[1])
+        fam = {"ztype": "pivot", "otype": "exp", "znodes": np.zeros(0), "coeffs": case[2 : 2 + n],
+               "param_idx": np.full(n, -1), "z0": float(ref["z0"]), "null": float(ref["null"]), "zmax": np.nan}
+        got = om.agn_contamination(agn, fam, np.array([z]), [k], None)[0]
+        assert np.max(np.abs(got - exp)) <= 1e-15

@@ -193,6 +193,27 @@ CONFIGS = {
     "global_all": lambda: make("global_all", RefMLPEmulator(small_nn(27, "mpg"), "synthetic_mpg_nn", "mpg"), "chab", rebin_k=1, seed=700, fit_type="global_all", use_ic=False, n=(8, 6, 2), width=0.05),
 }
 
+def make_agn_kat():
+    """AGN_Model.get_contamination of the reference (AGN_model.py:93-120) on a few (z, coeff)"""
+    rh.setup()
+    from cup1d.contaminants.AGN_model import AGN_Model
+
+    k = np.linspace(1e-3, 0.04, 200)
+    cases, outs = [], []
+    for z in (2.0, 2.2, 3.0, 3.7, 4.2, 4.4):
+        for coeff in ([0.0, -1.5], [0.8, -0.3], [-2.0], [0.0, -5.5], [0.3, -6.0]):
+            m = AGN_Model(ln_AGN_coeff=list(coeff))
+            c = m.get_contamination(z, k)
+            cases.append([z, len(coeff)] + list(coeff) + [0.0] * (2 - len(coeff)))
+            outs.append(np.ones_like(k) * c)
+    m = AGN_Model()
+    np.savez_compressed(os.path.join(OUT, "agn_kat.npz"), k=k, cases=np.array(cases), out=np.array(outs),
+                        agn_z=m.AGN_z, agn_expansion=m.AGN_expansion, null=m.null_value, z0=m.z_0)
+    print("agn_kat          %d cases" % len(cases))
+
+
+CONFIGS["agn_kat"] = make_agn_kat
+
 if __name__ == "__main__":
     assert rh.available(), "needs /root/reference"
     todo = sys.argv[1:] or list(CONFIGS)
