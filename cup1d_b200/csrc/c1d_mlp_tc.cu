@@ -3,9 +3,9 @@
 // (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulation in TMEM).
 //
 // One persistent CTA per SM, 6 warps:
-//   warps 0-3  one thread per row / TMEM lane: first layer on CUDA cores (fp64), per-layer
-//              epilogue TMEM -> registers -> bias + LeakyReLU -> hi/lo split -> next A operand,
-//              last layer (-> polynomial coefficients) on CUDA cores in fp64
+//   warps 0-3  one thread per row / TMEM lane: input normalisation, per-layer
+//              epilogue TMEM -> registers -> bias + LeakyReLU -> hi/lo split -> next A operand;
+//              every layer, including 6->10 and 50->6, is a tensor-core GEMM
 //   warp 4     TMEM allocation; lane 0 issues every tcgen05.mma and tcgen05.commit
 //   warp 5     lane 0 streams the pre-swizzled weight images with cp.async.bulk (TMA bulk copy)
 //              through a 3-stage mbarrier ring
@@ -16,6 +16,7 @@
 //   B_hi, B_lo  shared memory ring, one (layer, n-block<=128, k-chunk) unit per stage
 //   D      tensor memory columns [0, 256)
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -54,19 +55,19 @@ struct TcParams {
   const uint8_t* wimg;
   const TcUnit* units;
   const float* bias;        // tensor layers, padded, concatenated
-  const double *w_first, *b_first, *w_last, *b_last;
-  const double *emu_lo, *emu_hi;
+  const double *emu_lo, *emu_rng_inv;  // input normalisation: (x - lo) * 1/(hi - lo) - 0.5
   int n_units, n_tl;
-  int n_in, first_out, last_in, last_out;
+  int n_in, last_out;
   int tl_npad[TC_MAX_TL];
   int tl_bias_off[TC_MAX_TL];
   int tl_unit_begin[TC_MAX_TL + 1];
   double slope;
+  int debug;  // C1D_TC_DEBUG=1: block 0 prints per-phase cycle counts of its second tile
 };
 
 struct TcState {
   TcParams p;
-  void *d_wimg, *d_units, *d_bias, *d_wfirst, *d_bfirst, *d_wlast, *d_blast;
+  void *d_wimg, *d_units, *d_bias, *d_rng_inv;
   bool ready;
 };
 
@@ -202,6 +203,7 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
   TcUnit* units = reinterpret_cast<TcUnit*>(gen_base + (bar0 + TC_BAR_BYTES - base));
 
+  __shared__ long long dbg_t[2 * TC_MAX_TL + 2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < p.n_units; i += TC_THREADS) units[i] = p.units[i];
   if (tid == 0) {
@@ -232,47 +234,40 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
     uint32_t d_phase = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t grow = tile * TC_ROWS + row;
-      // ---- first layer on CUDA cores, fp64 ----
-      double xin[C1D_MAX_EMU];
-#pragma unroll
-      for (int j = 0; j < C1D_MAX_EMU; ++j) {
-        double xv = (grow < nrows && j < p.n_in) ? emu_in[grow * C1D_MAX_EMU + j] : 0.0;
-        xin[j] = (j < p.n_in) ? (xv - p.emu_lo[j]) / (p.emu_hi[j] - p.emu_lo[j]) - 0.5 : 0.0;
-      }
-      const int fo_pad = (p.first_out + 15) & ~15;
-      for (int col0 = 0; col0 < fo_pad; col0 += 16) {
+      const bool dbg = p.debug && blockIdx.x == 0 && tid == 0 && tile == (int64_t)gridDim.x;
+      long long tq0 = dbg ? clock64() : 0;
+      // ---- normalised inputs -> A operand of the first layer (k padded to 16 with zeros) ----
+      {
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          int n = col0 + i;
-          double acc = 0.0;
-          if (n < p.first_out) {
-            acc = __ldg(p.b_first + n);
-#pragma unroll
-            for (int j = 0; j < C1D_MAX_EMU; ++j)
-              if (j < p.n_in) acc = fma(__ldg(p.w_first + n * p.n_in + j), xin[j], acc);
-            acc = (acc > 0.0) ? acc : p.slope * acc;
+        for (int j = 0; j < 16; ++j) {
+          double xn = 0.0;
+          if (j < C1D_MAX_EMU && j < p.n_in) {
+            const double xv = (grow < nrows) ? emu_in[grow * C1D_MAX_EMU + j] : 0.0;
+            xn = (xv - __ldg(p.emu_lo + j)) * __ldg(p.emu_rng_inv + j) - 0.5;
           }
-          v[i] = (float)acc;
+          v[j] = (float)xn;
         }
-        store_act16(a_smem, tmem_lane, row, col0, v);
+        store_act16(a_smem, tmem_lane, row, 0, v);
       }
       fence_async_smem();
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(bar_aready);
+      if (dbg) dbg_t[0] = clock64() - tq0;
 
       for (int tl = 0; tl < p.n_tl; ++tl) {
+        long long tq1 = dbg ? clock64() : 0;
         mbar_wait(bar_dfull, d_phase);
         d_phase ^= 1;
         tc_fence_after();
+        long long tq2 = dbg ? clock64() : 0;
         const int npad = p.tl_npad[tl];
         const float* bias = p.bias + p.tl_bias_off[tl];
         if (tl < p.n_tl - 1) {
-          for (int col0 = 0; col0 < npad; col0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem_lane + (uint32_t)col0, r);
-            tc_wait_ld();
+          // TMEM -> registers is double buffered: the load of the next 16 columns is in flight
+          // while the current 16 are biased, activated, split and stored
+          auto process = [&](const uint32_t* r, int col0) {
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -280,38 +275,43 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
               v[i] = (t > 0.f) ? t : slope * t;
             }
             store_act16(a_smem, tmem_lane, row, col0, v);
+          };
+          uint32_t r0[16], r1[16];
+          tmem_ld16(tmem_lane, r0);
+          for (int col0 = 0; col0 < npad; col0 += 32) {
+            tc_wait_ld();
+            const bool more1 = col0 + 16 < npad;
+            if (more1) tmem_ld16(tmem_lane + (uint32_t)(col0 + 16), r1);
+            process(r0, col0);
+            if (more1) {
+              tc_wait_ld();
+              if (col0 + 32 < npad) tmem_ld16(tmem_lane + (uint32_t)(col0 + 32), r0);
+              process(r1, col0 + 16);
+            }
           }
           fence_async_smem();
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(bar_aready);
+          if (dbg) { dbg_t[1 + 2 * tl] = tq2 - tq1; dbg_t[2 + 2 * tl] = clock64() - tq2; }
         } else {
-          // ---- last tensor layer: activation, then the output layer on CUDA cores (fp64) ----
-          double acc[C1D_MAX_COEF];
-#pragma unroll
-          for (int o = 0; o < C1D_MAX_COEF; ++o) acc[o] = (o < p.last_out) ? __ldg(p.b_last + o) : 0.0;
-          for (int col0 = 0; col0 < npad; col0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem_lane + (uint32_t)col0, r);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              int k = col0 + i;
-              if (k < p.last_in) {
-                float t = __uint_as_float(r[i]) + __ldg(bias + k);
-                double a = (double)((t > 0.f) ? t : slope * t);
-#pragma unroll
-                for (int o = 0; o < C1D_MAX_COEF; ++o)
-                  if (o < p.last_out) acc[o] = fma(__ldg(p.w_last + o * p.last_in + k), a, acc[o]);
-              }
-            }
-          }
+          // ---- output layer: coefficients = D + bias (no activation) ----
+          uint32_t r[16];
+          tmem_ld16(tmem_lane, r);
+          tc_wait_ld();
           if (grow < nrows) {
 #pragma unroll
             for (int o = 0; o < C1D_MAX_COEF; ++o)
-              if (o < p.last_out) out[grow * out_stride + o] = acc[o];
+              if (o < p.last_out) out[grow * out_stride + o] = (double)(__uint_as_float(r[o]) + __ldg(bias + o));
           }
           tc_fence_before();
+          if (dbg) {
+            dbg_t[1 + 2 * tl] = tq2 - tq1;
+            dbg_t[2 + 2 * tl] = clock64() - tq2;
+            printf("tc tile cycles: layer0 %lld |", dbg_t[0]);
+            for (int q = 0; q <= tl; ++q) printf(" L%d mma-wait %lld epi %lld |", q, dbg_t[1 + 2 * q], dbg_t[2 + 2 * q]);
+            printf(" total %lld\n", clock64() - tq0);
+          }
         }
       }
     }
@@ -468,8 +468,7 @@ static inline float tf32_trunc(float x) {
 int c1d_tc_prepare(c1d_ctx* ctx) {
   const c1d_config& c = ctx->cfg;
   if (ctx->tc_state) { c1d_tc_destroy(ctx); }
-  // needs a CUDA-core first layer, >= 1 tensor layer and a CUDA-core output layer
-  if (c.emu_kind != 0 || c.n_layers < 3) return C1D_OK;
+  if (c.emu_kind != 0 || c.n_layers < 1) return C1D_OK;
   TcState* st = new TcState();
   memset(st, 0, sizeof(*st));
   ctx->tc_state = st;
@@ -490,16 +489,15 @@ int c1d_tc_prepare(c1d_ctx* ctx) {
 
   TcParams& p = st->p;
   p.n_in = c.layer_dims[0];
-  p.first_out = c.layer_dims[1];
-  p.last_in = c.layer_dims[L - 1];
   p.last_out = c.layer_dims[L];
-  p.n_tl = L - 2;
+  p.n_tl = L;  // every layer runs on the tensor cores
   p.slope = c.nn_slope;
+  p.debug = getenv("C1D_TC_DEBUG") ? 1 : 0;
   std::vector<TcUnit> units;
   std::vector<uint8_t> img;
   std::vector<float> bias;
   for (int tl = 0; tl < p.n_tl; ++tl) {
-    const int l = tl + 1;
+    const int l = tl;
     const int K = c.layer_dims[l], N = c.layer_dims[l + 1];
     const int npad = (N + 15) & ~15;
     p.tl_npad[tl] = npad;
@@ -548,12 +546,10 @@ int c1d_tc_prepare(c1d_ctx* ctx) {
     snprintf(ctx->err, sizeof(ctx->err), "tensor-core MLP: too many weight units (%d)", p.n_units);
     return C1D_ERR_ARG;
   }
-  // first / last layers as row-major [out][in] doubles
-  std::vector<double> wf((size_t)p.first_out * p.n_in), wl((size_t)p.last_out * p.last_in);
-  for (int n = 0; n < p.first_out; ++n)
-    for (int k = 0; k < p.n_in; ++k) wf[(size_t)n * p.n_in + k] = wat(0, n, k);
-  for (int n = 0; n < p.last_out; ++n)
-    for (int k = 0; k < p.last_in; ++k) wl[(size_t)n * p.last_in + k] = wat(L - 1, n, k);
+  std::vector<double> lo(c.n_emu), hi(c.n_emu), rinv(c.n_emu);
+  C1D_CUDA(ctx, cudaMemcpy(lo.data(), ctx->dev[C1D_F_EMU_LO], c.n_emu * sizeof(double), cudaMemcpyDeviceToHost));
+  C1D_CUDA(ctx, cudaMemcpy(hi.data(), ctx->dev[C1D_F_EMU_HI], c.n_emu * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int j = 0; j < c.n_emu; ++j) rinv[j] = 1.0 / (hi[j] - lo[j]);
 #define UP(dst, src, bytes)                                                   \
   do {                                                                        \
     C1D_CUDA(ctx, cudaMalloc(&(dst), (bytes) ? (bytes) : 16));                \
@@ -562,20 +558,13 @@ int c1d_tc_prepare(c1d_ctx* ctx) {
   UP(st->d_wimg, img.data(), img.size());
   UP(st->d_units, units.data(), units.size() * sizeof(TcUnit));
   UP(st->d_bias, bias.data(), bias.size() * sizeof(float));
-  UP(st->d_wfirst, wf.data(), wf.size() * sizeof(double));
-  UP(st->d_bfirst, &Bv[boff[0]], (size_t)p.first_out * sizeof(double));
-  UP(st->d_wlast, wl.data(), wl.size() * sizeof(double));
-  UP(st->d_blast, &Bv[boff[L - 1]], (size_t)p.last_out * sizeof(double));
+  UP(st->d_rng_inv, rinv.data(), rinv.size() * sizeof(double));
 #undef UP
   p.wimg = (const uint8_t*)st->d_wimg;
   p.units = (const TcUnit*)st->d_units;
   p.bias = (const float*)st->d_bias;
-  p.w_first = (const double*)st->d_wfirst;
-  p.b_first = (const double*)st->d_bfirst;
-  p.w_last = (const double*)st->d_wlast;
-  p.b_last = (const double*)st->d_blast;
   p.emu_lo = ctx->d.emu_lo;
-  p.emu_hi = ctx->d.emu_hi;
+  p.emu_rng_inv = (const double*)st->d_rng_inv;
   C1D_CUDA(ctx, cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
   st->ready = true;
   return C1D_OK;
@@ -585,7 +574,7 @@ int c1d_tc_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out
   TcState* st = (TcState*)ctx->tc_state;
   if (!st || !st->ready) {
     snprintf(ctx->err, sizeof(ctx->err),
-             "tensor-core emulator path unavailable (needs an NN emulator with >= 3 layers)");
+             "tensor-core emulator path unavailable (needs an NN emulator)");
     return C1D_ERR_STATE;
   }
   int64_t ntiles = (nrows + TC_ROWS - 1) / TC_ROWS;
@@ -599,8 +588,7 @@ int c1d_tc_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out
 void c1d_tc_destroy(c1d_ctx* ctx) {
   TcState* st = (TcState*)ctx->tc_state;
   if (!st) return;
-  cudaFree(st->d_wimg); cudaFree(st->d_units); cudaFree(st->d_bias); cudaFree(st->d_wfirst);
-  cudaFree(st->d_bfirst); cudaFree(st->d_wlast); cudaFree(st->d_blast);
+  cudaFree(st->d_wimg); cudaFree(st->d_units); cudaFree(st->d_bias); cudaFree(st->d_rng_inv);
   delete st;
   ctx->tc_state = nullptr;
 }
