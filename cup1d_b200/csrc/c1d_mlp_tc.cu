@@ -2,18 +2,18 @@
 // tcgen05.mma (kind::tf32) GEMMs over a 128-row tile of (walker, z) pairs, in 3xTF32
 // (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulation in TMEM).
 //
-// One persistent CTA per SM, 6 warps:
-//   warps 0-3  one thread per row / TMEM lane: input normalisation, per-layer
+// One persistent CTA per SM, 10 warps:
+//   warps 0-7  two threads per row / TMEM lane (alternate 16-column batches): input normalisation, per-layer
 //              epilogue TMEM -> registers -> bias + LeakyReLU -> hi/lo split -> next A operand;
 //              every layer, including 6->10 and 50->6, is a tensor-core GEMM
-//   warp 4     TMEM allocation; lane 0 issues every tcgen05.mma and tcgen05.commit
-//   warp 5     lane 0 streams the pre-swizzled weight images with cp.async.bulk (TMA bulk copy)
-//              through a 3-stage mbarrier ring
+//   warp 8     TMEM allocation; lane 0 issues every tcgen05.mma and tcgen05.commit
+//   warp 9     lane 0 streams the pre-swizzled weight images with cp.async.bulk (TMA bulk copy)
+//              through a 6-stage mbarrier ring of (layer, n-block <= 128, 16 k) units
 //
 // Operand placement (227 KB of shared memory cannot hold hi and lo of a 128 x 256 tile):
 //   A_hi   shared memory, K-major SWIZZLE_128B, 8 chunks of 32 k            (SS form)
 //   A_lo   tensor memory columns [256, 512), lane = row, column = k         (TS form)
-//   B_hi, B_lo  shared memory ring, one (layer, n-block<=128, k-chunk) unit per stage
+//   B_hi, B_lo  shared memory ring (K-major SWIZZLE_64B), one (layer, n-block<=128, 16 k) unit per stage
 //   D      tensor memory columns [0, 256)
 #include <math.h>
 #include <stdlib.h>
@@ -29,14 +29,21 @@ constexpr int TC_KCH = 32;                         // tf32 elements per 128-byte
 constexpr int TC_A_CHUNK_BYTES = TC_ROWS * 128;    // 16 KB
 constexpr int TC_MAX_KCHUNKS = 8;                  // K <= 256
 constexpr int TC_A_BYTES = TC_MAX_KCHUNKS * TC_A_CHUNK_BYTES;
-constexpr int TC_STAGE_BYTES = 32768;              // 128 rows x 128 B x (hi, lo)
-constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 192;
-constexpr int TC_MAX_UNITS = 64;
+#ifndef C1D_TC_BK
+#define C1D_TC_BK 32
+#endif
+constexpr int TC_BK = C1D_TC_BK;                   // k per weight unit: 32 (SWIZZLE_128B rows) or 16 (SWIZZLE_64B)
+constexpr int TC_STAGE_BYTES = 128 * TC_BK * 4 * 2;  // 128 rows x (hi, lo)
+constexpr int TC_STAGES = 98304 / TC_STAGE_BYTES;
+constexpr int TC_EPI_WARPS = 8;                    // two warps per TMEM lane quadrant
+constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 2);
+constexpr int TC_MMA_TID = 32 * TC_EPI_WARPS;      // lane 0 of the MMA warp
+constexpr int TC_LOAD_TID = 32 * (TC_EPI_WARPS + 1);
+constexpr int TC_MAX_UNITS = 96;
 constexpr int TC_MAX_TL = C1D_MAX_LAYERS;
 constexpr uint32_t TC_ALO_COL = 256;
 constexpr int TC_BAR_BYTES = 128;
-constexpr size_t TC_SMEM = 1024 + TC_A_BYTES + TC_STAGES * TC_STAGE_BYTES + TC_BAR_BYTES + TC_MAX_UNITS * 16;
+constexpr size_t TC_SMEM = 1024 + TC_A_BYTES + TC_STAGES * TC_STAGE_BYTES + TC_BAR_BYTES;
 static_assert(TC_SMEM <= 232448, "shared memory budget");
 
 struct TcUnit {
@@ -44,8 +51,8 @@ struct TcUnit {
   uint16_t rows;       // rows of the n-block (multiple of 16, <= 128)
   uint16_t dcol;       // first D column of the n-block
   uint8_t layer;       // tensor-layer index
-  uint8_t kchunk;      // which 32-wide k chunk of A
-  uint8_t ksteps;      // k-steps of 8 issued in this chunk
+  uint8_t kstep0;      // first k-step (of 8) of this unit
+  uint8_t ksteps;      // k-steps issued in this unit (1 or 2)
   uint8_t flags;       // 1 = first unit of its (layer, n-block), 2 = last unit of its layer
   uint32_t pad;
 };
@@ -53,7 +60,6 @@ static_assert(sizeof(TcUnit) == 16, "TcUnit layout");
 
 struct TcParams {
   const uint8_t* wimg;
-  const TcUnit* units;
   const float* bias;        // tensor layers, padded, concatenated
   const double *emu_lo, *emu_rng_inv;  // input normalisation: (x - lo) * 1/(hi - lo) - 0.5
   int n_units, n_tl;
@@ -62,12 +68,13 @@ struct TcParams {
   int tl_bias_off[TC_MAX_TL];
   int tl_unit_begin[TC_MAX_TL + 1];
   double slope;
+  TcUnit units[TC_MAX_UNITS];  // in the kernel-parameter constant bank: uniform loads for the MMA issuer
   int debug;  // C1D_TC_DEBUG=1: block 0 prints per-phase cycle counts of its second tile
 };
 
 struct TcState {
   TcParams p;
-  void *d_wimg, *d_units, *d_bias, *d_rng_inv;
+  void *d_wimg, *d_bias, *d_rng_inv;
   bool ready;
 };
 
@@ -121,6 +128,16 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
   d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
   return d;
 }
+// K-major, SWIZZLE_64B (64-byte rows: 16 tf32), 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                          // SWIZZLE_64B
+  return d;
+}
 // instruction descriptor: tf32 x tf32 -> f32, A and B K-major, M = 128
 __device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
@@ -164,6 +181,11 @@ __device__ __host__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t g)
   return (row >> 3) * 1024u + (row & 7u) * 128u + ((g ^ (row & 7u)) << 4);
 }
 
+// byte offset of (row, 16-byte group g in 0..3) inside a SWIZZLE_64B tile of 64-byte rows
+__device__ __host__ __forceinline__ uint32_t sw64_off(uint32_t row, uint32_t g) {
+  return (row >> 3) * 512u + (row & 7u) * 64u + ((g ^ ((row >> 1) & 3u)) << 4);
+}
+
 // split 16 fp32 activations into tf32 hi (to shared memory, swizzled) and lo (to TMEM)
 __device__ __forceinline__ void store_act16(uint32_t a_smem, uint32_t tmem_lane_base, uint32_t row, int col0, const float* v) {
   uint32_t hi[16], lo[16];
@@ -195,27 +217,24 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
   const uint32_t a_smem = base;
   const uint32_t b_smem = base + TC_A_BYTES;
   const uint32_t bar0 = b_smem + TC_STAGES * TC_STAGE_BYTES;
-  // barriers: b_full[s] at +0, b_empty[s] at +8*TC_STAGES, d_full, a_ready, then the TMEM pointer
+  // barriers: b_full[s], b_empty[s], d_full, a_ready, then the TMEM pointer
   const uint32_t bar_bfull = bar0, bar_bempty = bar0 + 8 * TC_STAGES;
   const uint32_t bar_dfull = bar0 + 16 * TC_STAGES, bar_aready = bar_dfull + 8;
   const uint32_t tmem_slot = bar_aready + 8;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
-  TcUnit* units = reinterpret_cast<TcUnit*>(gen_base + (bar0 + TC_BAR_BYTES - base));
 
-  __shared__ long long dbg_t[2 * TC_MAX_TL + 2];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < p.n_units; i += TC_THREADS) units[i] = p.units[i];
+  const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_bfull + 8 * s, 1);
       mbar_init(bar_bempty + 8 * s, 1);
     }
     mbar_init(bar_dfull, 1);
-    mbar_init(bar_aready, 128);
+    mbar_init(bar_aready, 32 * TC_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == TC_EPI_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -227,17 +246,20 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
   const int64_t ntiles = (nrows + TC_ROWS - 1) / TC_ROWS;
   const float slope = (float)p.slope;
 
-  if (warp < 4) {
-    // ============================ row owners / epilogue ============================
-    const uint32_t row = (uint32_t)tid;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+  if (warp < TC_EPI_WARPS) {
+    // ===================== row owners / epilogue: 2 warps per lane quadrant =====================
+    // warp w works on TMEM lanes 32 (w & 3) .. +31 (one row per thread) and on the 16-column
+    // batches of parity (w >> 2)
+    const uint32_t quad = (uint32_t)warp & 3u, half = (uint32_t)warp >> 2;
+    const uint32_t row = quad * 32u + ((uint32_t)tid & 31u);
+    const uint32_t tmem_lane = tmem_base + ((quad * 32u) << 16);
     uint32_t d_phase = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t grow = tile * TC_ROWS + row;
       const bool dbg = p.debug && blockIdx.x == 0 && tid == 0 && tile == (int64_t)gridDim.x;
-      long long tq0 = dbg ? clock64() : 0;
+      long long tq0 = dbg ? clock64() : 0, t_mma = 0, t_epi = 0;
       // ---- normalised inputs -> A operand of the first layer (k padded to 16 with zeros) ----
-      {
+      if (half == 0) {
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -254,7 +276,6 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(bar_aready);
-      if (dbg) dbg_t[0] = clock64() - tq0;
 
       for (int tl = 0; tl < p.n_tl; ++tl) {
         long long tq1 = dbg ? clock64() : 0;
@@ -277,92 +298,104 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
             store_act16(a_smem, tmem_lane, row, col0, v);
           };
           uint32_t r0[16], r1[16];
-          tmem_ld16(tmem_lane, r0);
-          for (int col0 = 0; col0 < npad; col0 += 32) {
+          const int c_first = 16 * (int)half;
+          if (c_first < npad) tmem_ld16(tmem_lane + (uint32_t)c_first, r0);
+          for (int col0 = c_first; col0 < npad; col0 += 64) {
             tc_wait_ld();
-            const bool more1 = col0 + 16 < npad;
-            if (more1) tmem_ld16(tmem_lane + (uint32_t)(col0 + 16), r1);
+            const bool more1 = col0 + 32 < npad;
+            if (more1) tmem_ld16(tmem_lane + (uint32_t)(col0 + 32), r1);
             process(r0, col0);
             if (more1) {
               tc_wait_ld();
-              if (col0 + 32 < npad) tmem_ld16(tmem_lane + (uint32_t)(col0 + 32), r0);
-              process(r1, col0 + 16);
+              if (col0 + 64 < npad) tmem_ld16(tmem_lane + (uint32_t)(col0 + 64), r0);
+              process(r1, col0 + 32);
             }
           }
           fence_async_smem();
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(bar_aready);
-          if (dbg) { dbg_t[1 + 2 * tl] = tq2 - tq1; dbg_t[2 + 2 * tl] = clock64() - tq2; }
         } else {
           // ---- output layer: coefficients = D + bias (no activation) ----
-          uint32_t r[16];
-          tmem_ld16(tmem_lane, r);
-          tc_wait_ld();
-          if (grow < nrows) {
+          if (half == 0) {
+            uint32_t r[16];
+            tmem_ld16(tmem_lane, r);
+            tc_wait_ld();
+            if (grow < nrows) {
 #pragma unroll
-            for (int o = 0; o < C1D_MAX_COEF; ++o)
-              if (o < p.last_out) out[grow * out_stride + o] = (double)(__uint_as_float(r[o]) + __ldg(bias + o));
+              for (int o = 0; o < C1D_MAX_COEF; ++o)
+                if (o < p.last_out) out[grow * out_stride + o] = (double)(__uint_as_float(r[o]) + __ldg(bias + o));
+            }
           }
           tc_fence_before();
-          if (dbg) {
-            dbg_t[1 + 2 * tl] = tq2 - tq1;
-            dbg_t[2 + 2 * tl] = clock64() - tq2;
-            printf("tc tile cycles: layer0 %lld |", dbg_t[0]);
-            for (int q = 0; q <= tl; ++q) printf(" L%d mma-wait %lld epi %lld |", q, dbg_t[1 + 2 * q], dbg_t[2 + 2 * q]);
-            printf(" total %lld\n", clock64() - tq0);
-          }
         }
+        if (dbg) { t_mma += tq2 - tq1; t_epi += clock64() - tq2; }
       }
+      if (dbg) printf("tc tile cycles: mma-wait %lld  epilogue %lld  total %lld\n", t_mma, t_epi, clock64() - tq0);
     }
-  } else if (tid == 128) {
+  } else if (warp == TC_EPI_WARPS) {
     // ================================ MMA issuer ================================
+    // the whole warp runs the loop (warp-uniform values stay in uniform registers, the unit
+    // table comes from the kernel-parameter constant bank); lane 0 issues
+    const bool leader = (tid & 31) == 0;
     uint32_t a_phase = 0, stage = 0, b_phase = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int tl = 0; tl < p.n_tl; ++tl) {
         mbar_wait(bar_aready, a_phase);
         a_phase ^= 1;
         tc_fence_after();
-        for (int u = p.tl_unit_begin[tl]; u < p.tl_unit_begin[tl + 1]; ++u) {
-          const TcUnit un = units[u];
+        const int u_end = p.tl_unit_begin[tl + 1];
+        for (int u = p.tl_unit_begin[tl]; u < u_end; ++u) {
+          const uint32_t rows = p.units[u].rows, dcol = p.units[u].dcol;
+          const uint32_t kstep0 = p.units[u].kstep0, nks = p.units[u].ksteps, uflags = p.units[u].flags;
           mbar_wait(bar_bfull + 8 * stage, b_phase);
           tc_fence_after();
           const uint32_t sb = b_smem + stage * TC_STAGE_BYTES;
-          const uint32_t idesc = make_idesc_tf32(un.rows);
-          const uint32_t d_tmem = tmem_base + un.dcol;
-          for (uint32_t ks = 0; ks < un.ksteps; ++ks) {
-            const uint64_t a_hi = make_desc_sw128(a_smem + un.kchunk * TC_A_CHUNK_BYTES + ks * 32u);
-            const uint64_t b_hi = make_desc_sw128(sb + ks * 32u);
-            const uint64_t b_lo = make_desc_sw128(sb + (uint32_t)un.rows * 128u + ks * 32u);
-            const uint32_t a_lo = tmem_base + TC_ALO_COL + (uint32_t)un.kchunk * TC_KCH + ks * 8u;
-            const uint32_t acc0 = ((un.flags & 1) && ks == 0) ? 0u : 1u;
-            mma_ts(d_tmem, a_lo, b_hi, idesc, acc0);  // small terms first
-            mma_ss(d_tmem, a_hi, b_lo, idesc, 1u);
-            mma_ss(d_tmem, a_hi, b_hi, idesc, 1u);
+          const uint32_t idesc = make_idesc_tf32(rows);
+          const uint32_t d_tmem = tmem_base + dcol;
+          for (uint32_t ks = 0; ks < nks; ++ks) {
+            const uint32_t kg = kstep0 + ks;  // global k-step: A chunk kg / 4, 32 B steps inside
+            const uint64_t a_hi = make_desc_sw128(a_smem + (kg >> 2) * TC_A_CHUNK_BYTES + (kg & 3u) * 32u);
+            const uint64_t b_hi = (TC_BK == 32) ? make_desc_sw128(sb + ks * 32u) : make_desc_sw64(sb + ks * 32u);
+            const uint64_t b_lo = (TC_BK == 32) ? make_desc_sw128(sb + rows * 128u + ks * 32u)
+                                                : make_desc_sw64(sb + rows * 64u + ks * 32u);
+            const uint32_t a_lo = tmem_base + TC_ALO_COL + kg * 8u;
+            const uint32_t acc0 = ((uflags & 1) && ks == 0) ? 0u : 1u;
+            if (leader) {
+              mma_ts(d_tmem, a_lo, b_hi, idesc, acc0);  // small terms first
+              mma_ss(d_tmem, a_hi, b_lo, idesc, 1u);
+              mma_ss(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
           }
-          tc_commit(bar_bempty + 8 * stage);
-          if (un.flags & 2) tc_commit(bar_dfull);
+          if (leader) {
+            tc_commit(bar_bempty + 8 * stage);
+            if (uflags & 2) tc_commit(bar_dfull);
+          }
+          __syncwarp();
           if (++stage == TC_STAGES) { stage = 0; b_phase ^= 1; }
         }
       }
     }
-  } else if (tid == 160) {
+  } else {
     // ============================== weight streamer ==============================
+    const bool leader = (tid & 31) == 0;
     uint32_t stage = 0, phase = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int u = 0; u < p.n_units; ++u) {
-        const TcUnit un = units[u];
+        const uint32_t bytes = (uint32_t)p.units[u].rows * (uint32_t)(TC_BK * 8);
         mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
-        const uint32_t bytes = (uint32_t)un.rows * 256u;
-        mbar_expect_tx(bar_bfull + 8 * stage, bytes);
-        bulk_g2s(b_smem + stage * TC_STAGE_BYTES, p.wimg + un.w_off, bytes, bar_bfull + 8 * stage);
+        if (leader) {
+          mbar_expect_tx(bar_bfull + 8 * stage, bytes);
+          bulk_g2s(b_smem + stage * TC_STAGE_BYTES, p.wimg + p.units[u].w_off, bytes, bar_bfull + 8 * stage);
+        }
+        __syncwarp();
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_EPI_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -413,7 +446,9 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
       for (int g = 0; g < 8; ++g) {
         uint32_t w[4];
         for (int i = 0; i < 4; ++i) w[i] = __float_as_uint(B[n * 32 + 4 * g + i]) & 0xffffe000u;
-        uint32_t addr = b_smem + sw128_off(n, g);
+        // mode 2: two SWIZZLE_64B chunks of 16 k, each N rows x 64 B
+        uint32_t addr = (mode == 2) ? b_smem + (uint32_t)(g >> 2) * (uint32_t)N * 64u + sw64_off(n, g & 3)
+                                    : b_smem + sw128_off(n, g);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
       }
     fence_async_smem();
@@ -425,8 +460,9 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
   if (tid == 128) {
     const uint32_t idesc = make_idesc_tf32(N);
     for (uint32_t ks = 0; ks < 4; ++ks) {
-      const uint64_t bd = make_desc_sw128(b_smem + ks * 32u);
-      if (mode == 0)
+      const uint64_t bd = (mode == 2) ? make_desc_sw64(b_smem + (ks >> 1) * (uint32_t)N * 64u + (ks & 1u) * 32u)
+                                      : make_desc_sw128(b_smem + ks * 32u);
+      if (mode == 0 || mode == 2)
         mma_ss(tmem_base, make_desc_sw128(a_smem + ks * 32u), bd, idesc, ks ? 1u : 0u);
       else
         mma_ts(tmem_base, tmem_base + TC_ALO_COL + ks * 8u, bd, idesc, ks ? 1u : 0u);
@@ -504,7 +540,7 @@ int c1d_tc_prepare(c1d_ctx* ctx) {
     p.tl_bias_off[tl] = (int)bias.size();
     for (int n = 0; n < npad; ++n) bias.push_back(n < N ? (float)Bv[boff[l] + n] : 0.f);
     p.tl_unit_begin[tl] = (int)units.size();
-    const int nkc = (K + TC_KCH - 1) / TC_KCH;
+    const int nkc = (K + TC_BK - 1) / TC_BK;
     int blocks[2], nblk = 1;
     if (npad <= 128) blocks[0] = npad;
     else { blocks[0] = ((npad / 2) + 15) & ~15; blocks[1] = npad - blocks[0]; nblk = 2; }
@@ -518,23 +554,24 @@ int c1d_tc_prepare(c1d_ctx* ctx) {
         u.rows = (uint16_t)rows;
         u.dcol = (uint16_t)n0;
         u.layer = (uint8_t)tl;
-        u.kchunk = (uint8_t)kc;
-        int kleft = K - kc * TC_KCH;
-        if (kleft > TC_KCH) kleft = TC_KCH;
+        u.kstep0 = (uint8_t)(kc * (TC_BK / 8));
+        int kleft = K - kc * TC_BK;
+        if (kleft > TC_BK) kleft = TC_BK;
         u.ksteps = (uint8_t)((kleft + 7) / 8);
         u.flags = (uint8_t)((kc == 0 ? 1 : 0) | ((b == nblk - 1 && kc == nkc - 1) ? 2 : 0));
         units.push_back(u);
         size_t o = img.size();
-        img.resize(o + (size_t)rows * 256, 0);
+        img.resize(o + (size_t)rows * TC_BK * 8, 0);
         for (int n = 0; n < rows; ++n)
-          for (int k = 0; k < TC_KCH; ++k) {
-            int gn = n0 + n, gk = kc * TC_KCH + k;
+          for (int k = 0; k < TC_BK; ++k) {
+            int gn = n0 + n, gk = kc * TC_BK + k;
             double w = (gn < N && gk < K) ? wat(l, gn, gk) : 0.0;
             float hi = tf32_trunc((float)w);
             float lo = (float)(w - (double)hi);
-            uint32_t off = sw128_off((uint32_t)n, (uint32_t)k >> 2) + ((uint32_t)k & 3u) * 4u;
+            uint32_t off = ((TC_BK == 32) ? sw128_off((uint32_t)n, (uint32_t)k >> 2) : sw64_off((uint32_t)n, (uint32_t)k >> 2)) +
+                           ((uint32_t)k & 3u) * 4u;
             memcpy(&img[o + off], &hi, 4);
-            memcpy(&img[o + (size_t)rows * 128 + off], &lo, 4);
+            memcpy(&img[o + (size_t)rows * TC_BK * 4 + off], &lo, 4);
           }
       }
       n0 += rows;
@@ -556,12 +593,11 @@ int c1d_tc_prepare(c1d_ctx* ctx) {
     C1D_CUDA(ctx, cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice)); \
   } while (0)
   UP(st->d_wimg, img.data(), img.size());
-  UP(st->d_units, units.data(), units.size() * sizeof(TcUnit));
+  for (size_t q = 0; q < units.size(); ++q) p.units[q] = units[q];
   UP(st->d_bias, bias.data(), bias.size() * sizeof(float));
   UP(st->d_rng_inv, rinv.data(), rinv.size() * sizeof(double));
 #undef UP
   p.wimg = (const uint8_t*)st->d_wimg;
-  p.units = (const TcUnit*)st->d_units;
   p.bias = (const float*)st->d_bias;
   p.emu_lo = ctx->d.emu_lo;
   p.emu_rng_inv = (const double*)st->d_rng_inv;
@@ -588,14 +624,14 @@ int c1d_tc_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out
 void c1d_tc_destroy(c1d_ctx* ctx) {
   TcState* st = (TcState*)ctx->tc_state;
   if (!st) return;
-  cudaFree(st->d_wimg); cudaFree(st->d_units); cudaFree(st->d_bias); cudaFree(st->d_rng_inv);
+  cudaFree(st->d_wimg); cudaFree(st->d_bias); cudaFree(st->d_rng_inv);
   delete st;
   ctx->tc_state = nullptr;
 }
 
 // D[128, N] = tf32(A[128, 32]) . tf32(B[N, 32])^T through one tcgen05.mma chain; host pointers.
 extern "C" int c1d_tc_selftest(int device, const float* A_host, const float* B_host, float* D_host, int N, int mode) {
-  if (!A_host || !B_host || !D_host || N < 16 || N > 256 || (N % 16) || (mode != 0 && mode != 1)) return C1D_ERR_ARG;
+  if (!A_host || !B_host || !D_host || N < 16 || N > 256 || (N % 16) || (mode < 0 || mode > 2)) return C1D_ERR_ARG;
   if (cudaSetDevice(device) != cudaSuccess) return C1D_ERR_CUDA;
   float *dA = nullptr, *dB = nullptr, *dD = nullptr;
   int rc = C1D_OK;

@@ -12,7 +12,7 @@ def _tf32(x):
     return b.view(np.float32)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("N", [16, 80, 128, 256])
 def test_single_mma_chain(mode, N):
     from cup1d_b200 import _abi
