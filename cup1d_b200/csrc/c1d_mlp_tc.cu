@@ -30,11 +30,16 @@ constexpr int TC_A_CHUNK_BYTES = TC_ROWS * 128;    // 16 KB
 constexpr int TC_MAX_KCHUNKS = 8;                  // K <= 256
 constexpr int TC_A_BYTES = TC_MAX_KCHUNKS * TC_A_CHUNK_BYTES;
 #ifndef C1D_TC_BK
-#define C1D_TC_BK 32
+#define C1D_TC_BK 16
+#endif
+#ifndef C1D_TC_NBLK
+#define C1D_TC_NBLK 256
 #endif
 constexpr int TC_BK = C1D_TC_BK;                   // k per weight unit: 32 (SWIZZLE_128B rows) or 16 (SWIZZLE_64B)
-constexpr int TC_STAGE_BYTES = 128 * TC_BK * 4 * 2;  // 128 rows x (hi, lo)
+constexpr int TC_NBLK = C1D_TC_NBLK;               // widest n-block = N of one tcgen05.mma (128 or 256)
+constexpr int TC_STAGE_BYTES = TC_NBLK * TC_BK * 4 * 2;  // rows x (hi, lo)
 constexpr int TC_STAGES = 98304 / TC_STAGE_BYTES;
+static_assert(TC_STAGES >= 2, "weight ring too shallow");
 constexpr int TC_EPI_WARPS = 8;                    // two warps per TMEM lane quadrant
 constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 2);
 constexpr int TC_MMA_TID = 32 * TC_EPI_WARPS;      // lane 0 of the MMA warp
@@ -542,7 +547,7 @@ int c1d_tc_prepare(c1d_ctx* ctx) {
     p.tl_unit_begin[tl] = (int)units.size();
     const int nkc = (K + TC_BK - 1) / TC_BK;
     int blocks[2], nblk = 1;
-    if (npad <= 128) blocks[0] = npad;
+    if (npad <= TC_NBLK) blocks[0] = npad;
     else { blocks[0] = ((npad / 2) + 15) & ~15; blocks[1] = npad - blocks[0]; nblk = 2; }
     int n0 = 0;
     for (int b = 0; b < nblk; ++b) {
