@@ -37,9 +37,9 @@ constexpr int TC_A_BYTES = TC_MAX_KCHUNKS * TC_A_CHUNK_BYTES;
 #endif
 constexpr int TC_BK = C1D_TC_BK;                   // k per weight unit: 32 (SWIZZLE_128B rows) or 16 (SWIZZLE_64B)
 constexpr int TC_NBLK = C1D_TC_NBLK;               // widest n-block = N of one tcgen05.mma (128 or 256)
-constexpr int TC_STAGE_BYTES = TC_NBLK * TC_BK * 4 * 2;  // rows x (hi, lo)
-constexpr int TC_STAGES = 98304 / TC_STAGE_BYTES;
-static_assert(TC_STAGES >= 2, "weight ring too shallow");
+constexpr int TC_RING_BYTES = 98304;               // weight ring: units of different size packed back to back
+constexpr int TC_NBAR = 16;                        // mbarrier pairs, used round-robin by the units
+static_assert(TC_NBLK * TC_BK * 4 * 2 * 2 <= TC_RING_BYTES, "weight ring too small for two of the largest units");
 constexpr int TC_EPI_WARPS = 8;                    // two warps per TMEM lane quadrant
 constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 2);
 constexpr int TC_MMA_TID = 32 * TC_EPI_WARPS;      // lane 0 of the MMA warp
@@ -47,8 +47,8 @@ constexpr int TC_LOAD_TID = 32 * (TC_EPI_WARPS + 1);
 constexpr int TC_MAX_UNITS = 96;
 constexpr int TC_MAX_TL = C1D_MAX_LAYERS;
 constexpr uint32_t TC_ALO_COL = 256;
-constexpr int TC_BAR_BYTES = 128;
-constexpr size_t TC_SMEM = 1024 + TC_A_BYTES + TC_STAGES * TC_STAGE_BYTES + TC_BAR_BYTES;
+constexpr int TC_BAR_BYTES = 16 * TC_NBAR + 64;
+constexpr size_t TC_SMEM = 1024 + TC_A_BYTES + TC_RING_BYTES + TC_BAR_BYTES;
 static_assert(TC_SMEM <= 232448, "shared memory budget");
 
 struct TcUnit {
@@ -58,8 +58,11 @@ struct TcUnit {
   uint8_t layer;       // tensor-layer index
   uint8_t kstep0;      // first k-step (of 8) of this unit
   uint8_t ksteps;      // k-steps issued in this unit (1 or 2)
-  uint8_t flags;       // 1 = first unit of its (layer, n-block), 2 = last unit of its layer
-  uint32_t pad;
+  uint8_t flags;       // 1 = first unit of its (layer, n-block), 2 = last unit of its layer,
+                       // 4 = 32-k unit in SWIZZLE_128B rows (else 16-k unit in SWIZZLE_64B rows)
+  uint16_t ring_kb;    // offset of the unit in the weight ring, in KiB
+  uint8_t back;        // the streamer waits for the completion of the unit `back` places earlier (1..TC_NBAR)
+  uint8_t pad;
 };
 static_assert(sizeof(TcUnit) == 16, "TcUnit layout");
 
@@ -221,17 +224,18 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = base;
   const uint32_t b_smem = base + TC_A_BYTES;
-  const uint32_t bar0 = b_smem + TC_STAGES * TC_STAGE_BYTES;
+  const uint32_t bar0 = b_smem + TC_RING_BYTES;
   // barriers: b_full[s], b_empty[s], d_full, a_ready, then the TMEM pointer
-  const uint32_t bar_bfull = bar0, bar_bempty = bar0 + 8 * TC_STAGES;
-  const uint32_t bar_dfull = bar0 + 16 * TC_STAGES, bar_aready = bar_dfull + 8;
+  const uint32_t bar_bfull = bar0, bar_bempty = bar0 + 8 * TC_NBAR;
+  const uint32_t bar_dfull = bar0 + 16 * TC_NBAR, bar_aready = bar_dfull + 8;
   const uint32_t tmem_slot = bar_aready + 8;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
 
+  __shared__ long long dbg_t[2 * TC_MAX_TL];
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < TC_NBAR; ++s) {
       mbar_init(bar_bfull + 8 * s, 1);
       mbar_init(bar_bempty + 8 * s, 1);
     }
@@ -334,36 +338,42 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
           }
           tc_fence_before();
         }
-        if (dbg) { t_mma += tq2 - tq1; t_epi += clock64() - tq2; }
+        if (dbg) { t_mma += tq2 - tq1; t_epi += clock64() - tq2; dbg_t[2 * tl] = tq2 - tq1; dbg_t[2 * tl + 1] = clock64() - tq2; }
       }
-      if (dbg) printf("tc tile cycles: mma-wait %lld  epilogue %lld  total %lld\n", t_mma, t_epi, clock64() - tq0);
+      if (dbg) {
+        printf("tc tile cycles: mma-wait %lld  epilogue %lld  total %lld |", t_mma, t_epi, clock64() - tq0);
+        for (int q = 0; q < p.n_tl; ++q) printf(" L%d %lld/%lld", q, dbg_t[2 * q], dbg_t[2 * q + 1]);
+        printf("\n");
+      }
     }
   } else if (warp == TC_EPI_WARPS) {
     // ================================ MMA issuer ================================
     // the whole warp runs the loop (warp-uniform values stay in uniform registers, the unit
     // table comes from the kernel-parameter constant bank); lane 0 issues
     const bool leader = (tid & 31) == 0;
-    uint32_t a_phase = 0, stage = 0, b_phase = 0;
+    uint32_t a_phase = 0;
+    uint32_t g = 0;  // running unit count: barrier pair g % TC_NBAR, phase (g / TC_NBAR) & 1
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int tl = 0; tl < p.n_tl; ++tl) {
         mbar_wait(bar_aready, a_phase);
         a_phase ^= 1;
         tc_fence_after();
         const int u_end = p.tl_unit_begin[tl + 1];
-        for (int u = p.tl_unit_begin[tl]; u < u_end; ++u) {
+        for (int u = p.tl_unit_begin[tl]; u < u_end; ++u, ++g) {
           const uint32_t rows = p.units[u].rows, dcol = p.units[u].dcol;
           const uint32_t kstep0 = p.units[u].kstep0, nks = p.units[u].ksteps, uflags = p.units[u].flags;
+          const uint32_t stage = g % TC_NBAR, b_phase = (g / TC_NBAR) & 1u;
           mbar_wait(bar_bfull + 8 * stage, b_phase);
           tc_fence_after();
-          const uint32_t sb = b_smem + stage * TC_STAGE_BYTES;
+          const uint32_t sb = b_smem + (uint32_t)p.units[u].ring_kb * 1024u;
           const uint32_t idesc = make_idesc_tf32(rows);
           const uint32_t d_tmem = tmem_base + dcol;
           for (uint32_t ks = 0; ks < nks; ++ks) {
             const uint32_t kg = kstep0 + ks;  // global k-step: A chunk kg / 4, 32 B steps inside
             const uint64_t a_hi = make_desc_sw128(a_smem + (kg >> 2) * TC_A_CHUNK_BYTES + (kg & 3u) * 32u);
-            const uint64_t b_hi = (TC_BK == 32) ? make_desc_sw128(sb + ks * 32u) : make_desc_sw64(sb + ks * 32u);
-            const uint64_t b_lo = (TC_BK == 32) ? make_desc_sw128(sb + rows * 128u + ks * 32u)
-                                                : make_desc_sw64(sb + rows * 64u + ks * 32u);
+            const bool wide = (uflags & 4u) != 0;
+            const uint64_t b_hi = wide ? make_desc_sw128(sb + ks * 32u) : make_desc_sw64(sb + ks * 32u);
+            const uint64_t b_lo = wide ? make_desc_sw128(sb + rows * 128u + ks * 32u) : make_desc_sw64(sb + rows * 64u + ks * 32u);
             const uint32_t a_lo = tmem_base + TC_ALO_COL + kg * 8u;
             const uint32_t acc0 = ((uflags & 1) && ks == 0) ? 0u : 1u;
             if (leader) {
@@ -377,24 +387,28 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
             if (uflags & 2) tc_commit(bar_dfull);
           }
           __syncwarp();
-          if (++stage == TC_STAGES) { stage = 0; b_phase ^= 1; }
         }
       }
     }
   } else {
     // ============================== weight streamer ==============================
     const bool leader = (tid & 31) == 0;
-    uint32_t stage = 0, phase = 0;
+    uint32_t g = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      for (int u = 0; u < p.n_units; ++u) {
-        const uint32_t bytes = (uint32_t)p.units[u].rows * (uint32_t)(TC_BK * 8);
-        mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
+      for (int u = 0; u < p.n_units; ++u, ++g) {
+        const uint32_t bytes = (uint32_t)p.units[u].rows * ((p.units[u].flags & 4u) ? 256u : 128u);
+        const uint32_t back = p.units[u].back;
+        if (g >= back) {
+          // the bytes this unit overwrites (and its barrier pair) are free once unit g - back is done
+          const uint32_t d = g - back;
+          mbar_wait(bar_bempty + 8 * (d % TC_NBAR), (d / TC_NBAR) & 1u);
+        }
+        const uint32_t stage = g % TC_NBAR;
         if (leader) {
           mbar_expect_tx(bar_bfull + 8 * stage, bytes);
-          bulk_g2s(b_smem + stage * TC_STAGE_BYTES, p.wimg + p.units[u].w_off, bytes, bar_bfull + 8 * stage);
+          bulk_g2s(b_smem + (uint32_t)p.units[u].ring_kb * 1024u, p.wimg + p.units[u].w_off, bytes, bar_bfull + 8 * stage);
         }
         __syncwarp();
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   }
@@ -545,7 +559,10 @@ int c1d_tc_prepare(c1d_ctx* ctx) {
     p.tl_bias_off[tl] = (int)bias.size();
     for (int n = 0; n < npad; ++n) bias.push_back(n < N ? (float)Bv[boff[l] + n] : 0.f);
     p.tl_unit_begin[tl] = (int)units.size();
-    const int nkc = (K + TC_BK - 1) / TC_BK;
+    // narrow layers (N <= 128): 32-k units (fewer, longer units); wide layers: 16-k units so that one
+    // tcgen05.mma can span up to 256 columns within a 32 KB unit
+    const int bk = (npad <= 128) ? 32 : 16;
+    const int nkc = (K + bk - 1) / bk;
     int blocks[2], nblk = 1;
     if (npad <= TC_NBLK) blocks[0] = npad;
     else { blocks[0] = ((npad / 2) + 15) & ~15; blocks[1] = npad - blocks[0]; nblk = 2; }
@@ -559,24 +576,24 @@ int c1d_tc_prepare(c1d_ctx* ctx) {
         u.rows = (uint16_t)rows;
         u.dcol = (uint16_t)n0;
         u.layer = (uint8_t)tl;
-        u.kstep0 = (uint8_t)(kc * (TC_BK / 8));
-        int kleft = K - kc * TC_BK;
-        if (kleft > TC_BK) kleft = TC_BK;
+        u.kstep0 = (uint8_t)(kc * (bk / 8));
+        int kleft = K - kc * bk;
+        if (kleft > bk) kleft = bk;
         u.ksteps = (uint8_t)((kleft + 7) / 8);
-        u.flags = (uint8_t)((kc == 0 ? 1 : 0) | ((b == nblk - 1 && kc == nkc - 1) ? 2 : 0));
+        u.flags = (uint8_t)((kc == 0 ? 1 : 0) | ((b == nblk - 1 && kc == nkc - 1) ? 2 : 0) | (bk == 32 ? 4 : 0));
         units.push_back(u);
         size_t o = img.size();
-        img.resize(o + (size_t)rows * TC_BK * 8, 0);
+        img.resize(o + (size_t)rows * bk * 8, 0);
         for (int n = 0; n < rows; ++n)
-          for (int k = 0; k < TC_BK; ++k) {
-            int gn = n0 + n, gk = kc * TC_BK + k;
+          for (int k = 0; k < bk; ++k) {
+            int gn = n0 + n, gk = kc * bk + k;
             double w = (gn < N && gk < K) ? wat(l, gn, gk) : 0.0;
             float hi = tf32_trunc((float)w);
             float lo = (float)(w - (double)hi);
-            uint32_t off = ((TC_BK == 32) ? sw128_off((uint32_t)n, (uint32_t)k >> 2) : sw64_off((uint32_t)n, (uint32_t)k >> 2)) +
+            uint32_t off = ((bk == 32) ? sw128_off((uint32_t)n, (uint32_t)k >> 2) : sw64_off((uint32_t)n, (uint32_t)k >> 2)) +
                            ((uint32_t)k & 3u) * 4u;
             memcpy(&img[o + off], &hi, 4);
-            memcpy(&img[o + (size_t)rows * TC_BK * 4 + off], &lo, 4);
+            memcpy(&img[o + (size_t)rows * bk * 4 + off], &lo, 4);
           }
       }
       n0 += rows;
@@ -584,6 +601,30 @@ int c1d_tc_prepare(c1d_ctx* ctx) {
   }
   p.tl_unit_begin[p.n_tl] = (int)units.size();
   p.n_units = (int)units.size();
+  {
+    // pack the units of one tile back to back into the ring (every tile restarts at offset 0, so
+    // the placement is the same for all tiles) and find, for each unit, the most recent earlier
+    // unit of the cyclic sequence whose bytes it overwrites: the streamer waits for that one.
+    const int nu = p.n_units;
+    std::vector<int> off(nu), len(nu);
+    int cur = 0;
+    for (int u = 0; u < nu; ++u) {
+      len[u] = ((int)units[u].rows * ((units[u].flags & 4) ? 256 : 128) + 1023) & ~1023;
+      if (cur + len[u] > TC_RING_BYTES) cur = 0;
+      off[u] = cur;
+      cur += len[u];
+    }
+    for (int u = 0; u < nu; ++u) {
+      int back = TC_NBAR;  // at least: the previous user of this barrier pair
+      for (int b = 1; b < TC_NBAR; ++b) {
+        int v = ((u - b) % nu + nu) % nu;
+        if (off[v] < off[u] + len[u] && off[u] < off[v] + len[v]) { back = b; break; }
+      }
+      if (back > nu) back = nu;  // a tile has fewer units than barrier pairs: wait for this unit's previous use
+      units[u].ring_kb = (uint16_t)(off[u] / 1024);
+      units[u].back = (uint8_t)back;
+    }
+  }
   if (p.n_units > TC_MAX_UNITS) {
     snprintf(ctx->err, sizeof(ctx->err), "tensor-core MLP: too many weight units (%d)", p.n_units);
     return C1D_ERR_ARG;
