@@ -84,6 +84,7 @@ struct TcState {
   TcParams p;
   void *d_wimg, *d_bias, *d_rng_inv;
   bool ready;
+  int cluster;  // CTAs per cluster sharing the weight stream (C1D_TC_CLUSTER: 1, 2 or 4; default 1)
 };
 
 // ------------------------------------------------------------------------------------
@@ -116,6 +117,33 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// one slice of a weight unit, written to the same shared-memory offset of every CTA in cta_mask;
+// each destination CTA's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -234,10 +262,14 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
 
   __shared__ long long dbg_t[2 * TC_MAX_TL];
   const int tid = threadIdx.x, warp = tid >> 5;
+  // CTAs of a cluster walk the same weight stream in lockstep: every unit is fetched from L2 once
+  // per cluster (each CTA loads 1/csize of it and multicasts the slice to all)
+  const uint32_t csize = cluster_nctarank(), crank = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   if (tid == 0) {
     for (int s = 0; s < TC_NBAR; ++s) {
       mbar_init(bar_bfull + 8 * s, 1);
-      mbar_init(bar_bempty + 8 * s, 1);
+      mbar_init(bar_bempty + 8 * s, csize);  // one tcgen05.commit arrival from every CTA of the cluster
     }
     mbar_init(bar_dfull, 1);
     mbar_init(bar_aready, 32 * TC_EPI_WARPS);
@@ -249,10 +281,13 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // barriers of every CTA are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_p;
 
   const int64_t ntiles = (nrows + TC_ROWS - 1) / TC_ROWS;
+  // the same trip count in every CTA keeps the cluster in lockstep (surplus tiles hold no rows)
+  const int64_t tiles_per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
   const float slope = (float)p.slope;
 
   if (warp < TC_EPI_WARPS) {
@@ -263,9 +298,10 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
     const uint32_t row = quad * 32u + ((uint32_t)tid & 31u);
     const uint32_t tmem_lane = tmem_base + ((quad * 32u) << 16);
     uint32_t d_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t it = 0; it < tiles_per_cta; ++it) {
+      const int64_t tile = it * gridDim.x + blockIdx.x;
       const int64_t grow = tile * TC_ROWS + row;
-      const bool dbg = p.debug && blockIdx.x == 0 && tid == 0 && tile == (int64_t)gridDim.x;
+      const bool dbg = p.debug && blockIdx.x == 0 && tid == 0 && it == 1;
       long long tq0 = dbg ? clock64() : 0, t_mma = 0, t_epi = 0;
       // ---- normalised inputs -> A operand of the first layer (k padded to 16 with zeros) ----
       if (half == 0) {
@@ -353,7 +389,7 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
     const bool leader = (tid & 31) == 0;
     uint32_t a_phase = 0;
     uint32_t g = 0;  // running unit count: barrier pair g % TC_NBAR, phase (g / TC_NBAR) & 1
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t it = 0; it < tiles_per_cta; ++it) {
       for (int tl = 0; tl < p.n_tl; ++tl) {
         mbar_wait(bar_aready, a_phase);
         a_phase ^= 1;
@@ -383,7 +419,8 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
             }
           }
           if (leader) {
-            tc_commit(bar_bempty + 8 * stage);
+            if (csize > 1) tc_commit_mcast(bar_bempty + 8 * stage, cmask);
+            else tc_commit(bar_bempty + 8 * stage);
             if (uflags & 2) tc_commit(bar_dfull);
           }
           __syncwarp();
@@ -394,7 +431,7 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
     // ============================== weight streamer ==============================
     const bool leader = (tid & 31) == 0;
     uint32_t g = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t it = 0; it < tiles_per_cta; ++it) {
       for (int u = 0; u < p.n_units; ++u, ++g) {
         const uint32_t bytes = (uint32_t)p.units[u].rows * ((p.units[u].flags & 4u) ? 256u : 128u);
         const uint32_t back = p.units[u].back;
@@ -405,8 +442,14 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
         }
         const uint32_t stage = g % TC_NBAR;
         if (leader) {
-          mbar_expect_tx(bar_bfull + 8 * stage, bytes);
-          bulk_g2s(b_smem + (uint32_t)p.units[u].ring_kb * 1024u, p.wimg + p.units[u].w_off, bytes, bar_bfull + 8 * stage);
+          mbar_expect_tx(bar_bfull + 8 * stage, bytes);  // all slices, whoever sends them
+          const uint32_t dst = b_smem + (uint32_t)p.units[u].ring_kb * 1024u;
+          if (csize > 1) {
+            const uint32_t slice = bytes / csize;  // unit sizes are multiples of 2 KB
+            bulk_g2s_mcast(dst + crank * slice, p.wimg + p.units[u].w_off + crank * slice, slice, bar_bfull + 8 * stage, cmask);
+          } else {
+            bulk_g2s(dst, p.wimg + p.units[u].w_off, bytes, bar_bfull + 8 * stage);
+          }
         }
         __syncwarp();
       }
@@ -414,6 +457,7 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == TC_EPI_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -476,7 +520,26 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (tid == 128) {
+  if (tid == 128 && mode >= 100) {
+    // issue-rate probe: 256 back-to-back MMAs of width N (100: SS, 101: TS, 102: SS,SS,TS);
+    // D[0] = cycles per MMA to completion, D[1] = cycles per MMA spent issuing
+    const uint32_t idesc = make_idesc_tf32(N);
+    const int REP = 256;
+    const long long t0 = clock64();
+    for (int r = 0; r < REP; ++r) {
+      const uint32_t ks = r & 3;
+      const uint64_t bd = make_desc_sw128(b_smem + ks * 32u);
+      const bool ts = (mode == 101) || (mode == 102 && (r % 3) == 2);
+      if (ts) mma_ts(tmem_base, tmem_base + TC_ALO_COL + ks * 8u, bd, idesc, r ? 1u : 0u);
+      else mma_ss(tmem_base, make_desc_sw128(a_smem + ks * 32u), bd, idesc, r ? 1u : 0u);
+    }
+    const long long t1 = clock64();
+    tc_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t2 = clock64();
+    D[0] = (float)(t2 - t0) / REP;
+    D[1] = (float)(t1 - t0) / REP;
+  } else if (tid == 128) {
     const uint32_t idesc = make_idesc_tf32(N);
     for (uint32_t ks = 0; ks < 4; ++ks) {
       const uint64_t bd = (mode == 2) ? make_desc_sw64(b_smem + (ks >> 1) * (uint32_t)N * 64u + (ks & 1u) * 32u)
@@ -488,7 +551,7 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
     }
     tc_commit(bar);
   }
-  if (warp < 4) {
+  if (warp < 4 && mode < 100) {
     mbar_wait(bar, 0);
     tc_fence_after();
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -548,6 +611,8 @@ int c1d_tc_prepare(c1d_ctx* ctx) {
   p.n_tl = L;  // every layer runs on the tensor cores
   p.slope = c.nn_slope;
   p.debug = getenv("C1D_TC_DEBUG") ? 1 : 0;
+  st->cluster = getenv("C1D_TC_CLUSTER") ? atoi(getenv("C1D_TC_CLUSTER")) : 1;
+  if (st->cluster != 1 && st->cluster != 2 && st->cluster != 4) st->cluster = 1;
   std::vector<TcUnit> units;
   std::vector<uint8_t> img;
   std::vector<float> bias;
@@ -661,7 +726,24 @@ int c1d_tc_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out
   }
   int64_t ntiles = (nrows + TC_ROWS - 1) / TC_ROWS;
   int grid = (int)(ntiles < ctx->num_sms ? ntiles : ctx->num_sms);
-  k_mlp_tc<<<grid, TC_THREADS, TC_SMEM, s>>>(st->p, emu_in, nrows, out, out_stride);
+  // optional clusters share the weight stream (multicast).  Measured on B200: no gain, the MMA phase
+  // is bound by tensor-pipe occupancy per instruction (tools/tc_issue_probe.py), not by L2 bandwidth
+  int csize = st->cluster;
+  while (csize > 1 && (grid % csize)) csize >>= 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  C1D_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_mlp_tc, st->p, emu_in, nrows, out, out_stride));
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return C1D_OK;
@@ -677,7 +759,7 @@ void c1d_tc_destroy(c1d_ctx* ctx) {
 
 // D[128, N] = tf32(A[128, 32]) . tf32(B[N, 32])^T through one tcgen05.mma chain; host pointers.
 extern "C" int c1d_tc_selftest(int device, const float* A_host, const float* B_host, float* D_host, int N, int mode) {
-  if (!A_host || !B_host || !D_host || N < 16 || N > 256 || (N % 16) || (mode < 0 || mode > 2)) return C1D_ERR_ARG;
+  if (!A_host || !B_host || !D_host || N < 16 || N > 256 || (N % 16) || (mode < 0 || (mode > 2 && (mode < 100 || mode > 102)))) return C1D_ERR_ARG;
   if (cudaSetDevice(device) != cudaSuccess) return C1D_ERR_CUDA;
   float *dA = nullptr, *dB = nullptr, *dD = nullptr;
   int rc = C1D_OK;
