@@ -196,7 +196,9 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
   }
   ctx->finalized = 1;
   if (c.emu_kind == 0) {
-    int rc = c1d_tc_prepare(ctx);  // builds the tensor-core weight images (no-op when unsupported)
+    int rc = c1d_mlp64_prepare(ctx);  // padded fp64 weight image + slab plan
+    if (rc != C1D_OK) return rc;
+    rc = c1d_tc_prepare(ctx);  // builds the tensor-core weight images (no-op when unsupported)
     if (rc != C1D_OK) return rc;
   }
   return C1D_OK;
@@ -400,6 +402,7 @@ extern "C" int c1d_ctx_destroy(c1d_ctx* ctx) {
   cudaSetDevice(ctx->cfg.device);
   cudaDeviceSynchronize();
   c1d_tc_destroy(ctx);
+  c1d_mlp64_destroy(ctx);
   ws_free(ctx);
   if (ctx->icov_pad) cudaFree(ctx->icov_pad);
   for (int f = 0; f < C1D_F_COUNT; ++f)

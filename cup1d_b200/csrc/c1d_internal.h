@@ -89,6 +89,8 @@ struct c1d_ctx {
   double* icov_pad;  // [ldd*ldd] zero-padded copy of the dense inverse covariance
   // tensor-core emulator path (c1d_mlp_tc.cu)
   void* tc_state;
+  // fp64 tensor-core emulator path (c1d_mlp_f64.cu)
+  void* mlp64_state;
   char err[512];
 };
 
@@ -114,6 +116,12 @@ int c1d_launch_finalize(c1d_ctx* ctx, int64_t W, double* lnp, double* lnl_z, dou
                         double* chi2, uint32_t flags, cudaStream_t s);
 
 int c1d_launch_pack7(c1d_ctx* ctx, int64_t W, cudaStream_t s);
+
+// fp64 (DMMA) MLP: padded weight image + slab plan, built at finalize
+int c1d_mlp64_prepare(c1d_ctx* ctx);
+int c1d_mlp64_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out, int out_stride,
+                     cudaStream_t s);
+void c1d_mlp64_destroy(c1d_ctx* ctx);
 
 // tensor-core MLP (optional translation unit)
 int c1d_tc_prepare(c1d_ctx* ctx);

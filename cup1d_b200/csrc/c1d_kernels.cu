@@ -2,7 +2,7 @@
 //
 //   stage 0/1/5  k_stage1      cube -> parameters -> per-z emulator inputs, contaminant
 //                              amplitudes, blobs, Gaussian prior, star box, hull
-//   stage 2      k_mlp_f64     LaCE-style MLP on the fp64 tensor cores (DMMA, exact-parity mode)
+//   stage 2      k_mlp_f64     LaCE-style MLP on the fp64 tensor cores (DMMA, exact-parity mode; c1d_mlp_f64.cu)
 //                k_gp_f64      GP posterior mean = batched kernel-vector product
 //   stage 3      k_fused_p1d   emulator polynomial -> contaminant templates -> rebin ->
 //                              residual, tables staged in shared memory per z
@@ -169,124 +169,6 @@ int c1d_launch_stage1(c1d_ctx* ctx, const double* x, int64_t W, double* blobs_ou
 }
 
 // ---------------------------------------------------------------------------------------
-// stage 2a: the MLP in fp64 (exact-parity mode) on the fp64 tensor cores (mma.sync m8n8k4).
-// One CTA owns a tile of 64 rows ((walker, z) pairs) and chains all layers with the
-// activations resident in shared memory (k-major, padded row stride).  Warp (wm, wn) owns
-// rows 32 wm .. +31 and a slab of 8*NB output columns; weights stream through L1/L2.
-// ---------------------------------------------------------------------------------------
-#define MLP_ROWS 64
-#define MLP_MAXW 256
-#define MLP_THREADS 256
-#define MLP_STR 68  // doubles per k-row of the activation tile (64 + 4: conflict-free fragments)
-
-__device__ __forceinline__ void dmma8(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-
-template <int NB>
-__device__ __forceinline__ void mlp_layer(const double* __restrict__ Wt, const double* __restrict__ b,
-                                          int K, int N, double* act, double slope, bool activate) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = warp & 1, wn = warp >> 1;
-  const int n0 = wn * (8 * NB), r0 = 32 * wm;
-  const int kq = lane & 3, g = lane >> 2;
-  double acc[4][NB][2];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) acc[a][nb][0] = acc[a][nb][1] = 0.0;
-  if (n0 < N) {
-#pragma unroll 2
-    for (int k0 = 0; k0 < K; k0 += 4) {
-      const int k = k0 + kq;
-      const bool kin = k < K;
-      double af[4], bf[NB];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) af[a] = kin ? act[k * MLP_STR + r0 + 8 * a + g] : 0.0;
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        const int n = n0 + 8 * nb + g;
-        bf[nb] = (kin && n < N) ? __ldg(Wt + (size_t)k * N + n) : 0.0;
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) dmma8(acc[a][nb][0], acc[a][nb][1], af[a], bf[nb]);
-    }
-  }
-  __syncthreads();  // every read of the input activations is done
-  if (n0 < N) {
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int n = n0 + 8 * nb + 2 * kq + e;
-        if (n < N) {
-          const double bv = b[n];
-#pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            double v = acc[a][nb][e] + bv;
-            if (activate) v = (v > 0.0) ? v : slope * v;  // LeakyReLU(slope)
-            act[n * MLP_STR + r0 + 8 * a + g] = v;
-          }
-        }
-      }
-  }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(MLP_THREADS, 1)
-k_mlp_f64(DevCtx c, const double* __restrict__ emu_in, int64_t nrows, double* __restrict__ out,
-          int out_stride) {
-  extern __shared__ __align__(16) double act[];  // [MLP_MAXW][MLP_STR]
-  const int64_t ntiles = (nrows + MLP_ROWS - 1) / MLP_ROWS;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t row0 = tile * MLP_ROWS;
-    // normalised inputs: (x - lo)/(hi - lo) - 0.5
-    for (int t = threadIdx.x; t < MLP_ROWS * c.n_emu; t += blockDim.x) {
-      int r = t / c.n_emu, j = t % c.n_emu;
-      int64_t row = row0 + r;
-      double v = 0.0;
-      if (row < nrows) {
-        double xv = emu_in[row * C1D_MAX_EMU + j];
-        v = (xv - c.emu_lo[j]) / (c.emu_hi[j] - c.emu_lo[j]) - 0.5;
-      }
-      act[j * MLP_STR + r] = v;
-    }
-    __syncthreads();
-    size_t woff = 0, boff = 0;
-    for (int l = 0; l < c.n_layers; ++l) {
-      const int K = c.layer_dims[l], N = c.layer_dims[l + 1];
-      const bool activate = l < c.n_layers - 1;
-      const double* Wt = c.nn_w + woff;
-      const double* b = c.nn_b + boff;
-      const int nb = (N + 31) / 32;  // 8-column blocks per warp slab (4 slabs)
-      switch (nb) {
-        case 1: mlp_layer<1>(Wt, b, K, N, act, c.nn_slope, activate); break;
-        case 2: mlp_layer<2>(Wt, b, K, N, act, c.nn_slope, activate); break;
-        case 3: mlp_layer<3>(Wt, b, K, N, act, c.nn_slope, activate); break;
-        case 4: mlp_layer<4>(Wt, b, K, N, act, c.nn_slope, activate); break;
-        case 5: mlp_layer<5>(Wt, b, K, N, act, c.nn_slope, activate); break;
-        case 6: mlp_layer<6>(Wt, b, K, N, act, c.nn_slope, activate); break;
-        case 7: mlp_layer<7>(Wt, b, K, N, act, c.nn_slope, activate); break;
-        default: mlp_layer<8>(Wt, b, K, N, act, c.nn_slope, activate); break;
-      }
-      woff += (size_t)K * N;
-      boff += N;
-    }
-    // polynomial coefficients of this tile
-    for (int t = threadIdx.x; t < MLP_ROWS * c.nc; t += blockDim.x) {
-      int r = t / c.nc, j = t % c.nc;
-      int64_t row = row0 + r;
-      if (row < nrows) out[row * out_stride + j] = act[j * MLP_STR + r];
-    }
-    __syncthreads();
-  }
-}
-
-// ---------------------------------------------------------------------------------------
 // stage 2b: GP posterior mean, one warp per row.  m_o = sum_i k(u, U_i) alpha[i, o] with
 // an ARD squared-exponential kernel; fp64 because alpha = K^-1 y cancels heavily.
 // ---------------------------------------------------------------------------------------
@@ -342,16 +224,7 @@ int c1d_launch_emulator(c1d_ctx* ctx, const double* emu_in, int64_t nrows, doubl
   if (nrows <= 0) return C1D_OK;
   if (ctx->cfg.emu_kind == 0) {
     if (flags & C1D_FLAG_EMU_TC) return c1d_tc_launch(ctx, emu_in, nrows, out, out_stride, s);
-    size_t smem = (size_t)MLP_MAXW * MLP_STR * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-      C1D_CUDA(ctx, cudaFuncSetAttribute(k_mlp_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
-      attr_set = true;
-    }
-    int64_t ntiles = (nrows + MLP_ROWS - 1) / MLP_ROWS;
-    int grid = (int)(ntiles < ctx->num_sms ? ntiles : ctx->num_sms);
-    k_mlp_f64<<<grid, MLP_THREADS, smem, s>>>(ctx->d, emu_in, nrows, out, out_stride);
+    return c1d_mlp64_launch(ctx, emu_in, nrows, out, out_stride, s);
   } else {
     int64_t warps_needed = nrows;
     int64_t blocks = (warps_needed + 7) / 8;

@@ -1,0 +1,351 @@
+// Stage 2 (exact-parity mode): the LaCE-style MLP in fp64 on the fp64 tensor cores
+// (mma.sync m8n8k4, DMMA).  Replaces, for all rows of a batch at once, the per-call
+// `NNEmulator.emulate_p1d_Mpc` network forward pass that Theory.get_p1d_kms drives
+// (reference call site cup1d/likelihood/lya_theory.py:794-812; LaCE itself is not in the
+// reference tree, see oracle/emulators.py for the restated network).
+//
+// One CTA per SM owns a tile of 64 rows ((walker, z) pairs) and chains all layers with the
+// activations resident in shared memory (k-major, row stride 68 doubles).  The weights of all
+// layers form one stream of k-slabs (<= 33 KB each) that a producer warp double buffers in
+// shared memory with cp.async.bulk + mbarriers: slab s+1 (possibly of the next layer, or of the
+// next tile) lands while slab s feeds the tensor cores, so no global-memory latency sits on the
+// DMMA path and the compute warps only meet at the two barriers a layer needs.  The weight image
+// is zero-padded on the host ([K to 4][N to 8, + 4 columns of row skew]) so the inner loop
+// carries no bounds checks and a slab is one contiguous copy.
+// Warp (wm, wn) owns rows 32 wm .. +31 and a run of 8-column blocks; the blocks of a layer are
+// dealt to the four n-warps as evenly as they divide.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "c1d_internal.h"
+
+namespace {
+
+constexpr int M64_ROWS = 64;
+constexpr int M64_CWARPS = 8;                         // compute warps
+constexpr int M64_THREADS = 32 * (M64_CWARPS + 1);   // + the weight streamer
+constexpr int M64_STR = 68;         // doubles per k-row of the activation tile (== 4 mod 16: conflict-free fragments)
+constexpr int M64_MAXW = 256;       // widest layer
+constexpr int M64_SLAB = 4224;      // doubles per weight slab buffer
+constexpr int M64_MAX_SLABS = 80;
+constexpr size_t M64_SMEM = ((size_t)M64_MAXW * M64_STR + 2 * (size_t)M64_SLAB) * sizeof(double) + 64;
+static_assert(M64_SMEM <= 232448, "shared memory budget");
+
+struct M64Slab {
+  uint32_t w_off;   // doubles from the start of the padded weight image
+  uint16_t k0, kc;  // first k-row and number of k-rows (multiple of 4)
+  uint8_t layer, first, last, pad;
+};
+
+struct M64Plan {
+  int n_layers, n_slabs, n_in, n_out;
+  double slope;
+  const double* wimg;  // padded weights, layer after layer, [Kp][Np]
+  const double* bimg;  // padded biases
+  int np[C1D_MAX_LAYERS];       // N padded to 8
+  int nbt[C1D_MAX_LAYERS];      // 8-column blocks of the layer
+  int boff[C1D_MAX_LAYERS];
+  M64Slab slabs[M64_MAX_SLABS];
+};
+
+struct M64State {
+  M64Plan p;
+  double *d_w, *d_b;
+};
+
+__device__ __forceinline__ void dmma8(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// barrier among the compute warps only (the streamer never joins)
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * M64_CWARPS) : "memory"); }
+
+// one layer on one tile; q is the running slab index (buffer parity), returns with every
+// activation of the layer written (or, for the output layer, stored to `out`)
+template <int NB>
+__device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint32_t& q, uint32_t bar_full, uint32_t bar_empty,
+                                          double* act, const double* wbuf, bool is_out, int64_t row0, int64_t nrows,
+                                          double* __restrict__ out, int out_stride) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp & 1, wn = warp >> 1;
+  const int kq = lane & 3, g = lane >> 2;
+  const int r0 = 32 * wm;
+  const int nbt = p.nbt[l];
+  const int base = nbt >> 2, rem = nbt & 3;
+  const int cnt = base + (wn < rem ? 1 : 0);                     // blocks of this warp: NB or NB - 1
+  const int n0 = 8 * (wn * base + (wn < rem ? wn : rem));         // first column
+  const int ns = p.np[l] + 4;
+  const bool last_blk = cnt == NB;  // the NB-th block exists for this warp
+  double acc[4][NB][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) acc[a][nb][0] = acc[a][nb][1] = 0.0;
+
+  for (;;) {
+    const M64Slab sl = p.slabs[s];
+    mbar_wait(bar_full + 8 * (q & 1u), (q >> 1) & 1u);  // slab q has landed
+    const double* wb = wbuf + (q & 1u) * M64_SLAB;
+    if (cnt > 0) {
+      const double* ap = act + (size_t)(sl.k0 + kq) * M64_STR + r0 + g;
+      const double* bp = wb + kq * ns + n0 + g;
+#pragma unroll 2
+      for (int kk = 0; kk < (int)sl.kc; kk += 4) {
+        double af[4], bf[NB];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) af[a] = ap[kk * M64_STR + 8 * a];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) bf[nb] = (nb < NB - 1 || last_blk) ? bp[kk * ns + 8 * nb] : 0.0;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          if (nb < NB - 1 || last_blk) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) dmma8(acc[a][nb][0], acc[a][nb][1], af[a], bf[nb]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8 * (q & 1u));  // this warp is done with the buffer
+    ++s;
+    ++q;
+    if (sl.last) break;
+  }
+  if (!is_out) {
+    compute_sync();  // every read of the input activations is done
+    const double* bias = p.bimg + p.boff[l];
+    const double slope = p.slope;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      if (nb < cnt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int n = n0 + 8 * nb + 2 * kq + e;
+          const double bv = __ldg(bias + n);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            double v = acc[a][nb][e] + bv;
+            v = (v > 0.0) ? v : slope * v;  // LeakyReLU(slope); padded columns stay exactly zero
+            act[(size_t)n * M64_STR + r0 + 8 * a + g] = v;
+          }
+        }
+      }
+    }
+    compute_sync();  // activations of the next layer are visible
+  } else {
+    const double* bias = p.bimg + p.boff[l];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      if (nb < cnt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int n = n0 + 8 * nb + 2 * kq + e;
+          if (n < p.n_out) {
+            const double bv = __ldg(bias + n);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const int64_t row = row0 + r0 + 8 * a + g;
+              if (row < nrows) out[row * out_stride + n] = acc[a][nb][e] + bv;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(M64_THREADS, 1)
+k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict__ emu_lo,
+          const double* __restrict__ emu_hi, int64_t nrows, double* __restrict__ out, int out_stride) {
+  extern __shared__ __align__(16) double smem_d[];
+  double* act = smem_d;                                  // [M64_MAXW][M64_STR]
+  double* wbuf = smem_d + (size_t)M64_MAXW * M64_STR;    // [2][M64_SLAB]
+  const uint32_t bar_full = smem_u32(wbuf + 2 * M64_SLAB), bar_empty = bar_full + 16;
+  const int64_t ntiles = (nrows + M64_ROWS - 1) / M64_ROWS;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_full + 8 * b, 1);
+      mbar_init(bar_empty + 8 * b, M64_CWARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t my_tiles = ((int64_t)blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (warp == M64_CWARPS) {
+    // ============================== weight streamer ==============================
+    if ((threadIdx.x & 31) == 0) {
+      uint32_t q = 0;
+      for (int64_t it = 0; it < my_tiles; ++it)
+        for (int s = 0; s < p.n_slabs; ++s, ++q) {
+          const uint32_t b = q & 1u;
+          mbar_wait(bar_empty + 8 * b, ((q >> 1) & 1u) ^ 1u);  // passes at once on the first lap
+          const M64Slab sl = p.slabs[s];
+          const uint32_t bytes = (uint32_t)sl.kc * (uint32_t)(p.np[sl.layer] + 4) * 8u;
+          mbar_expect_tx(bar_full + 8 * b, bytes);
+          bulk_g2s(smem_u32(wbuf + b * M64_SLAB), p.wimg + sl.w_off, bytes, bar_full + 8 * b);
+        }
+    }
+    return;
+  }
+  // ================================ compute warps ================================
+  uint32_t q = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * M64_ROWS;
+    // normalised inputs (x - lo)/(hi - lo) - 0.5, k rows padded to 8 with zeros
+    compute_sync();  // the previous tile's output layer has read its activations
+    for (int t = threadIdx.x; t < M64_ROWS * 8; t += 32 * M64_CWARPS) {
+      const int j = t >> 6, r = t & 63;
+      const int64_t row = row0 + r;
+      double v = 0.0;
+      if (j < p.n_in && row < nrows) {
+        const double lo = __ldg(emu_lo + j);
+        v = (emu_in[row * C1D_MAX_EMU + j] - lo) / (__ldg(emu_hi + j) - lo) - 0.5;
+      }
+      act[j * M64_STR + r] = v;
+    }
+    compute_sync();
+    int s = 0;
+    for (int l = 0; l < p.n_layers; ++l) {
+      const bool is_out = l == p.n_layers - 1;
+      const int nb = (p.nbt[l] + 3) >> 2;
+      switch (nb) {
+        case 1: m64_layer<1>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
+        case 2: m64_layer<2>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
+        case 3: m64_layer<3>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
+        case 4: m64_layer<4>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
+        case 5: m64_layer<5>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
+        case 6: m64_layer<6>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
+        case 7: m64_layer<7>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
+        default: m64_layer<8>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+void c1d_mlp64_destroy(c1d_ctx* ctx) {
+  M64State* st = (M64State*)ctx->mlp64_state;
+  if (!st) return;
+  cudaFree(st->d_w);
+  cudaFree(st->d_b);
+  delete st;
+  ctx->mlp64_state = nullptr;
+}
+
+int c1d_mlp64_prepare(c1d_ctx* ctx) {
+  const c1d_config& c = ctx->cfg;
+  c1d_mlp64_destroy(ctx);
+  if (c.emu_kind != 0 || c.n_layers < 1) return C1D_OK;
+  M64State* st = new M64State();
+  memset(st, 0, sizeof(*st));
+  ctx->mlp64_state = st;
+  const int L = c.n_layers;
+  size_t nw = 0, nb = 0;
+  std::vector<size_t> woff(L), boff(L);
+  for (int l = 0; l < L; ++l) {
+    woff[l] = nw;
+    boff[l] = nb;
+    nw += (size_t)c.layer_dims[l] * c.layer_dims[l + 1];
+    nb += c.layer_dims[l + 1];
+  }
+  std::vector<double> W(nw), Bv(nb);
+  C1D_CUDA(ctx, cudaMemcpy(W.data(), ctx->dev[C1D_F_NN_W], nw * sizeof(double), cudaMemcpyDeviceToHost));
+  C1D_CUDA(ctx, cudaMemcpy(Bv.data(), ctx->dev[C1D_F_NN_B], nb * sizeof(double), cudaMemcpyDeviceToHost));
+
+  M64Plan& p = st->p;
+  p.n_layers = L;
+  p.n_in = c.layer_dims[0];
+  p.n_out = c.layer_dims[L];
+  p.slope = c.nn_slope;
+  std::vector<double> img, bimg;
+  int n_slabs = 0;
+  for (int l = 0; l < L; ++l) {
+    const int K = c.layer_dims[l], N = c.layer_dims[l + 1];
+    // the input tile is zero-filled to 8 k-rows; hidden activations are exact zeros up to the
+    // previous layer's padded width, which covers K rounded up to 4
+    const int kp = (l == 0) ? ((K + 3) & ~3) : ((K + 3) & ~3);
+    const int np = (N + 7) & ~7;
+    p.np[l] = np;
+    p.nbt[l] = np / 8;
+    p.boff[l] = (int)bimg.size();
+    for (int n = 0; n < np; ++n) bimg.push_back(n < N ? Bv[boff[l] + n] : 0.0);
+    const size_t w0 = img.size();
+    const int ns = np + 4;  // row skew: fragments of 4 k-rows x 8 columns touch every bank once
+    img.resize(w0 + (size_t)kp * ns, 0.0);
+    for (int k = 0; k < K; ++k)
+      for (int n = 0; n < N; ++n) img[w0 + (size_t)k * ns + n] = W[woff[l] + (size_t)k * N + n];  // stored in-major: Wt[k*N + n]
+    int ks = (M64_SLAB / (np + 4)) & ~3;  // k-rows per slab
+    if (ks < 4) {
+      snprintf(ctx->err, sizeof(ctx->err), "layer %d too wide for the fp64 MLP slab buffer", l);
+      return C1D_ERR_ARG;
+    }
+    for (int k0 = 0; k0 < kp; k0 += ks) {
+      if (n_slabs >= M64_MAX_SLABS) {
+        snprintf(ctx->err, sizeof(ctx->err), "fp64 MLP slab table overflow");
+        return C1D_ERR_ARG;
+      }
+      M64Slab& sl = p.slabs[n_slabs++];
+      sl.w_off = (uint32_t)(w0 + (size_t)k0 * ns);
+      sl.k0 = (uint16_t)k0;
+      sl.kc = (uint16_t)((kp - k0 < ks) ? (kp - k0) : ks);
+      sl.layer = (uint8_t)l;
+      sl.first = k0 == 0;
+      sl.last = k0 + ks >= kp;
+      sl.pad = 0;
+    }
+  }
+  p.n_slabs = n_slabs;
+  C1D_CUDA(ctx, cudaMalloc(&st->d_w, img.size() * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&st->d_b, bimg.size() * sizeof(double)));
+  C1D_CUDA(ctx, cudaMemcpy(st->d_w, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice));
+  C1D_CUDA(ctx, cudaMemcpy(st->d_b, bimg.data(), bimg.size() * sizeof(double), cudaMemcpyHostToDevice));
+  p.wimg = st->d_w;
+  p.bimg = st->d_b;
+  C1D_CUDA(ctx, cudaFuncSetAttribute(k_mlp_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M64_SMEM));
+  return C1D_OK;
+}
+
+int c1d_mlp64_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out, int out_stride, cudaStream_t s) {
+  M64State* st = (M64State*)ctx->mlp64_state;
+  if (!st) {
+    snprintf(ctx->err, sizeof(ctx->err), "fp64 MLP not prepared");
+    return C1D_ERR_STATE;
+  }
+  const int64_t ntiles = (nrows + M64_ROWS - 1) / M64_ROWS;
+  const int grid = (int)(ntiles < ctx->num_sms ? ntiles : ctx->num_sms);
+  k_mlp_f64<<<grid, M64_THREADS, M64_SMEM, s>>>(st->p, emu_in, ctx->d.emu_lo, ctx->d.emu_hi, nrows, out, out_stride);
+  ctx->launches++;
+  C1D_CUDA(ctx, cudaPeekAtLastError());
+  return C1D_OK;
+}
