@@ -4,17 +4,22 @@
 // (reference call site cup1d/likelihood/lya_theory.py:794-812; LaCE itself is not in the
 // reference tree, see oracle/emulators.py for the restated network).
 //
-// One CTA per SM owns a tile of 64 rows ((walker, z) pairs) and chains all layers with the
-// activations resident in shared memory (k-major, row stride 68 doubles).  The weights of all
+// One CTA per SM works on two tiles of 32 rows ((walker, z) pairs) at a time, one per group of
+// four warps, and chains all layers with the activations resident in shared memory (k-major, row
+// stride 68 doubles).  The groups share the weight stream but synchronise separately, so one
+// group's layer epilogue (pipeline drain, activation write-back, barrier) hides under the other
+// group's DMMAs on the same SM sub-partitions.  The weights of all
 // layers form one stream of k-slabs (<= 33 KB each) that a producer warp double buffers in
 // shared memory with cp.async.bulk + mbarriers: slab s+1 (possibly of the next layer, or of the
 // next tile) lands while slab s feeds the tensor cores, so no global-memory latency sits on the
 // DMMA path and the compute warps only meet at the two barriers a layer needs.  The weight image
 // is zero-padded on the host ([K to 4][N to 8, + 4 columns of row skew]) so the inner loop
 // carries no bounds checks and a slab is one contiguous copy.
-// Warp (wm, wn) owns rows 32 wm .. +31 and a run of 8-column blocks; the blocks of a layer are
-// dealt to the four n-warps as evenly as they divide.
+// Warp wn of a group owns the group's 32 rows and a run of 8-column blocks; the blocks of a layer
+// are dealt to the four n-warps as evenly as they divide (the odd blocks go to opposite ends in
+// the two groups, which balances the sub-partitions).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -22,14 +27,16 @@
 
 namespace {
 
-constexpr int M64_ROWS = 64;
+constexpr int M64_ROWS = 32;                          // rows of one group's tile
 constexpr int M64_CWARPS = 8;                         // compute warps
 constexpr int M64_THREADS = 32 * (M64_CWARPS + 1);   // + the weight streamer
 constexpr int M64_STR = 68;         // doubles per k-row of the activation tile (== 4 mod 16: conflict-free fragments)
 constexpr int M64_MAXW = 256;       // widest layer
+constexpr int M64_NBUF = 2;         // weight slab buffers (ring)
 constexpr int M64_SLAB = 4224;      // doubles per weight slab buffer
-constexpr int M64_MAX_SLABS = 80;
-constexpr size_t M64_SMEM = ((size_t)M64_MAXW * M64_STR + 2 * (size_t)M64_SLAB) * sizeof(double) + 64;
+constexpr int M64_MAX_SLABS = 120;
+constexpr int M64_MAXBIAS = 1024;   // doubles of padded biases kept in shared memory
+constexpr size_t M64_SMEM = ((size_t)M64_MAXW * M64_STR + M64_NBUF * (size_t)M64_SLAB + M64_MAXBIAS) * sizeof(double) + 16 * M64_NBUF;
 static_assert(M64_SMEM <= 232448, "shared memory budget");
 
 struct M64Slab {
@@ -39,7 +46,7 @@ struct M64Slab {
 };
 
 struct M64Plan {
-  int n_layers, n_slabs, n_in, n_out;
+  int n_layers, n_slabs, n_in, n_out, debug, skew, n_bias;
   double slope;
   const double* wimg;  // padded weights, layer after layer, [Kp][Np]
   const double* bimg;  // padded biases
@@ -73,7 +80,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
       "r"(parity)
       : "memory");
@@ -83,35 +90,66 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-// barrier among the compute warps only (the streamer never joins)
-__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * M64_CWARPS) : "memory"); }
+// barrier among the four warps of one group (the streamer and the other group never join)
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
+
+// the two input values thread gtid of a group stages for a tile of 32 rows ([8 k-rows][32 rows])
+__device__ __forceinline__ void load_inputs(const M64Plan& p, const double* __restrict__ emu_in, const double* __restrict__ emu_lo,
+                                            const double* __restrict__ emu_hi, int64_t row0, int64_t nrows, int gtid, double* xin) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int t = gtid + 128 * u;
+    const int j = t >> 5;
+    const int64_t row = row0 + (t & 31);
+    double v = 0.0;
+    if (j < p.n_in && row < nrows) {
+      const double lo = __ldg(emu_lo + j);
+      v = (emu_in[row * C1D_MAX_EMU + j] - lo) / (__ldg(emu_hi + j) - lo) - 0.5;
+    }
+    xin[u] = v;
+  }
+}
 
 // one layer on one tile; q is the running slab index (buffer parity), returns with every
 // activation of the layer written (or, for the output layer, stored to `out`)
 template <int NB>
 __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint32_t& q, uint32_t bar_full, uint32_t bar_empty,
-                                          double* act, const double* wbuf, bool is_out, int64_t row0, int64_t nrows,
-                                          double* __restrict__ out, int out_stride) {
+                                          double* act, const double* wbuf, const double* bsm, bool is_out, int64_t row0, int64_t nrows,
+                                          double* __restrict__ out, int out_stride, long long* dbg) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = warp & 1, wn = warp >> 1;
+  const int grp = warp >> 2, wn = warp & 3;
   const int kq = lane & 3, g = lane >> 2;
-  const int r0 = 32 * wm;
+  const int r0 = 32 * grp;
   const int nbt = p.nbt[l];
   const int base = nbt >> 2, rem = nbt & 3;
-  const int cnt = base + (wn < rem ? 1 : 0);                     // blocks of this warp: NB or NB - 1
-  const int n0 = 8 * (wn * base + (wn < rem ? wn : rem));         // first column
+  // blocks of this warp: NB or NB - 1; the rem odd blocks go to the first warps of group 0 and to the last of group 1
+  const int wx = grp ? 3 - wn : wn;
+  const int cnt = base + (wx < rem ? 1 : 0);
+  const int before = grp ? (wn * base + (wn > 4 - rem ? wn - (4 - rem) : 0)) : (wn * base + (wn < rem ? wn : rem));
+  const int n0 = 8 * before;  // first column
   const int ns = p.np[l] + 4;
   const bool last_blk = cnt == NB;  // the NB-th block exists for this warp
+  // accumulators start from the bias (thread holds columns n0 + 8 nb + 2 kq + {0, 1} of rows r0 + 8 a + g)
+  const double* bias = bsm + p.boff[l];
   double acc[4][NB][2];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int nb = 0; nb < NB; ++nb) {
+    const double b0 = (nb < cnt) ? bias[n0 + 8 * nb + 2 * kq] : 0.0;
+    const double b1 = (nb < cnt) ? bias[n0 + 8 * nb + 2 * kq + 1] : 0.0;
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) acc[a][nb][0] = acc[a][nb][1] = 0.0;
+    for (int a = 0; a < 4; ++a) {
+      acc[a][nb][0] = b0;
+      acc[a][nb][1] = b1;
+    }
+  }
 
   for (;;) {
     const M64Slab sl = p.slabs[s];
-    mbar_wait(bar_full + 8 * (q & 1u), (q >> 1) & 1u);  // slab q has landed
-    const double* wb = wbuf + (q & 1u) * M64_SLAB;
+    const uint32_t buf = q % M64_NBUF;
+    const long long tw0 = dbg ? clock64() : 0;
+    mbar_wait(bar_full + 8 * buf, (q / M64_NBUF) & 1u);  // slab q has landed
+    const long long tw1 = dbg ? clock64() : 0;
+    const double* wb = wbuf + buf * M64_SLAB;
     if (cnt > 0) {
       const double* ap = act + (size_t)(sl.k0 + kq) * M64_STR + r0 + g;
       const double* bp = wb + kq * ns + n0 + g;
@@ -132,34 +170,38 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_empty + 8 * (q & 1u));  // this warp is done with the buffer
+    if (lane == 0) mbar_arrive(bar_empty + 8 * buf);  // this warp is done with the buffer
+    if (dbg) { dbg[0] += tw1 - tw0; dbg[1] += clock64() - tw1; }
     ++s;
     ++q;
     if (sl.last) break;
   }
+  const long long te0 = dbg ? clock64() : 0;
   if (!is_out) {
-    compute_sync();  // every read of the input activations is done
-    const double* bias = p.bimg + p.boff[l];
+    group_sync(grp);  // every read of the input activations is done
     const double slope = p.slope;
+    // LeakyReLU on the sign bit, then a store order that touches every bank once: lanes with
+    // kq < 2 store their even column first, the others their odd column (rows of the k-major tile
+    // are 68 doubles apart, so columns 4 apart share banks)
+    const bool swap = kq >= 2;
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
       if (nb < cnt) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int n = n0 + 8 * nb + 2 * kq + e;
-          const double bv = __ldg(bias + n);
-#pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            double v = acc[a][nb][e] + bv;
-            v = (v > 0.0) ? v : slope * v;  // LeakyReLU(slope); padded columns stay exactly zero
-            act[(size_t)n * M64_STR + r0 + 8 * a + g] = v;
-          }
+        for (int a = 0; a < 4; ++a) {
+          double v0 = acc[a][nb][0], v1 = acc[a][nb][1];
+          if (__double2hiint(v0) < 0) v0 *= slope;  // padded columns stay exactly zero
+          if (__double2hiint(v1) < 0) v1 *= slope;
+          const double first = swap ? v1 : v0, second = swap ? v0 : v1;
+          const int nf = n0 + 8 * nb + 2 * kq + (swap ? 1 : 0), nsx = n0 + 8 * nb + 2 * kq + (swap ? 0 : 1);
+          act[(size_t)nf * M64_STR + r0 + 8 * a + g] = first;
+          act[(size_t)nsx * M64_STR + r0 + 8 * a + g] = second;
         }
       }
     }
-    compute_sync();  // activations of the next layer are visible
+    group_sync(grp);  // activations of the next layer are visible
+    if (dbg) dbg[2] += clock64() - te0;
   } else {
-    const double* bias = p.bimg + p.boff[l];
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
       if (nb < cnt) {
@@ -167,11 +209,10 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
         for (int e = 0; e < 2; ++e) {
           const int n = n0 + 8 * nb + 2 * kq + e;
           if (n < p.n_out) {
-            const double bv = __ldg(bias + n);
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-              const int64_t row = row0 + r0 + 8 * a + g;
-              if (row < nrows) out[row * out_stride + n] = acc[a][nb][e] + bv;
+              const int64_t row = row0 + 8 * a + g;
+              if (row < nrows) out[row * out_stride + n] = acc[a][nb][e];
             }
           }
         }
@@ -185,27 +226,31 @@ k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict
           const double* __restrict__ emu_hi, int64_t nrows, double* __restrict__ out, int out_stride) {
   extern __shared__ __align__(16) double smem_d[];
   double* act = smem_d;                                  // [M64_MAXW][M64_STR]
-  double* wbuf = smem_d + (size_t)M64_MAXW * M64_STR;    // [2][M64_SLAB]
-  const uint32_t bar_full = smem_u32(wbuf + 2 * M64_SLAB), bar_empty = bar_full + 16;
+  double* wbuf = smem_d + (size_t)M64_MAXW * M64_STR;    // [M64_NBUF][M64_SLAB]
+  double* bsm = wbuf + M64_NBUF * M64_SLAB;               // [M64_MAXBIAS] padded biases of all layers
+  const uint32_t bar_full = smem_u32(bsm + M64_MAXBIAS), bar_empty = bar_full + 8 * M64_NBUF;
   const int64_t ntiles = (nrows + M64_ROWS - 1) / M64_ROWS;
   const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < p.n_bias; i += M64_THREADS) bsm[i] = __ldg(p.bimg + i);
   if (threadIdx.x == 0) {
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < M64_NBUF; ++b) {
       mbar_init(bar_full + 8 * b, 1);
       mbar_init(bar_empty + 8 * b, M64_CWARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const int64_t my_tiles = ((int64_t)blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // both groups walk the same number of tiles so that they consume the same slab stream
+  // (surplus tiles hold no rows)
+  const int64_t my_tiles = (ntiles + 2 * (int64_t)gridDim.x - 1) / (2 * (int64_t)gridDim.x);
   if (warp == M64_CWARPS) {
     // ============================== weight streamer ==============================
     if ((threadIdx.x & 31) == 0) {
       uint32_t q = 0;
       for (int64_t it = 0; it < my_tiles; ++it)
         for (int s = 0; s < p.n_slabs; ++s, ++q) {
-          const uint32_t b = q & 1u;
-          mbar_wait(bar_empty + 8 * b, ((q >> 1) & 1u) ^ 1u);  // passes at once on the first lap
+          const uint32_t b = q % M64_NBUF;
+          mbar_wait(bar_empty + 8 * b, ((q / M64_NBUF) & 1u) ^ 1u);  // passes at once on the first lap
           const M64Slab sl = p.slabs[s];
           const uint32_t bytes = (uint32_t)sl.kc * (uint32_t)(p.np[sl.layer] + 4) * 8u;
           mbar_expect_tx(bar_full + 8 * b, bytes);
@@ -215,35 +260,58 @@ k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict
     return;
   }
   // ================================ compute warps ================================
+  const int grp = warp >> 2, gtid = threadIdx.x & 127;
   uint32_t q = 0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  double xin[2];
+  if (grp == 1 && p.skew > 0) {
+    // start the second group half a slab late: the two groups then reach their layer epilogues at
+    // different times, and each hides the other's under its DMMAs
+    const long long t0 = clock64();
+    while (clock64() - t0 < p.skew) {}
+  }
+  for (int64_t it = 0; it < my_tiles; ++it) {
+    const int64_t tile = (it * gridDim.x + blockIdx.x) * 2 + grp;
     const int64_t row0 = tile * M64_ROWS;
-    // normalised inputs (x - lo)/(hi - lo) - 0.5, k rows padded to 8 with zeros
-    compute_sync();  // the previous tile's output layer has read its activations
-    for (int t = threadIdx.x; t < M64_ROWS * 8; t += 32 * M64_CWARPS) {
-      const int j = t >> 6, r = t & 63;
-      const int64_t row = row0 + r;
-      double v = 0.0;
-      if (j < p.n_in && row < nrows) {
-        const double lo = __ldg(emu_lo + j);
-        v = (emu_in[row * C1D_MAX_EMU + j] - lo) / (__ldg(emu_hi + j) - lo) - 0.5;
-      }
-      act[j * M64_STR + r] = v;
+    // normalised inputs (x - lo)/(hi - lo) - 0.5, k rows padded to 8 with zeros; they were fetched
+    // while the previous tile was in its last hidden layers
+    if (it == 0) load_inputs(p, emu_in, emu_lo, emu_hi, row0, nrows, gtid, xin);
+    group_sync(grp);  // the previous tile's output layer has read its activations
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int t = gtid + 128 * u;
+      act[(t >> 5) * M64_STR + 32 * grp + (t & 31)] = xin[u];
     }
-    compute_sync();
+    group_sync(grp);
     int s = 0;
+    long long dbg_store[3 * C1D_MAX_LAYERS];
+    const bool dbg_on = p.debug && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && it == 1;
+    const long long tt0 = dbg_on ? clock64() : 0;
     for (int l = 0; l < p.n_layers; ++l) {
+      long long* dbg = dbg_on ? dbg_store + 3 * l : nullptr;
+      if (dbg) dbg[0] = dbg[1] = dbg[2] = 0;
       const bool is_out = l == p.n_layers - 1;
+      if (l == p.n_layers - 2 && it + 1 < my_tiles)
+        load_inputs(p, emu_in, emu_lo, emu_hi, (((it + 1) * gridDim.x + blockIdx.x) * 2 + grp) * M64_ROWS, nrows, gtid, xin);
       const int nb = (p.nbt[l] + 3) >> 2;
       switch (nb) {
-        case 1: m64_layer<1>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
-        case 2: m64_layer<2>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
-        case 3: m64_layer<3>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
-        case 4: m64_layer<4>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
-        case 5: m64_layer<5>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
-        case 6: m64_layer<6>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
-        case 7: m64_layer<7>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
-        default: m64_layer<8>(p, l, s, q, bar_full, bar_empty, act, wbuf, is_out, row0, nrows, out, out_stride); break;
+        case 1: m64_layer<1>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        case 2: m64_layer<2>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        case 3: m64_layer<3>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        case 4: m64_layer<4>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        case 5: m64_layer<5>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        case 6: m64_layer<6>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        case 7: m64_layer<7>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        default: m64_layer<8>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+      }
+    }
+    if (dbg_on) {
+      const long long tt1 = clock64();
+      for (int w = 0; w < M64_CWARPS; ++w) {
+        if (w == warp) {
+          printf("mlp64 warp %d tile cycles %lld | per layer wait/compute/epilogue:", warp, tt1 - tt0);
+          for (int l = 0; l < p.n_layers; ++l) printf(" L%d %lld/%lld/%lld", l, dbg_store[3 * l], dbg_store[3 * l + 1], dbg_store[3 * l + 2]);
+          printf("\n");
+        }
       }
     }
   }
@@ -288,6 +356,8 @@ int c1d_mlp64_prepare(c1d_ctx* ctx) {
   p.n_in = c.layer_dims[0];
   p.n_out = c.layer_dims[L];
   p.slope = c.nn_slope;
+  p.debug = getenv("C1D_MLP64_DEBUG") ? 1 : 0;
+  p.skew = getenv("C1D_MLP64_SKEW") ? atoi(getenv("C1D_MLP64_SKEW")) : 2500;
   std::vector<double> img, bimg;
   int n_slabs = 0;
   for (int l = 0; l < L; ++l) {
@@ -326,6 +396,11 @@ int c1d_mlp64_prepare(c1d_ctx* ctx) {
     }
   }
   p.n_slabs = n_slabs;
+  p.n_bias = (int)bimg.size();
+  if (p.n_bias > M64_MAXBIAS) {
+    snprintf(ctx->err, sizeof(ctx->err), "fp64 MLP bias table overflow");
+    return C1D_ERR_ARG;
+  }
   C1D_CUDA(ctx, cudaMalloc(&st->d_w, img.size() * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&st->d_b, bimg.size() * sizeof(double)));
   C1D_CUDA(ctx, cudaMemcpy(st->d_w, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -342,8 +417,8 @@ int c1d_mlp64_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* 
     snprintf(ctx->err, sizeof(ctx->err), "fp64 MLP not prepared");
     return C1D_ERR_STATE;
   }
-  const int64_t ntiles = (nrows + M64_ROWS - 1) / M64_ROWS;
-  const int grid = (int)(ntiles < ctx->num_sms ? ntiles : ctx->num_sms);
+  const int64_t npairs = (nrows + 2 * M64_ROWS - 1) / (2 * M64_ROWS);
+  const int grid = (int)(npairs < ctx->num_sms ? npairs : ctx->num_sms);
   k_mlp_f64<<<grid, M64_THREADS, M64_SMEM, s>>>(st->p, emu_in, ctx->d.emu_lo, ctx->d.emu_hi, nrows, out, out_stride);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
