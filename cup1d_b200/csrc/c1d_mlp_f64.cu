@@ -46,7 +46,7 @@ struct M64Slab {
 };
 
 struct M64Plan {
-  int n_layers, n_slabs, n_in, n_out, debug, skew, n_bias;
+  int n_layers, n_slabs, n_in, n_out, debug, n_bias;
   double slope;
   const double* wimg;  // padded weights, layer after layer, [Kp][Np]
   const double* bimg;  // padded biases
@@ -263,12 +263,6 @@ k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict
   const int grp = warp >> 2, gtid = threadIdx.x & 127;
   uint32_t q = 0;
   double xin[2];
-  if (grp == 1 && p.skew > 0) {
-    // start the second group half a slab late: the two groups then reach their layer epilogues at
-    // different times, and each hides the other's under its DMMAs
-    const long long t0 = clock64();
-    while (clock64() - t0 < p.skew) {}
-  }
   for (int64_t it = 0; it < my_tiles; ++it) {
     const int64_t tile = (it * gridDim.x + blockIdx.x) * 2 + grp;
     const int64_t row0 = tile * M64_ROWS;
@@ -357,7 +351,6 @@ int c1d_mlp64_prepare(c1d_ctx* ctx) {
   p.n_out = c.layer_dims[L];
   p.slope = c.nn_slope;
   p.debug = getenv("C1D_MLP64_DEBUG") ? 1 : 0;
-  p.skew = getenv("C1D_MLP64_SKEW") ? atoi(getenv("C1D_MLP64_SKEW")) : 2500;
   std::vector<double> img, bimg;
   int n_slabs = 0;
   for (int l = 0; l < L; ++l) {

@@ -58,8 +58,11 @@ class B200Likelihood(object):
         self.zoff_d = fields["ZOFF_D"].astype(int)
         self._zmask_key = None
         self.set_emulator_precision(emulator_precision)
+        self._set_logdet()
+
+    def _set_logdet(self):
+        """constants for ignore_log_det_cov=False (likelihood.py:950, 962)"""
         d = self.spec["data"]
-        # constants for ignore_log_det_cov=False (likelihood.py:950, 962)
         self._logdet_z = np.array([np.log(np.abs(1 / np.linalg.det(c))) for c in d["icov"]])
         self._logdet_full = None
         if d["full_icov"] is not None:
@@ -87,6 +90,27 @@ class B200Likelihood(object):
             o += len(k)
         if self.spec["data"]["full_icov"] is not None:
             self.spec["data"]["full_Pk_kms"] = v.copy()
+
+    def set_icov(self, icov_Pk_kms, full_icov_Pk_kms=None):
+        """Replace the inverse covariances stage 4 keeps on the device: the
+        per-z blocks ``icov_Pk_kms`` and, for a full-covariance context, ``full_icov_Pk_kms`` —
+        the attributes ``Likelihood.set_icov`` fills (likelihood.py:385-399, 496-503), e.g. from
+        ``cup1d_b200.covariance.build_covariance``.  Shapes must match the context."""
+        d = self.spec["data"]
+        blocks = [np.ascontiguousarray(c, dtype=float) for c in icov_Pk_kms]
+        if len(blocks) != self.nz or any(b.shape != (len(k), len(k)) for b, k in zip(blocks, d["k_kms"])):
+            raise ValueError("per-z inverse covariance blocks do not match the data vector")
+        if self.has_full != (full_icov_Pk_kms is not None):
+            raise ValueError("context was built %s a full inverse covariance" % ("with" if self.has_full else "without"))
+        self.ctx.upload("ICOV_BLOCKS", np.concatenate([b.reshape(-1) for b in blocks]))
+        d["icov"] = blocks
+        if self.has_full:
+            full = np.ascontiguousarray(full_icov_Pk_kms, dtype=float)
+            if full.shape != (self.nd, self.nd):
+                raise ValueError("full inverse covariance shape")
+            self.ctx.upload("ICOV_FULL", full)
+            d["full_icov"] = full
+        self._set_logdet()
 
     def get_blobs_dtype(self):
         """lya_theory.py:500-512"""
