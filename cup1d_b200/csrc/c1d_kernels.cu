@@ -246,10 +246,18 @@ int c1d_launch_emulator(c1d_ctx* ctx, const double* emu_in, int64_t nrows, doubl
 #define P1D_WARPS (P1D_THREADS / 32)
 #define P1D_CHUNK 32   // walkers per work item
 #define P1D_NPAIR (C1D_NCOL / 2)
+// position (in double2 units) of column pair pr of fine point i in the staged tables
+#define P1D_TIDX(pr, i) ((((i) >> 5) * P1D_NPAIR + (pr)) * 32 + ((i) & 31))
 
-// 10^x for the emulator polynomial: 2^(x log2 10) with a two-term constant and a degree-12
+// 10^x for the emulator polynomial: 2^(x log2 10) with a two-term constant and a degree-13
 // polynomial for 2^r on |r| <= 1/2 (relative error ~2e-16); outside the safe exponent range
-// the library function is used.
+// the library function is used.  The coefficients ln2^k / k! sit in constant memory (DFMA takes
+// them as constant-bank operands, no per-use register moves) and the polynomial is evaluated in
+// Estrin form: dependent depth 4 instead of 13, which matters with 4 warps per sub-partition.
+__constant__ double c_exp2[14] = {1.0, 0.6931471805599453, 0.2402265069591007, 0.055504108664821576, 0.009618129107628477,
+                                  0.0013333558146428441, 0.00015403530393381606, 1.5252733804059838e-05,
+                                  1.3215486790144305e-06, 1.0178086009239696e-07, 7.054911620801121e-09,
+                                  4.44553827187081e-10, 2.5678435993488196e-11, 1.3691488853904124e-12};
 __device__ __forceinline__ double exp10_poly(double x) {
   if (!(fabs(x) < 280.0)) return exp10(x);
   const double L2_10_HI = 3.321928094887362, L2_10_LO = 1.661617516973592e-16;
@@ -257,20 +265,16 @@ __device__ __forceinline__ double exp10_poly(double x) {
   const double n = (double)ni;
   double r = fma(x, L2_10_HI, -n);
   r = fma(x, L2_10_LO, r);
-  double p = 1.3691488853904124e-12;  // ln2^k / k!, k = 13 .. 0
-  p = fma(p, r, 2.5678435993488196e-11);
-  p = fma(p, r, 4.44553827187081e-10);
-  p = fma(p, r, 7.054911620801121e-09);
-  p = fma(p, r, 1.0178086009239696e-07);
-  p = fma(p, r, 1.3215486790144305e-06);
-  p = fma(p, r, 1.5252733804059838e-05);
-  p = fma(p, r, 0.00015403530393381606);
-  p = fma(p, r, 0.0013333558146428441);
-  p = fma(p, r, 0.009618129107628477);
-  p = fma(p, r, 0.055504108664821576);
-  p = fma(p, r, 0.2402265069591007);
-  p = fma(p, r, 0.6931471805599453);
-  p = fma(p, r, 1.0);
+  const double r2 = r * r;
+  const double a0 = fma(c_exp2[1], r, c_exp2[0]), a1 = fma(c_exp2[3], r, c_exp2[2]);
+  const double a2 = fma(c_exp2[5], r, c_exp2[4]), a3 = fma(c_exp2[7], r, c_exp2[6]);
+  const double a4 = fma(c_exp2[9], r, c_exp2[8]), a5 = fma(c_exp2[11], r, c_exp2[10]);
+  const double a6 = fma(c_exp2[13], r, c_exp2[12]);
+  const double r4 = r2 * r2;
+  const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+  const double r8 = r4 * r4;
+  const double d0 = fma(b1, r4, b0), d1 = fma(a6, r4, b2);
+  const double p = fma(d1, r8, d0);
   return p * __longlong_as_double((long long)(ni + 1023) << 52);
 }
 
@@ -298,8 +302,8 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
   extern __shared__ __align__(16) double sm[];
   const int RW = c.rebin_width, RWP = RW | 1;        // odd row stride: conflict-free
   const int pb_len = nfz_max + (nfz_max >> 3) + 2;   // P(i) lives at i + i/8
-  double2* tab2 = reinterpret_cast<double2*>(sm);    // [P1D_NPAIR][nfz_max] column pairs
-  double* pbuf = sm + (size_t)2 * P1D_NPAIR * nfz_max;   // [P1D_WARPS][pb_len]
+  double2* tab2 = reinterpret_cast<double2*>(sm);    // [blocks of 32 points][P1D_NPAIR][32] column pairs
+  double* pbuf = sm + (size_t)2 * P1D_NPAIR * ((nfz_max + 31) & ~31);   // [P1D_WARPS][pb_len]
   double* rbw = pbuf + (size_t)P1D_WARPS * pb_len;   // [ndz_max][RWP]
   double* dat = rbw + (size_t)ndz_max * RWP;         // [ndz_max]
   double* dzb = dat + ndz_max;                       // [P1D_WARPS][ndz_max]
@@ -333,10 +337,12 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
     if (c_lo >= c_hi) continue;
 
     __syncthreads();  // previous z fully processed before its tables are overwritten
+    // table layout [block of 32 points][8 column pairs][32 lanes]: a lane reads all pairs of its
+    // point at compile-time offsets from one pointer that advances by one block per iteration
     for (int t = threadIdx.x; t < P1D_NPAIR * nfz; t += blockDim.x) {
       int pr = t / nfz, i = t % nfz;
-      tab2[pr * nfz_max + i] = make_double2(c.tab[(size_t)(2 * pr) * c.nf + f0 + i],
-                                            c.tab[(size_t)(2 * pr + 1) * c.nf + f0 + i]);
+      tab2[P1D_TIDX(pr, i)] = make_double2(c.tab[(size_t)(2 * pr) * c.nf + f0 + i],
+                                           c.tab[(size_t)(2 * pr + 1) * c.nf + f0 + i]);
     }
     for (int t = threadIdx.x; t < ndz * RW; t += blockDim.x)
       rbw[(t / RW) * RWP + (t % RW)] = c.rb_wgt[(size_t)d0 * RW + t];
@@ -345,15 +351,6 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
       rbs[t] = c.rb_start[d0 + t];
     }
     __syncthreads();
-    const double2* tKS = tab2 + (C1D_COL_K / 2) * nfz_max;      // (k, S)
-    const double2* tTT1 = tab2 + (C1D_COL_T / 2) * nfz_max;     // (t, T1)
-    const double2* t2 = tab2 + (C1D_COL_T2A / 2) * nfz_max;     // (T2A, T2BC)
-    const double2* t3 = tab2 + (C1D_COL_T3A / 2) * nfz_max;     // (T3A, T3BC)
-    const double2* tD12 = tab2 + (C1D_COL_D1 / 2) * nfz_max;    // (D1, D2)
-    const double2* tD34 = tab2 + (C1D_COL_D3 / 2) * nfz_max;    // (D3, D4)
-    const double2* tKQ = tab2 + (C1D_COL_KT / 2) * nfz_max;     // (KT, Q)
-    const double2* tAG = tab2 + (C1D_COL_AGN / 2) * nfz_max;    // (AGN delta, spare)
-
     const int64_t w_begin = c_lo * P1D_CHUNK;
     int64_t w_end = c_hi * P1D_CHUNK;
     if (w_end > W) w_end = W;
@@ -368,21 +365,29 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
         if (chi2z && lane == 0) chi2z[w * c.nz + z] = 0.0;
         continue;
       }
-      const double* a = amp + ((int64_t)z * W + w) * C1D_NAMP;
-      double av = (lane < C1D_NAMP) ? a[lane] : 0.0;
+      // amplitude record of (z, walker): every lane loads the same 16-byte words (one broadcast
+      // transaction each)
+      const double2* a2p = reinterpret_cast<const double2*>(amp + ((int64_t)z * W + w) * C1D_NAMP);
+      double av[C1D_NAMP];
+#pragma unroll
+      for (int j = 0; j < C1D_NAMP / 2; ++j) {
+        const double2 v = __ldg(a2p + j);
+        av[2 * j] = v.x;
+        av[2 * j + 1] = v.y;
+      }
       double cf[C1D_MAX_COEF];
 #pragma unroll
-      for (int j = 0; j < C1D_MAX_COEF; ++j) cf[j] = __shfl_sync(0xffffffffu, av, A_COEF0 + j);
-      const double s3 = __shfl_sync(0xffffffffu, av, A_S3), s2 = __shfl_sync(0xffffffffu, av, A_S2);
-      const double m0 = __shfl_sync(0xffffffffu, av, A_M0), c1 = __shfl_sync(0xffffffffu, av, A_C1);
-      const double c2a = __shfl_sync(0xffffffffu, av, A_C2A), c2b = __shfl_sync(0xffffffffu, av, A_C2B);
-      const double c3a = __shfl_sync(0xffffffffu, av, A_C3A), c3b = __shfl_sync(0xffffffffu, av, A_C3B);
-      const double h0 = __shfl_sync(0xffffffffu, av, A_H0);
-      const double hA = __shfl_sync(0xffffffffu, av, A_HCD1 + 0), hB = __shfl_sync(0xffffffffu, av, A_HCD1 + 1);
-      const double hC = __shfl_sync(0xffffffffu, av, A_HCD1 + 2), hD = __shfl_sync(0xffffffffu, av, A_HCD1 + 3);
-      const double aa = __shfl_sync(0xffffffffu, av, A_AA), sa2 = __shfl_sync(0xffffffffu, av, A_SA2);
-      const double res = __shfl_sync(0xffffffffu, av, A_RES);
-      const double fagn = __shfl_sync(0xffffffffu, av, A_AGN);
+      for (int j = 0; j < C1D_MAX_COEF; ++j) cf[j] = av[A_COEF0 + j];
+      const double s3 = av[A_S3], s2 = av[A_S2];
+      const double m0 = av[A_M0], c1 = av[A_C1];
+      const double c2a = av[A_C2A], c2b = av[A_C2B];
+      const double c3a = av[A_C3A], c3b = av[A_C3B];
+      const double h0 = av[A_H0];
+      const double hA = av[A_HCD1 + 0], hB = av[A_HCD1 + 1];
+      const double hC = av[A_HCD1 + 2], hD = av[A_HCD1 + 3];
+      const double aa = av[A_AA], sa2 = av[A_SA2];
+      const double res = av[A_RES];
+      const double fagn = av[A_AGN];
 
       // exp(-s k) and exp(-s^2 k^2) on an evenly spaced grid advance by constant ratios:
       // one exp per term and lane instead of one per point
@@ -390,8 +395,8 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
       const double sg3 = (METAL == 0) ? -s3 : s3;  // SiVid grows with k (si_vid_final.py:208)
       double E3 = 0.0, R3 = 0.0, E2 = 0.0, R2 = 0.0, gg = 0.0, grho = 0.0, gq = 0.0;
       if (uni) {
-        const double dk32 = 32.0 * ((tKS[nfz - 1].x - tKS[0].x) / (double)(nfz - 1));
-        const double kl = tKS[lane < nfz ? lane : 0].x;
+        const double dk32 = 32.0 * ((tab2[P1D_TIDX(C1D_COL_K / 2, nfz - 1)].x - tab2[P1D_TIDX(C1D_COL_K / 2, 0)].x) / (double)(nfz - 1));
+        const double kl = tab2[P1D_TIDX(C1D_COL_K / 2, lane < nfz ? lane : 0)].x;
         E3 = exp(sg3 * kl);
         R3 = exp(sg3 * dk32);
         E2 = exp(-s2 * kl);
@@ -400,8 +405,9 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
         grho = exp(-1.0 * sa2 * (2.0 * kl * dk32 + dk32 * dk32));
         gq = exp(-2.0 * sa2 * (dk32 * dk32));
       }
-      for (int i = lane; i < nfz; i += 32) {
-        const double2 ks = tKS[i], tt1 = tTT1[i];
+      const double2* tp = tab2 + lane;  // this lane's point of the current block
+      for (int i = lane; i < nfz; i += 32, tp += P1D_NPAIR * 32) {
+        const double2 ks = tp[(C1D_COL_K / 2) * 32], tt1 = tp[(C1D_COL_T / 2) * 32];  // (k, S), (t, T1)
         const double k = ks.x;
         if (!uni) {
           E3 = exp(sg3 * k);
@@ -422,7 +428,7 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
         double mult;
         if (METAL == 0) {
           // si_mult.py:212-218, 267-341:  G = 2 - 2/(1 + E)
-          const double2 v2 = t2[i], v3 = t3[i];
+          const double2 v2 = tp[(C1D_COL_T2A / 2) * 32], v3 = tp[(C1D_COL_T3A / 2) * 32];  // (T2A, T2BC), (T3A, T3BC)
           const double G3 = fma(-2.0, rcp_fast(1.0 + E3), 2.0);
           const double G2 = fma(-2.0, rcp_fast(1.0 + E2), 2.0);
           mult = m0 + (c1 * G3 * tt1.y + G2 * (c2a * v2.x + c2b * v2.y)) + (c3a * v3.x + c3b * v3.y);
@@ -430,9 +436,9 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
           // si_vid_final.py:205-219
           mult = 1.0 + c1 * E3 + c2a * tt1.y * E2;
         }
-        if (c.has_agn) mult *= fma(fagn, tAG[i].x, 1.0);  // AGN_model.py:116-120: 1 + f_AGN delta
+        if (c.has_agn) mult *= fma(fagn, tp[(C1D_COL_AGN / 2) * 32].x, 1.0);  // AGN_model.py:116-120: 1 + f_AGN delta
         // hcd_model_rogers_class.py:115-135 (or hcd_boss.py:5-7 through D1)
-        const double2 d12 = tD12[i], d34 = tD34[i], kq = tKQ[i];
+        const double2 d12 = tp[(C1D_COL_D1 / 2) * 32], d34 = tp[(C1D_COL_D3 / 2) * 32], kq = tp[(C1D_COL_KT / 2) * 32];  // (D1, D2), (D3, D4), (KT, Q)
         const double hcd = h0 + hA * d12.x + hB * d12.y + hC * d34.x + hD * d34.y;
         // si_add.py:168-219
         const double add = aa * kq.x * gg;
@@ -487,7 +493,7 @@ int c1d_launch_stage3(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int
   int nfz_max = ctx->nfz_max, ndz_max = ctx->ndz_max;
   const int RWP = cfg.rebin_width | 1;
   const int pb_len = nfz_max + (nfz_max >> 3) + 2;
-  size_t smem = ((size_t)C1D_NCOL * nfz_max + (size_t)P1D_WARPS * pb_len + (size_t)ndz_max * RWP + ndz_max +
+  size_t smem = ((size_t)C1D_NCOL * ((nfz_max + 31) & ~31) + (size_t)P1D_WARPS * pb_len + (size_t)ndz_max * RWP + ndz_max +
                  (size_t)P1D_WARPS * ndz_max) * sizeof(double) + (size_t)ndz_max * sizeof(int) + 16;
   if (smem > 227 * 1024) {
     snprintf(ctx->err, sizeof(ctx->err), "stage 3 needs %zu B of shared memory (z-bin too large)", smem);
