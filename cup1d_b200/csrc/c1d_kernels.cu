@@ -278,6 +278,30 @@ __device__ __forceinline__ double exp10_poly(double x) {
   return p * __longlong_as_double((long long)(ni + 1023) << 52);
 }
 
+// e^x with the same 2^r polynomial (log2 e in two terms); |x| < 700, else the library function.
+// Used for the per-(walker, z) ratio set-up of the exp recurrences.
+__device__ __forceinline__ double exp_poly(double x) {
+  if (!(fabs(x) < 700.0)) return exp(x);
+  const double L2E_HI = 1.4426950408889634, L2E_LO = 2.0355273740931033e-17;
+  const int ni = __double2int_rn(x * L2E_HI);
+  const double n = (double)ni;
+  double r = fma(x, L2E_HI, -n);
+  r = fma(x, L2E_LO, r);
+  const double r2 = r * r;
+  const double a0 = fma(c_exp2[1], r, c_exp2[0]), a1 = fma(c_exp2[3], r, c_exp2[2]);
+  const double a2 = fma(c_exp2[5], r, c_exp2[4]), a3 = fma(c_exp2[7], r, c_exp2[6]);
+  const double a4 = fma(c_exp2[9], r, c_exp2[8]), a5 = fma(c_exp2[11], r, c_exp2[10]);
+  const double a6 = fma(c_exp2[13], r, c_exp2[12]);
+  const double r4 = r2 * r2;
+  const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+  const double r8 = r4 * r4;
+  const double d0 = fma(b1, r4, b0), d1 = fma(a6, r4, b2);
+  const double p = fma(d1, r8, d0);
+  // split the scale so that results down to the subnormal range stay exact enough
+  const int h = ni >> 1;
+  return p * __longlong_as_double((long long)(h + 1023) << 52) * __longlong_as_double((long long)(ni - h + 1023) << 52);
+}
+
 // reciprocal to ~1 ulp: hardware seed + two Newton steps
 __device__ __forceinline__ double rcp_fast(double x) {
   double y;
@@ -307,7 +331,8 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
   double* rbw = pbuf + (size_t)P1D_WARPS * pb_len;   // [ndz_max][RWP]
   double* dat = rbw + (size_t)ndz_max * RWP;         // [ndz_max]
   double* dzb = dat + ndz_max;                       // [P1D_WARPS][ndz_max]
-  int* rbs = reinterpret_cast<int*>(dzb + (size_t)P1D_WARPS * ndz_max);  // [ndz_max]
+  int* rbs = reinterpret_cast<int*>(dzb + (size_t)P1D_WARPS * ndz_max);  // [ndz_max] first fine point of a bin
+  int* rbn = rbs + ndz_max;                                              // [ndz_max] taps up to the last non-zero weight
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* pb = pbuf + (size_t)warp * pb_len;
@@ -348,7 +373,12 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
       rbw[(t / RW) * RWP + (t % RW)] = c.rb_wgt[(size_t)d0 * RW + t];
     for (int t = threadIdx.x; t < ndz; t += blockDim.x) {
       dat[t] = c.data[d0 + t];
-      rbs[t] = c.rb_start[d0 + t];
+      const int st = c.rb_start[d0 + t];
+      rbs[t] = st;
+      int cnt = RW;
+      while (cnt > 1 && c.rb_wgt[(size_t)(d0 + t) * RW + cnt - 1] == 0.0) --cnt;
+      if (st + cnt > nfz) cnt = nfz - st;  // taps beyond the grid carry no weight
+      rbn[t] = cnt < 0 ? 0 : cnt;
     }
     __syncthreads();
     const int64_t w_begin = c_lo * P1D_CHUNK;
@@ -397,13 +427,16 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
       if (uni) {
         const double dk32 = 32.0 * ((tab2[P1D_TIDX(C1D_COL_K / 2, nfz - 1)].x - tab2[P1D_TIDX(C1D_COL_K / 2, 0)].x) / (double)(nfz - 1));
         const double kl = tab2[P1D_TIDX(C1D_COL_K / 2, lane < nfz ? lane : 0)].x;
-        E3 = exp(sg3 * kl);
-        R3 = exp(sg3 * dk32);
-        E2 = exp(-s2 * kl);
-        R2 = exp(-s2 * dk32);
-        gg = exp(-1.0 * sa2 * (kl * kl));
-        grho = exp(-1.0 * sa2 * (2.0 * kl * dk32 + dk32 * dk32));
-        gq = exp(-2.0 * sa2 * (dk32 * dk32));
+        E3 = exp_poly(sg3 * kl);
+        E2 = exp_poly(-s2 * kl);
+        gg = exp_poly(-1.0 * sa2 * (kl * kl));
+        grho = exp_poly(-1.0 * sa2 * (2.0 * kl * dk32 + dk32 * dk32));
+        // the three lane-independent ratios come from ONE evaluation: lanes 0..2 take one argument each
+        const double arg = (lane == 0) ? sg3 * dk32 : (lane == 1) ? -s2 * dk32 : -2.0 * sa2 * (dk32 * dk32);
+        const double rr = exp_poly(arg);
+        R3 = __shfl_sync(0xffffffffu, rr, 0);
+        R2 = __shfl_sync(0xffffffffu, rr, 1);
+        gq = __shfl_sync(0xffffffffu, rr, 2);
       }
       const double2* tp = tab2 + lane;  // this lane's point of the current block
       for (int i = lane; i < nfz; i += 32, tp += P1D_NPAIR * 32) {
@@ -456,12 +489,12 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
       __syncwarp();
       // rebinning (likelihood.py:147-161) and residual (likelihood.py:939, 957)
       for (int j = lane; j < ndz; j += 32) {
-        const int st = rbs[j];
+        const int st = rbs[j], cnt = rbn[j];
+        const double* wr = rbw + j * RWP;
         double m = 0.0;
-        for (int t = 0; t < RW; ++t) {
-          int ii = st + t;
-          double pv = (ii < nfz) ? pb[ii + (ii >> 3)] : 0.0;
-          m = fma(rbw[j * RWP + t], pv, m);
+        for (int t = 0; t < cnt; ++t) {
+          const int ii = st + t;
+          m = fma(wr[t], pb[ii + (ii >> 3)], m);
         }
         const double dj = dat[j] - m;
         if (dvec) dvec[w * c.ldd + d0 + j] = dj;
@@ -494,7 +527,7 @@ int c1d_launch_stage3(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int
   const int RWP = cfg.rebin_width | 1;
   const int pb_len = nfz_max + (nfz_max >> 3) + 2;
   size_t smem = ((size_t)C1D_NCOL * ((nfz_max + 31) & ~31) + (size_t)P1D_WARPS * pb_len + (size_t)ndz_max * RWP + ndz_max +
-                 (size_t)P1D_WARPS * ndz_max) * sizeof(double) + (size_t)ndz_max * sizeof(int) + 16;
+                 (size_t)P1D_WARPS * ndz_max) * sizeof(double) + 2 * (size_t)ndz_max * sizeof(int) + 16;
   if (smem > 227 * 1024) {
     snprintf(ctx->err, sizeof(ctx->err), "stage 3 needs %zu B of shared memory (z-bin too large)", smem);
     return C1D_ERR_ARG;
