@@ -604,6 +604,10 @@ k_chi2_dmma(int64_t W, int ndp, const double* __restrict__ dvec, const double* _
   double (*red)[Q_TW] = reinterpret_cast<double (*)[Q_TW]>(qsm + 2 * Q_TW * Q_ASTR + 2 * Q_KC * Q_BSTR);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;
+  // walker tiles are the fast grid index: all CTAs in flight stream the same two column tiles of C^-1.
+  // (Measured alternative, column-tile pairs fastest: the residuals are then read from HBM once, 371 MB
+  // instead of 1.94 GB per launch, but the kernel takes 1.28 ms instead of 1.10 ms — it is DMMA-bound,
+  // the extra reads are hidden — so the faster order stays.)
   const int64_t w0 = (int64_t)blockIdx.x * Q_TW;
   const int ntj = ndp / Q_TJ;
   const int pair = blockIdx.y;
