@@ -25,6 +25,14 @@
 
 #include "c1d_internal.h"
 
+// -DC1D_MLP64_TIMING compiles the per-layer cycle counters in (C1D_MLP64_DEBUG=1 prints them); the
+// product build leaves them out: the counter array otherwise costs registers and local memory
+#ifdef C1D_MLP64_TIMING
+#define M64_DBG(x) x
+#else
+#define M64_DBG(x)
+#endif
+
 namespace {
 
 constexpr int M64_ROWS = 32;                          // rows of one group's tile
@@ -146,9 +154,9 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
   for (;;) {
     const M64Slab sl = p.slabs[s];
     const uint32_t buf = q % M64_NBUF;
-    const long long tw0 = dbg ? clock64() : 0;
+    M64_DBG(const long long tw0 = dbg ? clock64() : 0;)
     mbar_wait(bar_full + 8 * buf, (q / M64_NBUF) & 1u);  // slab q has landed
-    const long long tw1 = dbg ? clock64() : 0;
+    M64_DBG(const long long tw1 = dbg ? clock64() : 0;)
     const double* wb = wbuf + buf * M64_SLAB;
     if (cnt > 0) {
       const double* ap = act + (size_t)(sl.k0 + kq) * M64_STR + r0 + g;
@@ -171,12 +179,12 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty + 8 * buf);  // this warp is done with the buffer
-    if (dbg) { dbg[0] += tw1 - tw0; dbg[1] += clock64() - tw1; }
+    M64_DBG(if (dbg) { dbg[0] += tw1 - tw0; dbg[1] += clock64() - tw1; })
     ++s;
     ++q;
     if (sl.last) break;
   }
-  const long long te0 = dbg ? clock64() : 0;
+  M64_DBG(const long long te0 = dbg ? clock64() : 0;)
   if (!is_out) {
     group_sync(grp);  // every read of the input activations is done
     const double slope = p.slope;
@@ -200,7 +208,7 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
       }
     }
     group_sync(grp);  // activations of the next layer are visible
-    if (dbg) dbg[2] += clock64() - te0;
+    M64_DBG(if (dbg) dbg[2] += clock64() - te0;)
   } else {
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
@@ -277,12 +285,14 @@ k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict
     }
     group_sync(grp);
     int s = 0;
+#ifdef C1D_MLP64_TIMING
     long long dbg_store[3 * C1D_MAX_LAYERS];
     const bool dbg_on = p.debug && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && it == 1;
     const long long tt0 = dbg_on ? clock64() : 0;
+#endif
     for (int l = 0; l < p.n_layers; ++l) {
-      long long* dbg = dbg_on ? dbg_store + 3 * l : nullptr;
-      if (dbg) dbg[0] = dbg[1] = dbg[2] = 0;
+      long long* dbg = nullptr;
+      M64_DBG(dbg = dbg_on ? dbg_store + 3 * l : nullptr; if (dbg) dbg[0] = dbg[1] = dbg[2] = 0;)
       const bool is_out = l == p.n_layers - 1;
       if (l == p.n_layers - 2 && it + 1 < my_tiles)
         load_inputs(p, emu_in, emu_lo, emu_hi, (((it + 1) * gridDim.x + blockIdx.x) * 2 + grp) * M64_ROWS, nrows, gtid, xin);
@@ -298,6 +308,7 @@ k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict
         default: m64_layer<8>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
       }
     }
+#ifdef C1D_MLP64_TIMING
     if (dbg_on) {
       const long long tt1 = clock64();
       for (int w = 0; w < M64_CWARPS; ++w) {
@@ -308,6 +319,7 @@ k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict
         }
       }
     }
+#endif
   }
 }
 
