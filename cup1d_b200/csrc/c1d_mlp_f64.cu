@@ -4,8 +4,8 @@
 // (reference call site cup1d/likelihood/lya_theory.py:794-812; LaCE itself is not in the
 // reference tree, see oracle/emulators.py for the restated network).
 //
-// One CTA per SM works on two tiles of 32 rows ((walker, z) pairs) at a time, one per group of
-// four warps, and chains all layers with the activations resident in shared memory (k-major, row
+// One CTA per SM works on three tiles of 24 rows ((walker, z) pairs) at a time, one per group of
+// four warps (so every SM sub-partition holds one warp of each group), and chains all layers with the activations resident in shared memory (k-major, row
 // stride 68 doubles).  The groups share the weight stream but synchronise separately, so one
 // group's layer epilogue (pipeline drain, activation write-back, barrier) hides under the other
 // group's DMMAs on the same SM sub-partitions.  The weights of all
@@ -35,10 +35,13 @@
 
 namespace {
 
-constexpr int M64_ROWS = 32;                          // rows of one group's tile
-constexpr int M64_CWARPS = 8;                         // compute warps
+constexpr int M64_GROUPS = 3;                         // row groups per CTA (one warp of each per SM sub-partition)
+constexpr int M64_RB = 3;                             // 8-row blocks per group
+constexpr int M64_ROWS = 8 * M64_RB;                  // rows of one group's tile
+constexpr int M64_CWARPS = 4 * M64_GROUPS;            // compute warps
 constexpr int M64_THREADS = 32 * (M64_CWARPS + 1);   // + the weight streamer
-constexpr int M64_STR = 68;         // doubles per k-row of the activation tile (== 4 mod 16: conflict-free fragments)
+constexpr int M64_STR = M64_GROUPS * M64_ROWS + 4;   // doubles per k-row of the activation tile
+static_assert(M64_STR % 16 == 4 || M64_STR % 16 == 12, "k-row stride must spread fragments over all banks");
 constexpr int M64_MAXW = 256;       // widest layer
 constexpr int M64_NBUF = 2;         // weight slab buffers (ring)
 constexpr int M64_SLAB = 4224;      // doubles per weight slab buffer
@@ -101,16 +104,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // barrier among the four warps of one group (the streamer and the other group never join)
 __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
 
-// the two input values thread gtid of a group stages for a tile of 32 rows ([8 k-rows][32 rows])
+// the two input values thread gtid of a group stages for its tile ([8 k-rows][M64_ROWS rows])
 __device__ __forceinline__ void load_inputs(const M64Plan& p, const double* __restrict__ emu_in, const double* __restrict__ emu_lo,
                                             const double* __restrict__ emu_hi, int64_t row0, int64_t nrows, int gtid, double* xin) {
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int t = gtid + 128 * u;
-    const int j = t >> 5;
-    const int64_t row = row0 + (t & 31);
+    const int j = t / M64_ROWS;
+    const int64_t row = row0 + (t % M64_ROWS);
     double v = 0.0;
-    if (j < p.n_in && row < nrows) {
+    if (t < 8 * M64_ROWS && j < p.n_in && row < nrows) {
       const double lo = __ldg(emu_lo + j);
       v = (emu_in[row * C1D_MAX_EMU + j] - lo) / (__ldg(emu_hi + j) - lo) - 0.5;
     }
@@ -127,25 +130,26 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = warp >> 2, wn = warp & 3;
   const int kq = lane & 3, g = lane >> 2;
-  const int r0 = 32 * grp;
+  const int r0 = M64_ROWS * grp;
   const int nbt = p.nbt[l];
   const int base = nbt >> 2, rem = nbt & 3;
-  // blocks of this warp: NB or NB - 1; the rem odd blocks go to the first warps of group 0 and to the last of group 1
-  const int wx = grp ? 3 - wn : wn;
+  // blocks of this warp: NB or NB - 1; the rem odd blocks rotate over the n-warps from group to group so
+  // that the sub-partitions (one warp of every group each) carry the same number of blocks
+  const int wx = (wn + grp) & 3;
   const int cnt = base + (wx < rem ? 1 : 0);
-  const int before = grp ? (wn * base + (wn > 4 - rem ? wn - (4 - rem) : 0)) : (wn * base + (wn < rem ? wn : rem));
+  const int before = wx * base + (wx < rem ? wx : rem);
   const int n0 = 8 * before;  // first column
   const int ns = p.np[l] + 4;
   const bool last_blk = cnt == NB;  // the NB-th block exists for this warp
   // accumulators start from the bias (thread holds columns n0 + 8 nb + 2 kq + {0, 1} of rows r0 + 8 a + g)
   const double* bias = bsm + p.boff[l];
-  double acc[4][NB][2];
+  double acc[M64_RB][NB][2];
 #pragma unroll
   for (int nb = 0; nb < NB; ++nb) {
     const double b0 = (nb < cnt) ? bias[n0 + 8 * nb + 2 * kq] : 0.0;
     const double b1 = (nb < cnt) ? bias[n0 + 8 * nb + 2 * kq + 1] : 0.0;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < M64_RB; ++a) {
       acc[a][nb][0] = b0;
       acc[a][nb][1] = b1;
     }
@@ -163,16 +167,16 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
       const double* bp = wb + kq * ns + n0 + g;
 #pragma unroll 2
       for (int kk = 0; kk < (int)sl.kc; kk += 4) {
-        double af[4], bf[NB];
+        double af[M64_RB], bf[NB];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) af[a] = ap[kk * M64_STR + 8 * a];
+        for (int a = 0; a < M64_RB; ++a) af[a] = ap[kk * M64_STR + 8 * a];
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) bf[nb] = (nb < NB - 1 || last_blk) ? bp[kk * ns + 8 * nb] : 0.0;
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
           if (nb < NB - 1 || last_blk) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a) dmma8(acc[a][nb][0], acc[a][nb][1], af[a], bf[nb]);
+            for (int a = 0; a < M64_RB; ++a) dmma8(acc[a][nb][0], acc[a][nb][1], af[a], bf[nb]);
           }
         }
       }
@@ -196,7 +200,7 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
     for (int nb = 0; nb < NB; ++nb) {
       if (nb < cnt) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < M64_RB; ++a) {
           double v0 = acc[a][nb][0], v1 = acc[a][nb][1];
           if (__double2hiint(v0) < 0) v0 *= slope;  // padded columns stay exactly zero
           if (__double2hiint(v1) < 0) v1 *= slope;
@@ -218,7 +222,7 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
           const int n = n0 + 8 * nb + 2 * kq + e;
           if (n < p.n_out) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
+            for (int a = 0; a < M64_RB; ++a) {
               const int64_t row = row0 + 8 * a + g;
               if (row < nrows) out[row * out_stride + n] = acc[a][nb][e];
             }
@@ -250,7 +254,7 @@ k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict
   __syncthreads();
   // both groups walk the same number of tiles so that they consume the same slab stream
   // (surplus tiles hold no rows)
-  const int64_t my_tiles = (ntiles + 2 * (int64_t)gridDim.x - 1) / (2 * (int64_t)gridDim.x);
+  const int64_t my_tiles = (ntiles + M64_GROUPS * (int64_t)gridDim.x - 1) / (M64_GROUPS * (int64_t)gridDim.x);
   if (warp == M64_CWARPS) {
     // ============================== weight streamer ==============================
     if ((threadIdx.x & 31) == 0) {
@@ -272,7 +276,7 @@ k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict
   uint32_t q = 0;
   double xin[2];
   for (int64_t it = 0; it < my_tiles; ++it) {
-    const int64_t tile = (it * gridDim.x + blockIdx.x) * 2 + grp;
+    const int64_t tile = (it * gridDim.x + blockIdx.x) * M64_GROUPS + grp;
     const int64_t row0 = tile * M64_ROWS;
     // normalised inputs (x - lo)/(hi - lo) - 0.5, k rows padded to 8 with zeros; they were fetched
     // while the previous tile was in its last hidden layers
@@ -281,7 +285,7 @@ k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int t = gtid + 128 * u;
-      act[(t >> 5) * M64_STR + 32 * grp + (t & 31)] = xin[u];
+      if (t < 8 * M64_ROWS) act[(t / M64_ROWS) * M64_STR + M64_ROWS * grp + (t % M64_ROWS)] = xin[u];
     }
     group_sync(grp);
     int s = 0;
@@ -295,7 +299,7 @@ k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict
       M64_DBG(dbg = dbg_on ? dbg_store + 3 * l : nullptr; if (dbg) dbg[0] = dbg[1] = dbg[2] = 0;)
       const bool is_out = l == p.n_layers - 1;
       if (l == p.n_layers - 2 && it + 1 < my_tiles)
-        load_inputs(p, emu_in, emu_lo, emu_hi, (((it + 1) * gridDim.x + blockIdx.x) * 2 + grp) * M64_ROWS, nrows, gtid, xin);
+        load_inputs(p, emu_in, emu_lo, emu_hi, (((it + 1) * gridDim.x + blockIdx.x) * M64_GROUPS + grp) * M64_ROWS, nrows, gtid, xin);
       const int nb = (p.nbt[l] + 3) >> 2;
       switch (nb) {
         case 1: m64_layer<1>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
@@ -422,7 +426,7 @@ int c1d_mlp64_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* 
     snprintf(ctx->err, sizeof(ctx->err), "fp64 MLP not prepared");
     return C1D_ERR_STATE;
   }
-  const int64_t npairs = (nrows + 2 * M64_ROWS - 1) / (2 * M64_ROWS);
+  const int64_t npairs = (nrows + M64_GROUPS * M64_ROWS - 1) / (M64_GROUPS * M64_ROWS);
   const int grid = (int)(npairs < ctx->num_sms ? npairs : ctx->num_sms);
   k_mlp_f64<<<grid, M64_THREADS, M64_SMEM, s>>>(st->p, emu_in, ctx->d.emu_lo, ctx->d.emu_hi, nrows, out, out_stride);
   ctx->launches++;
