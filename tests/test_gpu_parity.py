@@ -241,3 +241,48 @@ def test_set_icov_replaces_the_metric(golden):
     with pytest.raises(ValueError):
         like.set_icov(new_blocks, None)
     like.close()
+
+
+def test_edge_batches(golden):
+    """empty, single-row and ragged batches; a batch that crosses the internal chunk size (131 072 walkers);
+    every row rejected; non-contiguous / float32 inputs"""
+    import torch
+
+    from oracle.model import OracleLikelihood
+
+    spec, ref = golden("c1_chab_nn")
+    like = _like(spec)
+    ora = OracleLikelihood(spec)
+    n = like.ndim
+    # empty
+    lnp, blobs = like.log_prob_and_blobs_batch(np.zeros((0, n)))
+    assert lnp.shape == (0,) and blobs.shape == (0, 6)
+    assert like.get_p1d_kms_batch(np.zeros((0, n))).shape == (0, like.nd)
+    # one row, and ragged sizes around the tile sizes of the kernels (24/64/72/128 rows, 32-walker items)
+    x = ref["x"]
+    exp = ref["lnprob_blobs"][:, 0]
+    for W in (1, 7, 23, 25, 33, 47):
+        got = like.log_prob_batch(x[:W])
+        ok = exp[:W] > -1e99
+        assert np.all(np.abs(got[ok] - exp[:W][ok]) <= _tol(exp[:W][ok]))
+        np.testing.assert_array_equal(got[~ok], exp[:W][~ok])
+    # every row outside the cube: exact min_log_like, NaN blobs (likelihood.py:989-994)
+    bad = np.full((5, n), 1.5)
+    lnp, blobs = like.log_prob_and_blobs_batch(bad)
+    assert np.all(lnp == like.min_log_like) and np.all(np.isnan(blobs))
+    # crossing the chunk boundary: rows are independent, so a tiled batch repeats its block bit for bit
+    reps = 131072 // len(x) + 2
+    big = torch.as_tensor(np.tile(x, (reps, 1)), device="cuda:0")
+    assert big.shape[0] > 131072
+    out = like.log_prob_batch(big)
+    first = out[: len(x)]
+    assert torch.equal(out.view(reps, len(x)), first[None, :].expand(reps, len(x)))
+    np.testing.assert_array_equal(first.cpu().numpy(), like.log_prob_batch(x))
+    # strided and float32 inputs are converted, not misread
+    xs = np.asfortranarray(x[:16])
+    np.testing.assert_array_equal(like.log_prob_batch(xs), like.log_prob_batch(x[:16]))
+    x32 = x[:16].astype(np.float32)
+    np.testing.assert_array_equal(like.log_prob_batch(x32), like.log_prob_batch(x32.astype(np.float64)))
+    # scalar API on a rejected point keeps the reference's conventions
+    assert ora.log_prob(bad[0].copy()) == like.log_prob(bad[0].copy()) == like.min_log_like
+    like.close()
