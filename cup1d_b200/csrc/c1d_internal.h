@@ -27,7 +27,8 @@ enum {
 };
 
 // walker status written by stage 1
-enum { ST_OK = 0, ST_OUT_OF_CUBE = 1, ST_REJECTED = 2 };
+// combined with atomicMax by the (walker, z) threads of stage 1: out-of-cube wins over a rejection
+enum { ST_OK = 0, ST_REJECTED = 1, ST_OUT_OF_CUBE = 2 };
 
 struct DevCtx {
   int nz, ndim, n_emu, nd, nf, ell_width, rebin_width, emu_kind, nc, n_layers;

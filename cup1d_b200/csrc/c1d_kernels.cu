@@ -21,57 +21,64 @@ __device__ __forceinline__ double param_value(const DevCtx& c, const double* xw,
   return c.pmin[i] + xw[i] * c.pscale[i];
 }
 
+// One thread per (walker, z): blockIdx.y is the redshift bin.  The z = 0 thread of a walker also does
+// the walker-level work (cube test, Gaussian prior, blobs, star-prior box).  The status word is zeroed
+// before the launch and combined with atomicMax (out of cube > rejected > ok).
 __global__ void __launch_bounds__(128)
 k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ status,
          double* __restrict__ lnprior, double* __restrict__ blobs, double* __restrict__ emu_in,
          double* __restrict__ amp, uint32_t flags) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= W) return;
+  const int z = blockIdx.y;
   const double* xw = x + w * c.ndim;
-  double* bl = blobs + w * 6;
-
-  // compute_log_prob: out of the unit cube (likelihood.py:989-994)
-  bool out = false;
-  double lp = 0.0;
-  for (int i = 0; i < c.ndim; ++i) {
-    double xi = xw[i];
-    out |= (xi > 1.0) | (xi < 0.0);
-    if (c.has_gauss) {
-      double d = c.prior_x0[i] - xi;  // get_log_prior, likelihood.py:1060-1063
-      lp += d * d * c.prior_w[i];
-    }
-  }
-  if (out) {
-    status[w] = ST_OUT_OF_CUBE;
-    lnprior[w] = 0.0;
-    double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    for (int i = 0; i < 6; ++i) bl[i] = qnan;  // Theory.get_blob(), lya_theory.py:514-523
-    return;
-  }
-  lnprior[w] = -lp;
 
   // primordial-power rescaling (lya_theory.py:281-307, 542-580)
   double ratio_As = 1.0, d_ns = 0.0, d_nrun = 0.0;
   if (c.idx_As >= 0) ratio_As = param_value(c, xw, c.idx_As) / c.As_fid;
   if (c.idx_ns >= 0) d_ns = param_value(c, xw, c.idx_ns) - c.ns_fid;
   if (c.idx_nrun >= 0) d_nrun = param_value(c, xw, c.idx_nrun) - c.nrun_fid;
-  double ln_rA = log(ratio_As);
-  double e_emu = exp(ln_rA + (d_ns + 0.5 * d_nrun * c.L_emu) * c.L_emu);
-  double dn_emu = d_ns + d_nrun * c.L_emu;
-  double b0 = c.blob_fid[0] * exp(ln_rA + (d_ns + 0.5 * d_nrun * c.L_star) * c.L_star);
-  double b1 = c.blob_fid[1] + d_ns + d_nrun * c.L_star;
-  double b2 = c.blob_fid[2] + d_nrun;
-  bl[0] = b0; bl[1] = b1; bl[2] = b2;
-  bl[3] = c.blob_fid[3]; bl[4] = c.blob_fid[4]; bl[5] = c.blob_fid[5];
+  const double ln_rA = log(ratio_As);
+  const double e_emu = exp(ln_rA + (d_ns + 0.5 * d_nrun * c.L_emu) * c.L_emu);
+  const double dn_emu = d_ns + d_nrun * c.L_emu;
 
-  // star-prior box (lya_theory.py:647-654)
-  bool rej = (b0 > c.star_hi[0]) | (b0 < c.star_lo[0]) | (b1 > c.star_hi[1]) | (b1 < c.star_lo[1]) |
-             (b2 > c.star_hi[2]) | (b2 < c.star_lo[2]);
+  if (z == 0) {
+    double* bl = blobs + w * 6;
+    // compute_log_prob: out of the unit cube (likelihood.py:989-994)
+    bool out = false;
+    double lp = 0.0;
+    for (int i = 0; i < c.ndim; ++i) {
+      double xi = xw[i];
+      out |= (xi > 1.0) | (xi < 0.0);
+      if (c.has_gauss) {
+        double d = c.prior_x0[i] - xi;  // get_log_prior, likelihood.py:1060-1063
+        lp += d * d * c.prior_w[i];
+      }
+    }
+    if (out) {
+      atomicMax(status + w, (int)ST_OUT_OF_CUBE);
+      lnprior[w] = 0.0;
+      double qnan = __longlong_as_double(0x7ff8000000000000LL);
+      for (int i = 0; i < 6; ++i) bl[i] = qnan;  // Theory.get_blob(), lya_theory.py:514-523
+    } else {
+      lnprior[w] = -lp;
+      double b0 = c.blob_fid[0] * exp(ln_rA + (d_ns + 0.5 * d_nrun * c.L_star) * c.L_star);
+      double b1 = c.blob_fid[1] + d_ns + d_nrun * c.L_star;
+      double b2 = c.blob_fid[2] + d_nrun;
+      bl[0] = b0; bl[1] = b1; bl[2] = b2;
+      bl[3] = c.blob_fid[3]; bl[4] = c.blob_fid[4]; bl[5] = c.blob_fid[5];
+      // star-prior box (lya_theory.py:647-654)
+      bool rej0 = (b0 > c.star_hi[0]) | (b0 < c.star_lo[0]) | (b1 > c.star_hi[1]) | (b1 < c.star_lo[1]) |
+                  (b2 > c.star_hi[2]) | (b2 < c.star_lo[2]);
+      if (rej0) atomicMax(status + w, (int)ST_REJECTED);
+    }
+  }
 
   const bool use_hull = (c.n_hull_facets > 0) && !(flags & C1D_FLAG_NO_HULL);
   const bool use_zmask = (flags & C1D_FLAG_ZMASK) != 0;
-
-  for (int z = 0; z < c.nz && !rej; ++z) {
+  bool rej = false;
+  // rows of walkers that end up rejected are written too (finite or not): later stages skip them by status
+  {
     double q[C1D_NQ];
 #pragma unroll 1
     for (int iq = 0; iq < C1D_NQ; ++iq) {
@@ -116,7 +123,6 @@ k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ st
         double val = c.hull_abc[3 * f] * p0 + c.hull_abc[3 * f + 1] * p1 + c.hull_abc[3 * f + 2];
         if (!(val <= c.hull_tol)) { rej = true; break; }
       }
-      if (rej) break;
     }
     double* eo = emu_in + ((int64_t)z * W + w) * C1D_MAX_EMU;
     for (int j = 0; j < C1D_MAX_EMU; ++j) eo[j] = ev[j];
@@ -154,14 +160,15 @@ k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ st
     a[A_RES] = c.apply_resolution ? q[C1D_Q_RES] : 0.0;  // lya_theory.py:712-722
     a[A_AGN] = (q[C1D_Q_AGN_CONST] > 0.0) ? q[C1D_Q_AGN] : 0.0;  // AGN_model.py:81-91
   }
-  status[w] = rej ? ST_REJECTED : ST_OK;
+  if (rej) atomicMax(status + w, (int)ST_REJECTED);
 }
 
 int c1d_launch_stage1(c1d_ctx* ctx, const double* x, int64_t W, double* blobs_out, uint32_t flags,
                       cudaStream_t s) {
   int threads = 128;
   int64_t blocks = (W + threads - 1) / threads;
-  k_stage1<<<(unsigned)blocks, threads, 0, s>>>(ctx->d, x, W, ctx->ws.status, ctx->ws.lnprior,
+  C1D_CUDA(ctx, cudaMemsetAsync(ctx->ws.status, 0, (size_t)W * sizeof(int), s));
+  k_stage1<<<dim3((unsigned)blocks, (unsigned)ctx->cfg.nz), threads, 0, s>>>(ctx->d, x, W, ctx->ws.status, ctx->ws.lnprior,
                                                  blobs_out, ctx->ws.emu_in, ctx->ws.amp, flags);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
