@@ -195,6 +195,10 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
                                (size_t)c.nd * sizeof(double), c.nd, cudaMemcpyDeviceToDevice));
   }
   ctx->finalized = 1;
+  {
+    int rc = c1d_p1dw_prepare(ctx);  // two-bin rebinning maps for the walker-per-lane stage 3
+    if (rc != C1D_OK) return rc;
+  }
   if (c.emu_kind == 0) {
     int rc = c1d_mlp64_prepare(ctx);  // padded fp64 weight image + slab plan
     if (rc != C1D_OK) return rc;
@@ -403,6 +407,7 @@ extern "C" int c1d_ctx_destroy(c1d_ctx* ctx) {
   cudaDeviceSynchronize();
   c1d_tc_destroy(ctx);
   c1d_mlp64_destroy(ctx);
+  c1d_p1dw_destroy(ctx);
   ws_free(ctx);
   if (ctx->icov_pad) cudaFree(ctx->icov_pad);
   for (int f = 0; f < C1D_F_COUNT; ++f)

@@ -92,6 +92,8 @@ struct c1d_ctx {
   void* tc_state;
   // fp64 tensor-core emulator path (c1d_mlp_f64.cu)
   void* mlp64_state;
+  // walker-per-lane stage 3 (c1d_p1d_lanes.cu): per-fine-point rebinning maps, null when not applicable
+  void* p1dw_state;
   char err[512];
 };
 
@@ -123,6 +125,12 @@ int c1d_mlp64_prepare(c1d_ctx* ctx);
 int c1d_mlp64_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out, int out_stride,
                      cudaStream_t s);
 void c1d_mlp64_destroy(c1d_ctx* ctx);
+
+// walker-per-lane stage 3: prepare builds the two-bin rebinning maps; launch returns 1 when it ran,
+// 0 when the caller must use the warp-per-walker kernel
+int c1d_p1dw_prepare(c1d_ctx* ctx);
+int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, cudaStream_t s);
+void c1d_p1dw_destroy(c1d_ctx* ctx);
 
 // tensor-core MLP (optional translation unit)
 int c1d_tc_prepare(c1d_ctx* ctx);

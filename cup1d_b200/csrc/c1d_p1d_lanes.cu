@@ -1,0 +1,326 @@
+// Stage 3, walker-per-lane form: emulator polynomial -> contaminant templates -> rebinning ->
+// residual (reference: lya_theory.py:690-784, si_mult.py:157-343, si_vid_final.py:157-221,
+// si_add.py:130-221, hcd_model_rogers_class.py:94-140, resolution_class.py:88-114,
+// likelihood.py:147-161, 939, 957).
+//
+// A warp owns a work item (z, 32 walkers): lane = walker.  All lanes walk the fine k grid of the
+// redshift bin together, so every table value is ONE broadcast shared-memory read for the warp
+// (the warp-per-walker kernel in c1d_kernels.cu reads a different point per lane: 4x the
+// wavefronts), the walker's amplitudes are genuinely per-lane registers, the exp recurrences are
+// set up once per (walker, z) per LANE instead of 32 times, and the rebinning needs no staging
+// buffer: a fine point feeds at most two adjacent data bins (checked on the host), so two running
+// sums per lane are flushed as the bins complete — in the same summation order as the banded form.
+//
+// Used when the per-z chi2 is not requested (dense-covariance contexts and model-only calls);
+// otherwise, or when the rebinning operator is not of the two-bin form, c1d_launch_stage3 falls
+// back to the warp-per-walker kernel.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "c1d_internal.h"
+#include "c1d_devmath.cuh"
+
+namespace {
+
+constexpr int PL_THREADS = 512;
+constexpr int PL_WARPS = PL_THREADS / 32;
+constexpr int PL_ANCHOR = 32;  // fine points between exact re-evaluations of the exp recurrences
+
+struct P1dwState {
+  int* d_ja;       // [nf] local index of the first data bin a fine point feeds
+  double* d_wa;    // [nf] weight into bin ja
+  double* d_wb;    // [nf] weight into bin ja + 1
+};
+
+template <int NC, int KIND, int METAL, bool UNI>
+__global__ void __launch_bounds__(PL_THREADS, 1)
+k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restrict__ rwa_g,
+                  const double* __restrict__ rwb_g, int64_t W, const int* __restrict__ status,
+                  const double* __restrict__ amp, double* __restrict__ dvec, double* __restrict__ p_out,
+                  int nfz_max, int ndz_max) {
+  extern __shared__ __align__(16) double sm[];
+  double* tabw = sm;                                     // [nfz_max][C1D_NCOL] table row of a fine point
+  double* rwa = tabw + (size_t)nfz_max * C1D_NCOL;       // [nfz_max]
+  double* rwb = rwa + nfz_max;                           // [nfz_max]
+  double* dat = rwb + nfz_max;                           // [ndz_max]
+  int* rja = reinterpret_cast<int*>(dat + ndz_max);      // [nfz_max]
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+  // cost-balanced contiguous range of this CTA in units of fine points, items = (z, 32 walkers)
+  const int64_t nitems = (W + 31) / 32;
+  int64_t total = 0;
+  for (int z = 0; z < c.nz; ++z) total += nitems * (int64_t)(c.zoff_f[z + 1] - c.zoff_f[z]);
+  const int64_t t0 = total * blockIdx.x / gridDim.x, t1 = total * (blockIdx.x + 1) / gridDim.x;
+
+  int64_t cum = 0;
+  for (int z = 0; z < c.nz; ++z) {
+    const int f0 = c.zoff_f[z], nfz = c.zoff_f[z + 1] - f0;
+    const int d0 = c.zoff_d[z], ndz = c.zoff_d[z + 1] - d0;
+    const int64_t cost = nfz;
+    const int64_t zend = cum + nitems * cost;
+    const int64_t c_lo = (t0 > cum) ? (t0 - cum + cost - 1) / cost : 0;
+    const int64_t c_hi = (t1 < zend) ? ((t1 > cum) ? (t1 - cum + cost - 1) / cost : 0) : nitems;
+    cum = zend;
+    if (c_lo >= c_hi) continue;
+
+    __syncthreads();  // previous z fully processed before its tables are overwritten
+    for (int t = threadIdx.x; t < C1D_NCOL * nfz; t += blockDim.x) {
+      const int col = t / nfz, i = t - col * nfz;
+      tabw[i * C1D_NCOL + col] = c.tab[(size_t)col * c.nf + f0 + i];
+    }
+    for (int t = threadIdx.x; t < nfz; t += blockDim.x) {
+      rwa[t] = rwa_g[f0 + t];
+      rwb[t] = rwb_g[f0 + t];
+      rja[t] = rja_g[f0 + t];
+    }
+    for (int t = threadIdx.x; t < ndz; t += blockDim.x) dat[t] = c.data[d0 + t];
+    __syncthreads();
+    const double dk = UNI ? (tabw[(nfz - 1) * C1D_NCOL + C1D_COL_K] - tabw[C1D_COL_K]) / (double)(nfz - 1) : 0.0;
+
+    for (int64_t item = c_lo + warp; item < c_hi; item += PL_WARPS) {
+      const int64_t w = item * 32 + lane;
+      const bool live = w < W;
+      const int64_t wv = live ? w : W - 1;
+      const bool ok = live && status[wv] == ST_OK;
+      double* dv = dvec ? dvec + wv * c.ldd + d0 : nullptr;
+      double* po = p_out ? p_out + wv * c.nd + d0 : nullptr;
+      if (!__any_sync(0xffffffffu, ok)) {
+        // rejected walkers carry no model (the reference returns None)
+        if (live)
+          for (int j = 0; j < ndz; ++j) {
+            if (dv) dv[j] = 0.0;
+            if (po) po[j] = qnan;
+          }
+        continue;
+      }
+      // amplitude record of this lane's (z, walker); rejected lanes compute on whatever stage 1 left
+      // there and their outputs are overridden
+      const double2* a2p = reinterpret_cast<const double2*>(amp + ((int64_t)z * W + wv) * C1D_NAMP);
+      double av[C1D_NAMP];
+#pragma unroll
+      for (int j = 0; j < C1D_NAMP / 2; ++j) {
+        const double2 v = __ldg(a2p + j);
+        av[2 * j] = v.x;
+        av[2 * j + 1] = v.y;
+      }
+      double cf[C1D_MAX_COEF];
+#pragma unroll
+      for (int j = 0; j < C1D_MAX_COEF; ++j) cf[j] = av[A_COEF0 + j];
+      const double s3 = av[A_S3], s2 = av[A_S2];
+      const double m0 = av[A_M0], c1 = av[A_C1];
+      const double c2a = av[A_C2A], c2b = av[A_C2B];
+      const double c3a = av[A_C3A], c3b = av[A_C3B];
+      const double h0 = av[A_H0];
+      const double hA = av[A_HCD1 + 0], hB = av[A_HCD1 + 1];
+      const double hC = av[A_HCD1 + 2], hD = av[A_HCD1 + 3];
+      const double aa = av[A_AA], sa2 = av[A_SA2];
+      const double res = av[A_RES];
+      const double fagn = av[A_AGN];
+
+      // exp(-s k) and exp(-s^2 k^2) on an evenly spaced grid advance by constant ratios; the products
+      // are re-anchored with an exact evaluation every PL_ANCHOR points
+      const double sg3 = (METAL == 0) ? -s3 : s3;  // SiVid grows with k (si_vid_final.py:208)
+      double E3 = 0.0, R3 = 0.0, E2 = 0.0, R2 = 0.0, gg = 0.0, grho = 0.0, gq = 0.0;
+      if (UNI) {
+        R3 = exp_poly(sg3 * dk);
+        R2 = exp_poly(-s2 * dk);
+        gq = exp_poly(-2.0 * sa2 * (dk * dk));
+      }
+      int jc = 0;
+      double acc0 = 0.0, acc1 = 0.0;
+      auto flush = [&](int j, double m) {
+        const double dj = dat[j] - m;
+        if (live) {
+          if (dv) dv[j] = ok ? dj : 0.0;
+          if (po) po[j] = ok ? m : qnan;
+        }
+      };
+      const double2* tp = reinterpret_cast<const double2*>(tabw);
+      for (int i = 0; i < nfz; ++i, tp += C1D_NCOL / 2) {
+        const double2 ks = tp[C1D_COL_K / 2], tt1 = tp[C1D_COL_T / 2];  // (k, S), (t, T1)
+        const double k = ks.x;
+        if (UNI) {
+          if ((i & (PL_ANCHOR - 1)) == 0) {
+            E3 = exp_poly(sg3 * k);
+            E2 = exp_poly(-s2 * k);
+            gg = exp_poly(-1.0 * sa2 * (k * k));
+            grho = exp_poly(-1.0 * sa2 * (2.0 * k * dk + dk * dk));
+          }
+        } else {
+          E3 = exp(sg3 * k);
+          E2 = exp(-s2 * k);
+          gg = exp(-1.0 * sa2 * (k * k));
+        }
+        // emulator polynomial (Horner) -> P_emu in km/s (lya_theory.py:690-701)
+        double pl = 0.0;
+        if (NC > 0) {
+#pragma unroll
+          for (int j = NC - 1; j >= 0; --j) pl = fma(pl, tt1.x, cf[j]);
+        } else {
+#pragma unroll
+          for (int j = C1D_MAX_COEF - 1; j >= 0; --j)
+            if (j < c.nc) pl = fma(pl, tt1.x, cf[j]);
+        }
+        const double p_emu = ks.y * (KIND == 0 ? exp10_poly(pl) : exp(pl));
+        double mult;
+        if (METAL == 0) {
+          // si_mult.py:212-218, 267-341:  G = 2 - 2/(1 + E)
+          const double2 v2 = tp[C1D_COL_T2A / 2], v3 = tp[C1D_COL_T3A / 2];  // (T2A, T2BC), (T3A, T3BC)
+          const double G3 = fma(-2.0, rcp_fast(1.0 + E3), 2.0);
+          const double G2 = fma(-2.0, rcp_fast(1.0 + E2), 2.0);
+          mult = m0 + (c1 * G3 * tt1.y + G2 * (c2a * v2.x + c2b * v2.y)) + (c3a * v3.x + c3b * v3.y);
+        } else {
+          // si_vid_final.py:205-219
+          mult = 1.0 + c1 * E3 + c2a * tt1.y * E2;
+        }
+        if (c.has_agn) mult *= fma(fagn, tp[C1D_COL_AGN / 2].x, 1.0);  // AGN_model.py:116-120: 1 + f_AGN delta
+        // hcd_model_rogers_class.py:115-135 (or hcd_boss.py:5-7 through D1)
+        const double2 d12 = tp[C1D_COL_D1 / 2], d34 = tp[C1D_COL_D3 / 2], kq = tp[C1D_COL_KT / 2];  // (D1, D2), (D3, D4), (KT, Q)
+        const double hcd = h0 + hA * d12.x + hB * d12.y + hC * d34.x + hD * d34.y;
+        // si_add.py:168-219
+        const double add = aa * kq.x * gg;
+        // resolution_class.py:99-108
+        const double syst = 1.0 + res * kq.y;
+        // lya_theory.py:778-784 (IC correction is folded into the S column)
+        const double P = (hcd * mult * p_emu + add) * syst;
+        if (UNI) {
+          E3 *= R3;
+          E2 *= R2;
+          gg *= grho;
+          grho *= gq;
+        }
+        // rebinning (likelihood.py:147-161): this point feeds bins ja and ja + 1
+        const int ja = rja[i];
+        while (jc < ja) {
+          flush(jc, acc0);
+          acc0 = acc1;
+          acc1 = 0.0;
+          ++jc;
+        }
+        acc0 = fma(rwa[i], P, acc0);
+        acc1 = fma(rwb[i], P, acc1);
+      }
+      while (jc < ndz) {
+        flush(jc, acc0);
+        acc0 = acc1;
+        acc1 = 0.0;
+        ++jc;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+void c1d_p1dw_destroy(c1d_ctx* ctx) {
+  P1dwState* st = (P1dwState*)ctx->p1dw_state;
+  if (!st) return;
+  cudaFree(st->d_ja);
+  cudaFree(st->d_wa);
+  cudaFree(st->d_wb);
+  delete st;
+  ctx->p1dw_state = nullptr;
+}
+
+// Per fine point: the (at most two, adjacent) data bins it feeds.  Leaves p1dw_state null when the
+// rebinning operator is not of that form (the caller then uses the warp-per-walker kernel).
+int c1d_p1dw_prepare(c1d_ctx* ctx) {
+  const c1d_config& c = ctx->cfg;
+  c1d_p1dw_destroy(ctx);
+  const int RW = c.rebin_width;
+  std::vector<int> zf(c.nz + 1), zd(c.nz + 1), st(c.nd);
+  std::vector<double> wg((size_t)c.nd * RW);
+  C1D_CUDA(ctx, cudaMemcpy(zf.data(), ctx->dev[C1D_F_ZOFF_F], (c.nz + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  C1D_CUDA(ctx, cudaMemcpy(zd.data(), ctx->dev[C1D_F_ZOFF_D], (c.nz + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  C1D_CUDA(ctx, cudaMemcpy(st.data(), ctx->dev[C1D_F_RB_START], c.nd * sizeof(int), cudaMemcpyDeviceToHost));
+  C1D_CUDA(ctx, cudaMemcpy(wg.data(), ctx->dev[C1D_F_RB_WGT], wg.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  std::vector<int> ja(c.nf, 0);
+  std::vector<double> wa(c.nf, 0.0), wb(c.nf, 0.0);
+  for (int z = 0; z < c.nz; ++z) {
+    const int f0 = zf[z], nfz = zf[z + 1] - f0, d0 = zd[z], ndz = zd[z + 1] - d0;
+    std::vector<int> first(nfz, -1), count(nfz, 0);
+    for (int j = 0; j < ndz; ++j)
+      for (int t = 0; t < RW; ++t) {
+        const double wt = wg[(size_t)(d0 + j) * RW + t];
+        const int i = st[d0 + j] + t;
+        if (wt == 0.0 || i >= nfz) continue;
+        if (first[i] < 0) {
+          first[i] = j;
+          wa[f0 + i] = wt;
+        } else if (j == first[i] + 1 && count[i] == 1) {
+          wb[f0 + i] = wt;
+        } else {
+          return C1D_OK;  // a fine point feeds more than two (or non-adjacent) bins
+        }
+        count[i]++;
+      }
+    int last = 0;
+    for (int i = 0; i < nfz; ++i) {
+      if (first[i] < 0) first[i] = last;  // feeds no bin: stay on the current one with zero weights
+      if (first[i] < last) return C1D_OK;  // bins must come in grid order
+      last = first[i];
+      ja[f0 + i] = first[i];
+    }
+  }
+  P1dwState* s = new P1dwState();
+  memset(s, 0, sizeof(*s));
+  ctx->p1dw_state = s;
+  C1D_CUDA(ctx, cudaMalloc(&s->d_ja, c.nf * sizeof(int)));
+  C1D_CUDA(ctx, cudaMalloc(&s->d_wa, c.nf * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&s->d_wb, c.nf * sizeof(double)));
+  C1D_CUDA(ctx, cudaMemcpy(s->d_ja, ja.data(), c.nf * sizeof(int), cudaMemcpyHostToDevice));
+  C1D_CUDA(ctx, cudaMemcpy(s->d_wa, wa.data(), c.nf * sizeof(double), cudaMemcpyHostToDevice));
+  C1D_CUDA(ctx, cudaMemcpy(s->d_wb, wb.data(), c.nf * sizeof(double), cudaMemcpyHostToDevice));
+  return C1D_OK;
+}
+
+// returns 1 when the launch was done here, 0 when the caller must use the warp-per-walker kernel,
+// a negative c1d_status on error
+int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, cudaStream_t s) {
+  P1dwState* st = (P1dwState*)ctx->p1dw_state;
+  static const int disabled = getenv("C1D_P1D_LAYOUT") && !strcmp(getenv("C1D_P1D_LAYOUT"), "warp");
+  if (!st || disabled) return 0;
+  const c1d_config& cfg = ctx->cfg;
+  const int nfz_max = ctx->nfz_max, ndz_max = ctx->ndz_max;
+  const size_t smem = ((size_t)nfz_max * (C1D_NCOL + 2) + ndz_max) * sizeof(double) + (size_t)nfz_max * sizeof(int) + 16;
+  if (smem > 227 * 1024) return 0;
+  typedef void (*kern_t)(DevCtx, const int*, const double*, const double*, int64_t, const int*, const double*, double*, double*, int, int);
+  kern_t kern = nullptr;
+  const int nc = (cfg.nc >= 5 && cfg.nc <= 7) ? cfg.nc : 0;
+  const int sel = ((nc ? nc - 4 : 0) << 3) | (cfg.emu_kind << 2) | (cfg.metal_model << 1) | (cfg.uniform_k ? 1 : 0);
+#define PL_CASE(NCI, NCV)                                                        \
+  case ((NCI) << 3) | 0: kern = k_fused_p1d_lanes<NCV, 0, 0, false>; break;      \
+  case ((NCI) << 3) | 1: kern = k_fused_p1d_lanes<NCV, 0, 0, true>; break;       \
+  case ((NCI) << 3) | 2: kern = k_fused_p1d_lanes<NCV, 0, 1, false>; break;      \
+  case ((NCI) << 3) | 3: kern = k_fused_p1d_lanes<NCV, 0, 1, true>; break;       \
+  case ((NCI) << 3) | 4: kern = k_fused_p1d_lanes<NCV, 1, 0, false>; break;      \
+  case ((NCI) << 3) | 5: kern = k_fused_p1d_lanes<NCV, 1, 0, true>; break;       \
+  case ((NCI) << 3) | 6: kern = k_fused_p1d_lanes<NCV, 1, 1, false>; break;      \
+  case ((NCI) << 3) | 7: kern = k_fused_p1d_lanes<NCV, 1, 1, true>; break;
+  switch (sel) {
+    PL_CASE(0, 0)
+    PL_CASE(1, 5)
+    PL_CASE(2, 6)
+    PL_CASE(3, 7)
+  }
+#undef PL_CASE
+  if (!kern) return 0;
+  C1D_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t items = ((W + 31) / 32) * cfg.nz;
+  int64_t grid = (int64_t)ctx->num_sms;
+  if (grid > (items + PL_WARPS - 1) / PL_WARPS) grid = (items + PL_WARPS - 1) / PL_WARPS;
+  if (grid < 1) grid = 1;
+  double* dvec = want_dvec ? ctx->ws.dvec : nullptr;
+  kern<<<(unsigned)grid, PL_THREADS, smem, s>>>(ctx->d, st->d_ja, st->d_wa, st->d_wb, W, ctx->ws.status, ctx->ws.amp, dvec, p_out,
+                                                nfz_max, ndz_max);
+  ctx->launches++;
+  C1D_CUDA(ctx, cudaPeekAtLastError());
+  return 1;
+}
