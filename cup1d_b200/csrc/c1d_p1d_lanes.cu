@@ -24,9 +24,13 @@
 
 namespace {
 
-constexpr int PL_THREADS = 512;
-constexpr int PL_WARPS = PL_THREADS / 32;
 constexpr int PL_ANCHOR = 32;  // fine points between exact re-evaluations of the exp recurrences
+// U fine points per loop trip as independent instruction streams, with 64K / threads registers per
+// thread.  Measured on B200 (C4, 65 536 walkers): U=1 x 512 threads 2.52 ms, U=2 x 384 3.00 ms,
+// U=4 x 384 2.78 ms, U=4 x 256 3.57 ms, and U=1 with 640 / 768 / 1024 threads (spilling) 2.96 / 3.23 /
+// 3.88 ms: warps beat unrolling, and 16 warps at the 128-register cap is the optimum.
+constexpr int PL_U = 1;
+__host__ __device__ constexpr int pl_threads(int U) { return U == 1 ? 512 : (U == 2 ? 384 : 256); }
 
 struct P1dwState {
   int* d_ja;       // [nf] local index of the first data bin a fine point feeds
@@ -34,14 +38,15 @@ struct P1dwState {
   double* d_wb;    // [nf] weight into bin ja + 1
 };
 
-template <int NC, int KIND, int METAL, bool UNI>
-__global__ void __launch_bounds__(PL_THREADS, 1)
+template <int NC, int KIND, int METAL, bool UNI, int U>
+__global__ void __launch_bounds__(pl_threads(U), 1)
 k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restrict__ rwa_g,
                   const double* __restrict__ rwb_g, int64_t W, const int* __restrict__ status,
                   const double* __restrict__ amp, double* __restrict__ dvec, double* __restrict__ p_out,
                   int nfz_max, int ndz_max) {
+  constexpr int PL_WARPS = pl_threads(U) / 32;
   extern __shared__ __align__(16) double sm[];
-  double* tabw = sm;                                     // [nfz_max][C1D_NCOL] table row of a fine point
+  double* tabw = sm;                                     // [nfz_max][C1D_NCOL] table row of a fine point (nfz_max: multiple of U)
   double* rwa = tabw + (size_t)nfz_max * C1D_NCOL;       // [nfz_max]
   double* rwb = rwa + nfz_max;                           // [nfz_max]
   double* dat = rwb + nfz_max;                           // [ndz_max]
@@ -68,14 +73,18 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restr
     if (c_lo >= c_hi) continue;
 
     __syncthreads();  // previous z fully processed before its tables are overwritten
-    for (int t = threadIdx.x; t < C1D_NCOL * nfz; t += blockDim.x) {
-      const int col = t / nfz, i = t - col * nfz;
-      tabw[i * C1D_NCOL + col] = c.tab[(size_t)col * c.nf + f0 + i];
+    // the grid of this z is padded to a multiple of U with copies of its last point that carry no
+    // rebinning weight, so the loop body needs no bounds tests
+    const int nfp = (nfz + U - 1) / U * U;
+    for (int t = threadIdx.x; t < C1D_NCOL * nfp; t += blockDim.x) {
+      const int col = t / nfp, i = t - col * nfp;
+      tabw[i * C1D_NCOL + col] = c.tab[(size_t)col * c.nf + f0 + (i < nfz ? i : nfz - 1)];
     }
-    for (int t = threadIdx.x; t < nfz; t += blockDim.x) {
-      rwa[t] = rwa_g[f0 + t];
-      rwb[t] = rwb_g[f0 + t];
-      rja[t] = rja_g[f0 + t];
+    for (int t = threadIdx.x; t < nfp; t += blockDim.x) {
+      const bool in = t < nfz;
+      rwa[t] = in ? rwa_g[f0 + t] : 0.0;
+      rwb[t] = in ? rwb_g[f0 + t] : 0.0;
+      rja[t] = rja_g[f0 + (in ? t : nfz - 1)];
     }
     for (int t = threadIdx.x; t < ndz; t += blockDim.x) dat[t] = c.data[d0 + t];
     __syncthreads();
@@ -139,70 +148,81 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restr
           if (po) po[j] = ok ? m : qnan;
         }
       };
-      const double2* tp = reinterpret_cast<const double2*>(tabw);
-      for (int i = 0; i < nfz; ++i, tp += C1D_NCOL / 2) {
-        const double2 ks = tp[C1D_COL_K / 2], tt1 = tp[C1D_COL_T / 2];  // (k, S), (t, T1)
-        const double k = ks.x;
-        if (UNI) {
-          if ((i & (PL_ANCHOR - 1)) == 0) {
-            E3 = exp_poly(sg3 * k);
-            E2 = exp_poly(-s2 * k);
-            gg = exp_poly(-1.0 * sa2 * (k * k));
-            grho = exp_poly(-1.0 * sa2 * (2.0 * k * dk + dk * dk));
+      const double2* tp0 = reinterpret_cast<const double2*>(tabw);
+      for (int i0 = 0; i0 < nfp; i0 += U, tp0 += U * (C1D_NCOL / 2)) {
+        if (UNI && (i0 & (PL_ANCHOR - 1)) == 0) {
+          const double k = tp0[C1D_COL_K / 2].x;
+          E3 = exp_poly(sg3 * k);
+          E2 = exp_poly(-s2 * k);
+          gg = exp_poly(-1.0 * sa2 * (k * k));
+          grho = exp_poly(-1.0 * sa2 * (2.0 * k * dk + dk * dk));
+        }
+        double P[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const double2* tp = tp0 + u * (C1D_NCOL / 2);
+          const double2 ks = tp[C1D_COL_K / 2], tt1 = tp[C1D_COL_T / 2];  // (k, S), (t, T1)
+          const double k = ks.x;
+          double e3, e2, g;
+          if (UNI) {
+            e3 = E3;
+            e2 = E2;
+            g = gg;
+            E3 *= R3;
+            E2 *= R2;
+            gg *= grho;
+            grho *= gq;
+          } else {
+            e3 = exp(sg3 * k);
+            e2 = exp(-s2 * k);
+            g = exp(-1.0 * sa2 * (k * k));
           }
-        } else {
-          E3 = exp(sg3 * k);
-          E2 = exp(-s2 * k);
-          gg = exp(-1.0 * sa2 * (k * k));
-        }
-        // emulator polynomial (Horner) -> P_emu in km/s (lya_theory.py:690-701)
-        double pl = 0.0;
-        if (NC > 0) {
+          // emulator polynomial (Horner) -> P_emu in km/s (lya_theory.py:690-701)
+          double pl = 0.0;
+          if (NC > 0) {
 #pragma unroll
-          for (int j = NC - 1; j >= 0; --j) pl = fma(pl, tt1.x, cf[j]);
-        } else {
+            for (int j = NC - 1; j >= 0; --j) pl = fma(pl, tt1.x, cf[j]);
+          } else {
 #pragma unroll
-          for (int j = C1D_MAX_COEF - 1; j >= 0; --j)
-            if (j < c.nc) pl = fma(pl, tt1.x, cf[j]);
+            for (int j = C1D_MAX_COEF - 1; j >= 0; --j)
+              if (j < c.nc) pl = fma(pl, tt1.x, cf[j]);
+          }
+          const double p_emu = ks.y * (KIND == 0 ? exp10_poly(pl) : exp(pl));
+          double mult;
+          if (METAL == 0) {
+            // si_mult.py:212-218, 267-341:  G = 2 - 2/(1 + E)
+            const double2 v2 = tp[C1D_COL_T2A / 2], v3 = tp[C1D_COL_T3A / 2];  // (T2A, T2BC), (T3A, T3BC)
+            const double G3 = fma(-2.0, rcp_fast(1.0 + e3), 2.0);
+            const double G2 = fma(-2.0, rcp_fast(1.0 + e2), 2.0);
+            mult = m0 + (c1 * G3 * tt1.y + G2 * (c2a * v2.x + c2b * v2.y)) + (c3a * v3.x + c3b * v3.y);
+          } else {
+            // si_vid_final.py:205-219
+            mult = 1.0 + c1 * e3 + c2a * tt1.y * e2;
+          }
+          if (c.has_agn) mult *= fma(fagn, tp[C1D_COL_AGN / 2].x, 1.0);  // AGN_model.py:116-120: 1 + f_AGN delta
+          // hcd_model_rogers_class.py:115-135 (or hcd_boss.py:5-7 through D1)
+          const double2 d12 = tp[C1D_COL_D1 / 2], d34 = tp[C1D_COL_D3 / 2], kq = tp[C1D_COL_KT / 2];  // (D1, D2), (D3, D4), (KT, Q)
+          const double hcd = h0 + hA * d12.x + hB * d12.y + hC * d34.x + hD * d34.y;
+          // si_add.py:168-219
+          const double add = aa * kq.x * g;
+          // resolution_class.py:99-108
+          const double syst = 1.0 + res * kq.y;
+          // lya_theory.py:778-784 (IC correction is folded into the S column)
+          P[u] = (hcd * mult * p_emu + add) * syst;
         }
-        const double p_emu = ks.y * (KIND == 0 ? exp10_poly(pl) : exp(pl));
-        double mult;
-        if (METAL == 0) {
-          // si_mult.py:212-218, 267-341:  G = 2 - 2/(1 + E)
-          const double2 v2 = tp[C1D_COL_T2A / 2], v3 = tp[C1D_COL_T3A / 2];  // (T2A, T2BC), (T3A, T3BC)
-          const double G3 = fma(-2.0, rcp_fast(1.0 + E3), 2.0);
-          const double G2 = fma(-2.0, rcp_fast(1.0 + E2), 2.0);
-          mult = m0 + (c1 * G3 * tt1.y + G2 * (c2a * v2.x + c2b * v2.y)) + (c3a * v3.x + c3b * v3.y);
-        } else {
-          // si_vid_final.py:205-219
-          mult = 1.0 + c1 * E3 + c2a * tt1.y * E2;
+        // rebinning (likelihood.py:147-161): point i feeds bins ja and ja + 1
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int ja = rja[i0 + u];
+          while (jc < ja) {
+            flush(jc, acc0);
+            acc0 = acc1;
+            acc1 = 0.0;
+            ++jc;
+          }
+          acc0 = fma(rwa[i0 + u], P[u], acc0);
+          acc1 = fma(rwb[i0 + u], P[u], acc1);
         }
-        if (c.has_agn) mult *= fma(fagn, tp[C1D_COL_AGN / 2].x, 1.0);  // AGN_model.py:116-120: 1 + f_AGN delta
-        // hcd_model_rogers_class.py:115-135 (or hcd_boss.py:5-7 through D1)
-        const double2 d12 = tp[C1D_COL_D1 / 2], d34 = tp[C1D_COL_D3 / 2], kq = tp[C1D_COL_KT / 2];  // (D1, D2), (D3, D4), (KT, Q)
-        const double hcd = h0 + hA * d12.x + hB * d12.y + hC * d34.x + hD * d34.y;
-        // si_add.py:168-219
-        const double add = aa * kq.x * gg;
-        // resolution_class.py:99-108
-        const double syst = 1.0 + res * kq.y;
-        // lya_theory.py:778-784 (IC correction is folded into the S column)
-        const double P = (hcd * mult * p_emu + add) * syst;
-        if (UNI) {
-          E3 *= R3;
-          E2 *= R2;
-          gg *= grho;
-          grho *= gq;
-        }
-        // rebinning (likelihood.py:147-161): this point feeds bins ja and ja + 1
-        const int ja = rja[i];
-        while (jc < ja) {
-          flush(jc, acc0);
-          acc0 = acc1;
-          acc1 = 0.0;
-          ++jc;
-        }
-        acc0 = fma(rwa[i], P, acc0);
-        acc1 = fma(rwb[i], P, acc1);
       }
       while (jc < ndz) {
         flush(jc, acc0);
@@ -289,21 +309,24 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, cudaS
   if (!st || disabled) return 0;
   const c1d_config& cfg = ctx->cfg;
   const int nfz_max = ctx->nfz_max, ndz_max = ctx->ndz_max;
-  const size_t smem = ((size_t)nfz_max * (C1D_NCOL + 2) + ndz_max) * sizeof(double) + (size_t)nfz_max * sizeof(int) + 16;
+  constexpr int U = PL_U;
+  const int nfp_max = (nfz_max + 3) & ~3;
+  const size_t smem = ((size_t)nfp_max * (C1D_NCOL + 2) + ndz_max) * sizeof(double) + (size_t)nfp_max * sizeof(int) + 16;
   if (smem > 227 * 1024) return 0;
   typedef void (*kern_t)(DevCtx, const int*, const double*, const double*, int64_t, const int*, const double*, double*, double*, int, int);
   kern_t kern = nullptr;
   const int nc = (cfg.nc >= 5 && cfg.nc <= 7) ? cfg.nc : 0;
   const int sel = ((nc ? nc - 4 : 0) << 3) | (cfg.emu_kind << 2) | (cfg.metal_model << 1) | (cfg.uniform_k ? 1 : 0);
-#define PL_CASE(NCI, NCV)                                                        \
-  case ((NCI) << 3) | 0: kern = k_fused_p1d_lanes<NCV, 0, 0, false>; break;      \
-  case ((NCI) << 3) | 1: kern = k_fused_p1d_lanes<NCV, 0, 0, true>; break;       \
-  case ((NCI) << 3) | 2: kern = k_fused_p1d_lanes<NCV, 0, 1, false>; break;      \
-  case ((NCI) << 3) | 3: kern = k_fused_p1d_lanes<NCV, 0, 1, true>; break;       \
-  case ((NCI) << 3) | 4: kern = k_fused_p1d_lanes<NCV, 1, 0, false>; break;      \
-  case ((NCI) << 3) | 5: kern = k_fused_p1d_lanes<NCV, 1, 0, true>; break;       \
-  case ((NCI) << 3) | 6: kern = k_fused_p1d_lanes<NCV, 1, 1, false>; break;      \
-  case ((NCI) << 3) | 7: kern = k_fused_p1d_lanes<NCV, 1, 1, true>; break;
+#define PL_PICK(...) k_fused_p1d_lanes<__VA_ARGS__, PL_U>
+#define PL_CASE(NCI, NCV)                                              \
+  case ((NCI) << 3) | 0: kern = PL_PICK(NCV, 0, 0, false); break;      \
+  case ((NCI) << 3) | 1: kern = PL_PICK(NCV, 0, 0, true); break;       \
+  case ((NCI) << 3) | 2: kern = PL_PICK(NCV, 0, 1, false); break;      \
+  case ((NCI) << 3) | 3: kern = PL_PICK(NCV, 0, 1, true); break;       \
+  case ((NCI) << 3) | 4: kern = PL_PICK(NCV, 1, 0, false); break;      \
+  case ((NCI) << 3) | 5: kern = PL_PICK(NCV, 1, 0, true); break;       \
+  case ((NCI) << 3) | 6: kern = PL_PICK(NCV, 1, 1, false); break;      \
+  case ((NCI) << 3) | 7: kern = PL_PICK(NCV, 1, 1, true); break;
   switch (sel) {
     PL_CASE(0, 0)
     PL_CASE(1, 5)
@@ -311,15 +334,17 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, cudaS
     PL_CASE(3, 7)
   }
 #undef PL_CASE
+#undef PL_PICK
   if (!kern) return 0;
   C1D_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = pl_threads(U), warps = threads / 32;
   const int64_t items = ((W + 31) / 32) * cfg.nz;
   int64_t grid = (int64_t)ctx->num_sms;
-  if (grid > (items + PL_WARPS - 1) / PL_WARPS) grid = (items + PL_WARPS - 1) / PL_WARPS;
+  if (grid > (items + warps - 1) / warps) grid = (items + warps - 1) / warps;
   if (grid < 1) grid = 1;
   double* dvec = want_dvec ? ctx->ws.dvec : nullptr;
-  kern<<<(unsigned)grid, PL_THREADS, smem, s>>>(ctx->d, st->d_ja, st->d_wa, st->d_wb, W, ctx->ws.status, ctx->ws.amp, dvec, p_out,
-                                                nfz_max, ndz_max);
+  kern<<<(unsigned)grid, threads, smem, s>>>(ctx->d, st->d_ja, st->d_wa, st->d_wb, W, ctx->ws.status, ctx->ws.amp, dvec, p_out,
+                                                nfp_max, ndz_max);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return 1;
