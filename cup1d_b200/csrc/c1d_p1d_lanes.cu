@@ -339,6 +339,9 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, cudaS
   C1D_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = pl_threads(U), warps = threads / 32;
   const int64_t items = ((W + 31) / 32) * cfg.nz;
+  // a warp-item is 32 walkers long: small batches do not fill the machine in this form (measured
+  // crossover on C4: between 4096 and 8192 walkers), the warp-per-walker kernel takes them
+  if (items < (int64_t)ctx->num_sms * warps) return 0;
   int64_t grid = (int64_t)ctx->num_sms;
   if (grid > (items + warps - 1) / warps) grid = (items + warps - 1) / warps;
   if (grid < 1) grid = 1;
