@@ -305,8 +305,10 @@ int c1d_p1dw_prepare(c1d_ctx* ctx) {
 // a negative c1d_status on error
 int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, cudaStream_t s) {
   P1dwState* st = (P1dwState*)ctx->p1dw_state;
-  static const int disabled = getenv("C1D_P1D_LAYOUT") && !strcmp(getenv("C1D_P1D_LAYOUT"), "warp");
-  if (!st || disabled) return 0;
+  // C1D_P1D_LAYOUT=warp | lanes overrides the choice by batch size (tests run both forms on the same inputs)
+  const char* layout = getenv("C1D_P1D_LAYOUT");
+  const bool force_warp = layout && !strcmp(layout, "warp"), force_lanes = layout && !strcmp(layout, "lanes");
+  if (!st || force_warp) return 0;
   const c1d_config& cfg = ctx->cfg;
   const int nfz_max = ctx->nfz_max, ndz_max = ctx->ndz_max;
   constexpr int U = PL_U;
@@ -341,7 +343,7 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, cudaS
   const int64_t items = ((W + 31) / 32) * cfg.nz;
   // a warp-item is 32 walkers long: small batches do not fill the machine in this form (measured
   // crossover on C4: between 4096 and 8192 walkers), the warp-per-walker kernel takes them
-  if (items < (int64_t)ctx->num_sms * warps) return 0;
+  if (items < (int64_t)ctx->num_sms * warps && !force_lanes) return 0;
   int64_t grid = (int64_t)ctx->num_sms;
   if (grid > (items + warps - 1) / warps) grid = (items + warps - 1) / warps;
   if (grid < 1) grid = 1;
