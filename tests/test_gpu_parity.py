@@ -301,7 +301,7 @@ def test_edge_batches(golden):
 
 
 @pytest.mark.parametrize("layout", ["lanes", "warp"])
-@pytest.mark.parametrize("name", ["dr1_full_nn", "nyx_gp_priors", "hcd_boss"])
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
 def test_both_stage3_forms_on_goldens(golden, monkeypatch, name, layout):
     """the walker-per-lane and the warp-per-walker stage 3 (chosen by batch size in production) are both
     held to the reference goldens: C1D_P1D_LAYOUT forces one form"""
