@@ -658,11 +658,8 @@ int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
   const int npairs = (ntj + 1) / 2;
   dim3 grid((unsigned)((W + Q_TW - 1) / Q_TW), (unsigned)npairs);
   const size_t smem = (size_t)(2 * Q_TW * Q_ASTR + 2 * Q_KC * Q_BSTR + 2 * Q_TW) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    C1D_CUDA(ctx, cudaFuncSetAttribute(k_chi2_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // per launch, not once per process: the attribute is per device and a process may own several contexts
+  C1D_CUDA(ctx, cudaFuncSetAttribute(k_chi2_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_chi2_dmma<<<grid, 256, smem, s>>>(W, ndp, ctx->ws.dvec, ctx->icov_pad, ctx->ws.chi2p, npairs);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
