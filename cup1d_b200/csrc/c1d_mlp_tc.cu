@@ -40,7 +40,11 @@ constexpr int TC_NBLK = C1D_TC_NBLK;               // widest n-block = N of one 
 constexpr int TC_RING_BYTES = 98304;               // weight ring: units of different size packed back to back
 constexpr int TC_NBAR = 16;                        // mbarrier pairs, used round-robin by the units
 static_assert(TC_NBLK * TC_BK * 4 * 2 * 2 <= TC_RING_BYTES, "weight ring too small for two of the largest units");
-constexpr int TC_EPI_WARPS = 8;                    // two warps per TMEM lane quadrant
+#ifndef TC_EPI_PER_QUAD
+#define TC_EPI_PER_QUAD 3  // measured: epilogue 18.3k -> 15.2k -> 13.7k cycles per tile for 2, 3, 4 (4 needs <= 112 registers)
+#endif
+constexpr int TC_EPI_WARPS = 4 * TC_EPI_PER_QUAD;   // TC_EPI_PER_QUAD warps per TMEM lane quadrant
+constexpr int TC_BSTEP = 16 * TC_EPI_PER_QUAD;      // columns between consecutive 16-column batches of one warp
 constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 2);
 constexpr int TC_MMA_TID = 32 * TC_EPI_WARPS;      // lane 0 of the MMA warp
 constexpr int TC_LOAD_TID = 32 * (TC_EPI_WARPS + 1);
@@ -291,9 +295,9 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
   const float slope = (float)p.slope;
 
   if (warp < TC_EPI_WARPS) {
-    // ===================== row owners / epilogue: 2 warps per lane quadrant =====================
+    // ============== row owners / epilogue: TC_EPI_PER_QUAD warps per lane quadrant ==============
     // warp w works on TMEM lanes 32 (w & 3) .. +31 (one row per thread) and on the 16-column
-    // batches of parity (w >> 2)
+    // batches congruent to (w >> 2) modulo TC_EPI_PER_QUAD
     const uint32_t quad = (uint32_t)warp & 3u, half = (uint32_t)warp >> 2;
     const uint32_t row = quad * 32u + ((uint32_t)tid & 31u);
     const uint32_t tmem_lane = tmem_base + ((quad * 32u) << 16);
@@ -345,15 +349,15 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
           uint32_t r0[16], r1[16];
           const int c_first = 16 * (int)half;
           if (c_first < npad) tmem_ld16(tmem_lane + (uint32_t)c_first, r0);
-          for (int col0 = c_first; col0 < npad; col0 += 64) {
+          for (int col0 = c_first; col0 < npad; col0 += 2 * TC_BSTEP) {
             tc_wait_ld();
-            const bool more1 = col0 + 32 < npad;
-            if (more1) tmem_ld16(tmem_lane + (uint32_t)(col0 + 32), r1);
+            const bool more1 = col0 + TC_BSTEP < npad;
+            if (more1) tmem_ld16(tmem_lane + (uint32_t)(col0 + TC_BSTEP), r1);
             process(r0, col0);
             if (more1) {
               tc_wait_ld();
-              if (col0 + 64 < npad) tmem_ld16(tmem_lane + (uint32_t)(col0 + 64), r0);
-              process(r1, col0 + 32);
+              if (col0 + 2 * TC_BSTEP < npad) tmem_ld16(tmem_lane + (uint32_t)(col0 + 2 * TC_BSTEP), r0);
+              process(r1, col0 + TC_BSTEP);
             }
           }
           fence_async_smem();
