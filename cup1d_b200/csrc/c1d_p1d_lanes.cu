@@ -24,7 +24,7 @@
 
 namespace {
 
-constexpr int PL_ANCHOR = 32;  // fine points between exact re-evaluations of the exp recurrences
+constexpr int PL_ANCHOR = 64;  // fine points between exact re-evaluations of the exp recurrences
 // U fine points per loop trip as independent instruction streams, with 64K / threads registers per
 // thread.  Measured on B200 (C4, 65 536 walkers): U=1 x 512 threads 2.52 ms, U=2 x 384 3.00 ms,
 // U=4 x 384 2.78 ms, U=4 x 256 3.57 ms, and U=1 with 640 / 768 / 1024 threads (spilling) 2.96 / 3.23 /
@@ -50,9 +50,11 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restr
   double* rwa = tabw + (size_t)nfz_max * C1D_NCOL;       // [nfz_max]
   double* rwb = rwa + nfz_max;                           // [nfz_max]
   double* dat = rwb + nfz_max;                           // [ndz_max]
-  int* rja = reinterpret_cast<int*>(dat + ndz_max);      // [nfz_max]
+  double* etab = dat + ndz_max;                          // [32] 2^(j/32) for exp10_tab
+  int* rja = reinterpret_cast<int*>(etab + 32);          // [nfz_max]
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 32) etab[threadIdx.x] = c_exp2_tab[threadIdx.x];  // visible after the first __syncthreads below
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
   // cost-balanced contiguous range of this CTA in units of fine points, items = (z, 32 walkers)
@@ -187,13 +189,13 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restr
             for (int j = C1D_MAX_COEF - 1; j >= 0; --j)
               if (j < c.nc) pl = fma(pl, tt1.x, cf[j]);
           }
-          const double p_emu = ks.y * (KIND == 0 ? exp10_poly(pl) : exp(pl));
+          const double p_emu = ks.y * (KIND == 0 ? exp10_tab(pl, etab) : exp(pl));
           double mult;
           if (METAL == 0) {
             // si_mult.py:212-218, 267-341:  G = 2 - 2/(1 + E)
             const double2 v2 = tp[C1D_COL_T2A / 2], v3 = tp[C1D_COL_T3A / 2];  // (T2A, T2BC), (T3A, T3BC)
-            const double G3 = fma(-2.0, rcp_fast(1.0 + e3), 2.0);
-            const double G2 = fma(-2.0, rcp_fast(1.0 + e2), 2.0);
+            const double G3 = fma(-2.0, rcp_fast1(1.0 + e3), 2.0);
+            const double G2 = fma(-2.0, rcp_fast1(1.0 + e2), 2.0);
             mult = m0 + (c1 * G3 * tt1.y + G2 * (c2a * v2.x + c2b * v2.y)) + (c3a * v3.x + c3b * v3.y);
           } else {
             // si_vid_final.py:205-219
@@ -313,7 +315,7 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, cudaS
   const int nfz_max = ctx->nfz_max, ndz_max = ctx->ndz_max;
   constexpr int U = PL_U;
   const int nfp_max = (nfz_max + 3) & ~3;
-  const size_t smem = ((size_t)nfp_max * (C1D_NCOL + 2) + ndz_max) * sizeof(double) + (size_t)nfp_max * sizeof(int) + 16;
+  const size_t smem = ((size_t)nfp_max * (C1D_NCOL + 2) + ndz_max + 32) * sizeof(double) + (size_t)nfp_max * sizeof(int) + 16;
   if (smem > 227 * 1024) return 0;
   typedef void (*kern_t)(DevCtx, const int*, const double*, const double*, int64_t, const int*, const double*, double*, double*, int, int);
   kern_t kern = nullptr;
