@@ -1,11 +1,14 @@
 // Hand-written sm_100a kernels of the batched P1D log-likelihood.
 //
 //   stage 0/1/5  k_stage1      cube -> parameters -> per-z emulator inputs, contaminant
-//                              amplitudes, blobs, Gaussian prior, star box, hull
+//                              amplitudes, blobs, Gaussian prior, star box, hull; thread per (walker, z)
 //   stage 2      k_mlp_f64     LaCE-style MLP on the fp64 tensor cores (DMMA, exact-parity mode; c1d_mlp_f64.cu)
+//                k_mlp_tc      the same MLP on tcgen05 in 3xTF32 (c1d_mlp_tc.cu)
 //                k_gp_f64      GP posterior mean = batched kernel-vector product
-//   stage 3      k_fused_p1d   emulator polynomial -> contaminant templates -> rebin ->
-//                              residual, tables staged in shared memory per z
+//   stage 3      k_fused_p1d   emulator polynomial -> contaminant templates -> rebin -> residual
+//                              (-> per-z chi2), warp per walker, tables staged in shared memory per z:
+//                              small batches, block-diagonal contexts, lnL_z requests
+//                k_fused_p1d_lanes  the same with lane = walker (c1d_p1d_lanes.cu): large batches
 //   stage 4      k_chi2_dmma   chi2 = d^T C^-1 d: tiled fp64 tensor-core GEMM (DMMA), symmetric,
 //                              row-dot fused into the epilogue
 //   stage 5      k_finalize    regulate + prior, blobs conventions

@@ -2,19 +2,27 @@
 // tcgen05.mma (kind::tf32) GEMMs over a 128-row tile of (walker, z) pairs, in 3xTF32
 // (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulation in TMEM).
 //
-// One persistent CTA per SM, 10 warps:
-//   warps 0-7  two threads per row / TMEM lane (alternate 16-column batches): input normalisation, per-layer
-//              epilogue TMEM -> registers -> bias + LeakyReLU -> hi/lo split -> next A operand;
-//              every layer, including 6->10 and 50->6, is a tensor-core GEMM
-//   warp 8     TMEM allocation; lane 0 issues every tcgen05.mma and tcgen05.commit
-//   warp 9     lane 0 streams the pre-swizzled weight images with cp.async.bulk (TMA bulk copy)
-//              through a 6-stage mbarrier ring of (layer, n-block <= 128, 16 k) units
+// One persistent CTA per SM, 4 TC_EPI_PER_QUAD + 2 warps (14 by default):
+//   epilogue warps  TC_EPI_PER_QUAD threads per row / TMEM lane (taking 16-column batches in turn): input
+//              normalisation, per-layer epilogue TMEM -> registers -> bias + LeakyReLU -> hi/lo split ->
+//              next A operand; every layer, including 6->10 and 50->6, is a tensor-core GEMM
+//   MMA warp   TMEM allocation; lane 0 issues every tcgen05.mma and tcgen05.commit
+//   streamer   lane 0 streams the pre-swizzled weight images with cp.async.bulk (TMA bulk copy) through a
+//              byte-granular 96 KB ring with 16 mbarrier pairs; units are (layer, n-block, k-range):
+//              32 k in SWIZZLE_128B rows for layers up to 128 wide, 16 k in SWIZZLE_64B rows with
+//              n-blocks up to 256 (one tcgen05.mma spans the whole layer) otherwise.  With
+//              C1D_TC_CLUSTER > 1 the CTAs of a cluster fetch each unit once and multicast it.
 //
 // Operand placement (227 KB of shared memory cannot hold hi and lo of a 128 x 256 tile):
 //   A_hi   shared memory, K-major SWIZZLE_128B, 8 chunks of 32 k            (SS form)
 //   A_lo   tensor memory columns [256, 512), lane = row, column = k         (TS form)
-//   B_hi, B_lo  shared memory ring (K-major SWIZZLE_64B), one (layer, n-block<=128, 16 k) unit per stage
+//   B_hi, B_lo  shared memory ring, hi rows followed by lo rows inside a unit
 //   D      tensor memory columns [0, 256)
+//
+// Measured limits (tools/tc_issue_probe.py): one kind::tf32 MMA (M=128, K=8) holds the tensor pipe
+// for max(92, 128 N / 256 + 11) cycles with A in TMEM and 108 / 140 / 172 cycles at N = 128 / 192 / 256
+// with A in shared memory; a tile needs ~290 of them (41 k cycles) plus a 14-18 k cycle epilogue that
+// cannot overlap, because TMEM holds exactly one tile (256 D + 256 A_lo columns).
 #include <math.h>
 #include <stdlib.h>
 
