@@ -278,10 +278,23 @@ def test_edge_batches(golden):
         ok = exp[:W] > -1e99
         assert np.all(np.abs(got[ok] - exp[:W][ok]) <= _tol(exp[:W][ok]))
         np.testing.assert_array_equal(got[~ok], exp[:W][~ok])
-    # every row outside the cube: exact min_log_like, NaN blobs (likelihood.py:989-994)
-    bad = np.full((5, n), 1.5)
-    lnp, blobs = like.log_prob_and_blobs_batch(bad)
-    assert np.all(lnp == like.min_log_like) and np.all(np.isnan(blobs))
+    # every row outside the cube: exact min_log_like, NaN blobs (likelihood.py:989-994), no model; in both
+    # forms of stage 3 (a whole 32-walker item is rejected in the walker-per-lane form)
+    import os
+
+    bad = np.full((37, n), 1.5)
+    for layout in ("lanes", "warp"):
+        os.environ["C1D_P1D_LAYOUT"] = layout
+        try:
+            lnp, blobs = like.log_prob_and_blobs_batch(bad)
+            assert np.all(lnp == like.min_log_like) and np.all(np.isnan(blobs))
+            assert np.isnan(like.get_p1d_kms_batch(bad)).all()
+            mixed = np.concatenate([bad, x[:3], bad[:2]])
+            pm = like.get_p1d_kms_batch(mixed)
+            assert np.isnan(pm[:37]).all() and np.isnan(pm[40:]).all()
+            np.testing.assert_array_equal(pm[37:40], like.get_p1d_kms_batch(x[:3]))
+        finally:
+            del os.environ["C1D_P1D_LAYOUT"]
     # crossing the chunk boundary: rows are independent, so a tiled batch repeats its block bit for bit
     reps = 131072 // len(x) + 2
     big = torch.as_tensor(np.tile(x, (reps, 1)), device="cuda:0")
