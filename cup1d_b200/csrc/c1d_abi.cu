@@ -194,6 +194,23 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
     C1D_CUDA(ctx, cudaMemcpy2D(ctx->icov_pad, ldd * sizeof(double), ctx->dev[C1D_F_ICOV_FULL], (size_t)c.nd * sizeof(double),
                                (size_t)c.nd * sizeof(double), c.nd, cudaMemcpyDeviceToDevice));
   }
+  // zero-padded per-z blocks for the per-z chi2 GEMM (z blocks at 64-aligned offsets)
+  if (ctx->icovz_pad) { cudaFree(ctx->icovz_pad); ctx->icovz_pad = nullptr; }
+  {
+    const int tzw = (ctx->ndz_max + 63) / 64 * 64;
+    ctx->tzw = tzw;
+    C1D_CUDA(ctx, cudaMalloc(&ctx->icovz_pad, (size_t)c.nz * tzw * tzw * sizeof(double)));
+    C1D_CUDA(ctx, cudaMemset(ctx->icovz_pad, 0, (size_t)c.nz * tzw * tzw * sizeof(double)));
+    size_t off = 0;
+    for (int z = 0; z < c.nz; ++z) {
+      const int ndz = zd[z + 1] - zd[z];
+      C1D_CUDA(ctx, cudaMemcpy2D(ctx->icovz_pad + (size_t)z * tzw * tzw, (size_t)tzw * sizeof(double),
+                                 (const double*)ctx->dev[C1D_F_ICOV_BLOCKS] + off, (size_t)ndz * sizeof(double),
+                                 (size_t)ndz * sizeof(double), ndz, cudaMemcpyDeviceToDevice));
+      off += (size_t)ndz * ndz;
+    }
+  }
+  if (ctx->ws.dvz) { cudaFree(ctx->ws.dvz); ctx->ws.dvz = nullptr; }  // its width may have changed
   ctx->finalized = 1;
   {
     int rc = c1d_p1dw_prepare(ctx);  // two-bin rebinning maps for the walker-per-lane stage 3
@@ -211,7 +228,7 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
 static void ws_free(c1d_ctx* ctx) {
   Workspace& w = ctx->ws;
   cudaFree(w.status); cudaFree(w.lnprior); cudaFree(w.blobs); cudaFree(w.emu_in); cudaFree(w.amp);
-  cudaFree(w.dvec); cudaFree(w.chi2z); cudaFree(w.chi2p); cudaFree(w.lnp); cudaFree(w.xdev); cudaFree(w.out7); cudaFree(w.factors); cudaFree(w.blobs_q);
+  cudaFree(w.dvec); cudaFree(w.dvz); cudaFree(w.chi2z); cudaFree(w.chi2p); cudaFree(w.lnp); cudaFree(w.xdev); cudaFree(w.out7); cudaFree(w.factors); cudaFree(w.blobs_q);
   memset(&w, 0, sizeof(w));
 }
 
@@ -410,6 +427,7 @@ extern "C" int c1d_ctx_destroy(c1d_ctx* ctx) {
   c1d_p1dw_destroy(ctx);
   ws_free(ctx);
   if (ctx->icov_pad) cudaFree(ctx->icov_pad);
+  if (ctx->icovz_pad) cudaFree(ctx->icovz_pad);
   for (int f = 0; f < C1D_F_COUNT; ++f)
     if (ctx->dev[f]) cudaFree(ctx->dev[f]);
   for (int i = 0; i < 9; ++i)

@@ -66,6 +66,7 @@ struct Workspace {
   double* amp;     // [nz*cap*C1D_NAMP]
   double* dvec;    // [cap*ldd], pad columns stay zero
   double* chi2z;   // [cap*nz]
+  double* dvz;     // [cap*nz*tzw] residuals with every z block at a 64-aligned offset (lazily allocated), pads zero
   double* chi2p;   // [cap*npairs] partial dense chi2 per column-tile pair
   double* lnp;     // [cap]   (host-variant staging on the device)
   double* xdev;    // [cap*ndim]
@@ -88,6 +89,8 @@ struct c1d_ctx {
   cudaEvent_t ev[9];
   double last_ms[8];
   double* icov_pad;  // [ldd*ldd] zero-padded copy of the dense inverse covariance
+  double* icovz_pad; // [nz][tzw*tzw] zero-padded per-z inverse covariance blocks, tzw = ndz_max rounded up to 64
+  int tzw;
   // tensor-core emulator path (c1d_mlp_tc.cu)
   void* tc_state;
   // fp64 tensor-core emulator path (c1d_mlp_f64.cu)
@@ -129,7 +132,8 @@ void c1d_mlp64_destroy(c1d_ctx* ctx);
 // walker-per-lane stage 3: prepare builds the two-bin rebinning maps; launch returns 1 when it ran,
 // 0 when the caller must use the warp-per-walker kernel
 int c1d_p1dw_prepare(c1d_ctx* ctx);
-int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, cudaStream_t s);
+int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int want_chi2z, cudaStream_t s);
+int c1d_launch_chi2z(c1d_ctx* ctx, int64_t W, cudaStream_t s);  // per-z chi2 of the z-aligned residuals ws.dvz
 void c1d_p1dw_destroy(c1d_ctx* ctx);
 
 // tensor-core MLP (optional translation unit)

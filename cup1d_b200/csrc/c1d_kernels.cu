@@ -7,10 +7,11 @@
 //                k_gp_f64      GP posterior mean = batched kernel-vector product
 //   stage 3      k_fused_p1d   emulator polynomial -> contaminant templates -> rebin -> residual
 //                              (-> per-z chi2), warp per walker, tables staged in shared memory per z:
-//                              small batches, block-diagonal contexts, lnL_z requests
+//                              small batches and rebinning operators outside the two-bin form
 //                k_fused_p1d_lanes  the same with lane = walker (c1d_p1d_lanes.cu): large batches
 //   stage 4      k_chi2_dmma   chi2 = d^T C^-1 d: tiled fp64 tensor-core GEMM (DMMA), symmetric,
 //                              row-dot fused into the epilogue
+//                k_chi2z_dmma  per-z chi2 of z-aligned residuals (behind k_fused_p1d_lanes)
 //   stage 5      k_finalize    regulate + prior, blobs conventions
 //
 // Reference lines are cited next to each formula.
@@ -470,10 +471,12 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
 int c1d_launch_stage3(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int want_chi2z,
                       cudaStream_t s) {
   const c1d_config& cfg = ctx->cfg;
-  if (!want_chi2z) {
-    // no per-z chi2 needed: the walker-per-lane kernel (c1d_p1d_lanes.cu) when its rebinning form applies
-    const int rc = c1d_p1dw_launch(ctx, W, p_out, want_dvec, s);
-    if (rc != 0) return rc < 0 ? rc : C1D_OK;
+  {
+    // the walker-per-lane kernel (c1d_p1d_lanes.cu) when its rebinning form applies and the batch fills the
+    // machine; a requested per-z chi2 then comes from a small tensor-core kernel over its z-aligned residuals
+    const int rc = c1d_p1dw_launch(ctx, W, p_out, want_dvec, want_chi2z, s);
+    if (rc < 0) return rc;
+    if (rc > 0) return want_chi2z ? c1d_launch_chi2z(ctx, W, s) : C1D_OK;
   }
   int nfz_max = ctx->nfz_max, ndz_max = ctx->ndz_max;
   const int RWP = cfg.rebin_width | 1;
@@ -653,6 +656,117 @@ k_chi2_dmma(int64_t W, int ndp, const double* __restrict__ dvec, const double* _
     __syncthreads();
   }
   if (tid < Q_TW && w0 + tid < W) partial[(w0 + tid) * npairs + pair] = tot;
+}
+
+// Per-z chi2_z = d_z^T C_z^-1 d_z (likelihood.py:939-940) for the walker-per-lane stage 3: the residuals
+// live in a z-aligned buffer dvz[w][z * tzw + j] (tzw = widest z block rounded up to 64, pads zero) and the
+// per-z blocks in a zero-padded [nz][tzw][tzw] array, so every (walker tile, z) is a small dense
+// [128 x tzw] . [tzw x tzw] product on the fp64 tensor cores with the row-dot fused, exactly as above but
+// without the symmetric pairing (the blocks are only tzw / 64 column tiles wide).
+__global__ void __launch_bounds__(256)
+k_chi2z_dmma(int64_t W, int nz, int tzw, const double* __restrict__ dvz, const double* __restrict__ Cz,
+             double* __restrict__ chi2z) {
+  extern __shared__ __align__(16) double qsm[];
+  double (*As)[Q_TW][Q_ASTR] = reinterpret_cast<double (*)[Q_TW][Q_ASTR]>(qsm);
+  double (*Bs)[Q_KC][Q_BSTR] = reinterpret_cast<double (*)[Q_KC][Q_BSTR]>(qsm + 2 * Q_TW * Q_ASTR);
+  double (*red)[Q_TW] = reinterpret_cast<double (*)[Q_TW]>(qsm + 2 * Q_TW * Q_ASTR + 2 * Q_KC * Q_BSTR);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int64_t w0 = (int64_t)blockIdx.x * Q_TW;
+  const int z = blockIdx.y;
+  const int ldz = nz * tzw;
+  const double* dz = dvz + (size_t)z * tzw;           // column 0 of this z in a residual row
+  const double* cz = Cz + (size_t)z * tzw * tzw;
+  const int nk = tzw / Q_KC;
+  double tot = 0.0;  // thread r < 128 owns walker w0 + r
+
+  for (int jt = 0; jt < tzw / Q_TJ; ++jt) {
+    const int j0 = jt * Q_TJ;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    auto load_chunk = [&](int kc, int buf) {
+      const int i0 = kc * Q_KC;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {  // A: 128 rows x 8 pieces of 16 B
+        int piece = tid + t * 256;
+        int r = piece >> 3, cc = piece & 7;
+        int64_t wr = w0 + r;
+        if (wr >= W) wr = W - 1;
+        cp_async16(&As[buf][r][cc * 2], dz + wr * ldz + i0 + cc * 2);
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {  // B: 16 rows x 32 pieces
+        int piece = tid + t * 256;
+        int r = piece >> 5, cc = piece & 31;
+        cp_async16(&Bs[buf][r][cc * 2], cz + (size_t)(i0 + r) * tzw + j0 + cc * 2);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    load_chunk(0, 0);
+    for (int kc = 0; kc < nk; ++kc) {
+      const int buf = kc & 1;
+      if (kc + 1 < nk) {
+        load_chunk(kc + 1, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+#pragma unroll
+      for (int ks = 0; ks < Q_KC / 4; ++ks) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) af[a] = As[buf][32 * wm + 8 * a + (lane >> 2)][4 * ks + (lane & 3)];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf[b] = Bs[buf][4 * ks + (lane & 3)][32 * wn + 8 * b + (lane >> 2)];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+      }
+      __syncthreads();
+    }
+    // epilogue: sum_j Q[w][j] d[w][j] over this column tile
+    double ps[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int64_t wr = w0 + 32 * wm + 8 * a + (lane >> 2);
+      if (wr >= W) wr = W - 1;
+      double sum = 0.0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double2 dv = *reinterpret_cast<const double2*>(dz + wr * ldz + j0 + 32 * wn + 8 * b + 2 * (lane & 3));
+        sum = fma(acc[a][b][0], dv.x, sum);
+        sum = fma(acc[a][b][1], dv.y, sum);
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      ps[a] = sum;
+    }
+    if ((lane & 3) == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) red[wn][32 * wm + 8 * a + (lane >> 2)] = ps[a];
+    }
+    __syncthreads();
+    if (tid < Q_TW) tot += red[0][tid] + red[1][tid];
+    __syncthreads();
+  }
+  if (tid < Q_TW && w0 + tid < W) chi2z[(w0 + tid) * nz + z] = tot;
+}
+
+int c1d_launch_chi2z(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
+  dim3 grid((unsigned)((W + Q_TW - 1) / Q_TW), (unsigned)ctx->cfg.nz);
+  const size_t smem = (size_t)(2 * Q_TW * Q_ASTR + 2 * Q_KC * Q_BSTR + 2 * Q_TW) * sizeof(double);
+  C1D_CUDA(ctx, cudaFuncSetAttribute(k_chi2z_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_chi2z_dmma<<<grid, 256, smem, s>>>(W, ctx->cfg.nz, ctx->tzw, ctx->ws.dvz, ctx->icovz_pad, ctx->ws.chi2z);
+  ctx->launches++;
+  C1D_CUDA(ctx, cudaPeekAtLastError());
+  return C1D_OK;
 }
 
 int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, cudaStream_t s) {

@@ -11,9 +11,10 @@
 // buffer: a fine point feeds at most two adjacent data bins (checked on the host), so two running
 // sums per lane are flushed as the bins complete — in the same summation order as the banded form.
 //
-// Used when the per-z chi2 is not requested (dense-covariance contexts and model-only calls);
-// otherwise, or when the rebinning operator is not of the two-bin form, c1d_launch_stage3 falls
-// back to the warp-per-walker kernel.
+// When the per-z chi2 is requested (block-diagonal contexts, lnL_z outputs) the residuals are also
+// written to a z-aligned buffer and a small tensor-core kernel (k_chi2z_dmma) forms d_z^T C_z^-1 d_z.
+// Small batches, and rebinning operators that are not of the two-bin form, fall back to the
+// warp-per-walker kernel in c1d_launch_stage3.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(pl_threads(U), 1)
 k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restrict__ rwa_g,
                   const double* __restrict__ rwb_g, int64_t W, const int* __restrict__ status,
                   const double* __restrict__ amp, double* __restrict__ dvec, double* __restrict__ p_out,
-                  int nfz_max, int ndz_max) {
+                  double* __restrict__ dvz, int tzw, int nfz_max, int ndz_max) {
   constexpr int PL_WARPS = pl_threads(U) / 32;
   extern __shared__ __align__(16) double sm[];
   double* tabw = sm;                                     // [nfz_max][C1D_NCOL] table row of a fine point (nfz_max: multiple of U)
@@ -99,11 +100,13 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restr
       const bool ok = live && status[wv] == ST_OK;
       double* dv = dvec ? dvec + wv * c.ldd + d0 : nullptr;
       double* po = p_out ? p_out + wv * c.nd + d0 : nullptr;
+      double* dzp = dvz ? dvz + wv * ((int64_t)c.nz * tzw) + (int64_t)z * tzw : nullptr;  // z-aligned copy for the per-z chi2
       if (!__any_sync(0xffffffffu, ok)) {
         // rejected walkers carry no model (the reference returns None)
         if (live)
           for (int j = 0; j < ndz; ++j) {
             if (dv) dv[j] = 0.0;
+            if (dzp) dzp[j] = 0.0;
             if (po) po[j] = qnan;
           }
         continue;
@@ -147,6 +150,7 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restr
         const double dj = dat[j] - m;
         if (live) {
           if (dv) dv[j] = ok ? dj : 0.0;
+          if (dzp) dzp[j] = ok ? dj : 0.0;
           if (po) po[j] = ok ? m : qnan;
         }
       };
@@ -305,7 +309,7 @@ int c1d_p1dw_prepare(c1d_ctx* ctx) {
 
 // returns 1 when the launch was done here, 0 when the caller must use the warp-per-walker kernel,
 // a negative c1d_status on error
-int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, cudaStream_t s) {
+int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int want_chi2z, cudaStream_t s) {
   P1dwState* st = (P1dwState*)ctx->p1dw_state;
   // C1D_P1D_LAYOUT=warp | lanes overrides the choice by batch size (tests run both forms on the same inputs)
   const char* layout = getenv("C1D_P1D_LAYOUT");
@@ -317,7 +321,8 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, cudaS
   const int nfp_max = (nfz_max + 3) & ~3;
   const size_t smem = ((size_t)nfp_max * (C1D_NCOL + 2) + ndz_max + 32) * sizeof(double) + (size_t)nfp_max * sizeof(int) + 16;
   if (smem > 227 * 1024) return 0;
-  typedef void (*kern_t)(DevCtx, const int*, const double*, const double*, int64_t, const int*, const double*, double*, double*, int, int);
+  typedef void (*kern_t)(DevCtx, const int*, const double*, const double*, int64_t, const int*, const double*, double*, double*, double*, int,
+                         int, int);
   kern_t kern = nullptr;
   const int nc = (cfg.nc >= 5 && cfg.nc <= 7) ? cfg.nc : 0;
   const int sel = ((nc ? nc - 4 : 0) << 3) | (cfg.emu_kind << 2) | (cfg.metal_model << 1) | (cfg.uniform_k ? 1 : 0);
@@ -350,8 +355,18 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, cudaS
   if (grid > (items + warps - 1) / warps) grid = (items + warps - 1) / warps;
   if (grid < 1) grid = 1;
   double* dvec = want_dvec ? ctx->ws.dvec : nullptr;
+  double* dvz = nullptr;
+  if (want_chi2z) {
+    if (!ctx->ws.dvz) {
+      // allocated on first use: [cap][nz * tzw], pad columns stay zero
+      const size_t n = (size_t)ctx->ws.cap * cfg.nz * ctx->tzw;
+      C1D_CUDA(ctx, cudaMalloc(&ctx->ws.dvz, n * sizeof(double)));
+      C1D_CUDA(ctx, cudaMemsetAsync(ctx->ws.dvz, 0, n * sizeof(double), s));
+    }
+    dvz = ctx->ws.dvz;
+  }
   kern<<<(unsigned)grid, threads, smem, s>>>(ctx->d, st->d_ja, st->d_wa, st->d_wb, W, ctx->ws.status, ctx->ws.amp, dvec, p_out,
-                                                nfp_max, ndz_max);
+                                                dvz, ctx->tzw, nfp_max, ndz_max);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return 1;

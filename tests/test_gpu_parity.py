@@ -296,13 +296,19 @@ def test_edge_batches(golden):
         finally:
             del os.environ["C1D_P1D_LAYOUT"]
     # crossing the chunk boundary: rows are independent, so a tiled batch repeats its block bit for bit
+    # (within one form of stage 3: the short last chunk would otherwise take the warp-per-walker kernel)
     reps = 131072 // len(x) + 2
     big = torch.as_tensor(np.tile(x, (reps, 1)), device="cuda:0")
     assert big.shape[0] > 131072
-    out = like.log_prob_batch(big)
-    first = out[: len(x)]
-    assert torch.equal(out.view(reps, len(x)), first[None, :].expand(reps, len(x)))
-    np.testing.assert_array_equal(first.cpu().numpy(), like.log_prob_batch(x))
+    for layout in ("lanes", "warp"):
+        os.environ["C1D_P1D_LAYOUT"] = layout
+        try:
+            out = like.log_prob_batch(big)
+            first = out[: len(x)]
+            assert torch.equal(out.view(reps, len(x)), first[None, :].expand(reps, len(x)))
+            np.testing.assert_array_equal(first.cpu().numpy(), like.log_prob_batch(x))
+        finally:
+            del os.environ["C1D_P1D_LAYOUT"]
     # strided and float32 inputs are converted, not misread
     xs = np.asfortranarray(x[:16])
     np.testing.assert_array_equal(like.log_prob_batch(xs), like.log_prob_batch(x[:16]))
@@ -333,4 +339,17 @@ def test_both_stage3_forms_on_goldens(golden, monkeypatch, name, layout):
     none = np.isnan(refp).all(axis=1)
     assert np.isnan(p[none]).all()
     assert np.max(np.abs(p[~none] / refp[~none] - 1)) <= RTOL_P1D
+    # per-z log-likelihoods (k_chi2z_dmma behind the walker-per-lane form) and a z-masked call
+    lnl, lnl_z = like.get_log_like_batch(x)
+    rl = ref["loglike"]
+    inf = np.isinf(rl)
+    assert np.all(np.isinf(lnl[inf]))
+    assert np.all(np.abs(lnl[~inf] - rl[~inf]) <= _tol(rl[~inf]))
+    assert np.all(np.abs(lnl_z[~inf] - ref["loglike_all"][~inf]) <= _tol(ref["loglike_all"][~inf]))
+    if not np.isnan(ref["lnprob_zmask"]).any():
+        gz = like.log_prob_batch(x, zmask=ref["zmask"])
+        ez = ref["lnprob_zmask"]
+        okz = ez > -1e99
+        np.testing.assert_array_equal(gz[~okz], ez[~okz])
+        assert np.all(np.abs(gz[okz] - ez[okz]) <= _tol(ez[okz]))
     like.close()
