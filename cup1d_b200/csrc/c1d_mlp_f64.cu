@@ -233,6 +233,9 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
   }
 }
 
+// 13 warps are allocated as 16 (groups of four), so 128 registers per thread is the hardware cap for this
+// block size (a 144- or 152-register build fails to launch); register double buffering of the fragments
+// spills at 128 and was dropped
 __global__ void __launch_bounds__(M64_THREADS, 1)
 k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict__ emu_lo,
           const double* __restrict__ emu_hi, int64_t nrows, double* __restrict__ out, int out_stride) {
