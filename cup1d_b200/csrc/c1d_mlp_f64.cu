@@ -235,7 +235,8 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
 
 // 13 warps are allocated as 16 (groups of four), so 128 registers per thread is the hardware cap for this
 // block size (a 144- or 152-register build fails to launch); register double buffering of the fragments
-// spills at 128 and was dropped
+// spills at 128 and was dropped.  Also measured: no streamer warp (the last warp out of a slab buffer
+// starts its refill, 12 warps at 168 registers): 4.96 ms against 4.78 ms, 5.05 ms with double buffering.
 __global__ void __launch_bounds__(M64_THREADS, 1)
 k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict__ emu_lo,
           const double* __restrict__ emu_hi, int64_t nrows, double* __restrict__ out, int out_stride) {
