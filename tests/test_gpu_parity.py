@@ -353,3 +353,29 @@ def test_both_stage3_forms_on_goldens(golden, monkeypatch, name, layout):
         np.testing.assert_array_equal(gz[~okz], ez[~okz])
         assert np.all(np.abs(gz[okz] - ez[okz]) <= _tol(ez[okz]))
     like.close()
+
+
+def test_gp_large_batch_kernel():
+    """the shared-memory GP kernel (two rows per warp, table-based exp) takes over above ~215 walkers:
+    same tolerances against the oracle as the row-per-warp kernel"""
+    from cup1d_b200 import synth
+    from oracle.model import OracleLikelihood
+
+    spec = _synthetic("c2")
+    like = _like(spec)
+    ora = OracleLikelihood(spec)
+    x = np.concatenate([synth.walkers_ball(spec, 600, seed=3), synth.walkers_sweep(spec, 425, seed=4, frac_out=0.02)])
+    got = like.log_prob_and_blobs_vectorized(x)       # 1025 walkers: large-batch kernels, odd row count
+    small = like.log_prob_and_blobs_vectorized(x[:64])  # row-per-warp GP kernel
+    idx = np.r_[0:24, 600:640, len(x) - 1]
+    exp = ora.log_prob_and_blobs_many(x[idx])
+    bad = exp[:, 0] <= -1e99
+    np.testing.assert_array_equal(got[idx][bad, 0], exp[bad, 0])
+    assert np.all(np.abs(got[idx][~bad, 0] - exp[~bad, 0]) <= _tol(exp[~bad, 0]))
+    fin = small[:, 0] > -1e99
+    assert np.all(np.abs(got[:64][fin, 0] - small[fin, 0]) <= _tol(small[fin, 0]))
+    p = like.get_p1d_kms_batch(x[idx][~bad][:16])
+    for i, v in enumerate(x[idx][~bad][:16]):
+        po = np.concatenate(ora.get_p1d_kms(values=v)[0])
+        assert np.max(np.abs(p[i] / po - 1)) <= RTOL_P1D
+    like.close()
