@@ -236,7 +236,9 @@ k_gp_f64(DevCtx c, const double* __restrict__ emu_in, int64_t nrows, double* __r
 // training point read feeds two rows, and e^x from a 32-entry table + degree-6 polynomial: 34 fp64
 // operations per (row, training point) instead of ~73 with eight uncoalesced global loads.  One
 // persistent 16-warp CTA per SM.  Used when the training set fits in shared memory.
+#ifndef GP_THREADS
 #define GP_THREADS 512
+#endif
 __global__ void __launch_bounds__(GP_THREADS, 1)
 k_gp_f64_smem(DevCtx c, const double* __restrict__ emu_in, int64_t nrows, double* __restrict__ out,
               int out_stride, int ntp) {
