@@ -16,6 +16,7 @@ GOLDEN_NAMES = [
     "hcd_boss",
     "hcd_const",
     "global_all",
+    "chab2019_real",  # the reference's measured Chabanier et al. (2019) data set and covariance
 ]
 
 

@@ -190,8 +190,46 @@ CONFIGS = {
     # variations: free HCD_const (pivot, otype const)
     "hcd_const": lambda: make("hcd_const", RefGPEmulator(small_gp(26, "mpg"), "synthetic_mpg_gp", "mpg"), "chab", nz=5, rebin_k=1, full=True, seed=600, name_variation="HCD0"),
     # 11 nodes per family: 189 free parameters
+    "chab2019_real": lambda: make_real_chabanier(),
     "global_all": lambda: make("global_all", RefMLPEmulator(small_nn(27, "mpg"), "synthetic_mpg_nn", "mpg"), "chab", rebin_k=1, seed=700, fit_type="global_all", use_ic=False, n=(8, 6, 2), width=0.05),
 }
+
+
+def make_real_chabanier(name="chab2019_real", nz=11, rebin_k=2, seed=800, n=(24, 20, 4)):
+    """The reference's own measured data set: Chabanier et al. (2019) P1D, statistical + systematic
+    covariance with its correlation matrices, parsed by the reference's read_from_file
+    (cup1d/p1ds/data_Chabanier2019.py:43-120; its P1D_Chabanier2019 class itself fails in
+    _drop_zbins, base_p1d_data.py:72, so the z cut is made here), 11 z x 35 k, block-diagonal."""
+    rh.setup()
+    from cup1d.p1ds import data_Chabanier2019 as dc
+
+    tot = dc.read_from_file(add_syst=True)
+    stat = dc.read_from_file(add_syst=False)
+    zs = np.asarray(tot[0][:nz], dtype=float)
+    ks = [np.asarray(k, dtype=float) for k in tot[1][:nz]]
+    kmins, kmaxs = [], []
+    for k in ks:
+        edges = np.concatenate([[k[0] - 0.5 * (k[1] - k[0])], 0.5 * (k[1:] + k[:-1]), [k[-1] + 0.5 * (k[-1] - k[-2])]])
+        kmins.append(edges[:-1])
+        kmaxs.append(edges[1:])
+    Pk = [np.asarray(p, dtype=float) for p in tot[2][:nz]]
+    cov = [np.asarray(c, dtype=float) for c in tot[3][:nz]]
+    cov_stat = [np.asarray(c, dtype=float) for c in stat[3][:nz]]
+    data = rh.make_data_namespace(zs, ks, kmins, kmaxs, Pk, cov, cov_stat)
+    emu = RefMLPEmulator(small_nn(28, "mpg"), "synthetic_mpg_nn", "mpg")
+    nd = sum(len(k) for k in ks)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        like, args = rh.build_reference_likelihood(emu, data, rebin_k=rebin_k, emu_cov_type="block")
+        x = walkers(like, n[0], n[1], n[2], seed + 2, width=0.1)
+        res = run_reference(like, x, zmask=[zs[1], zs[4]])
+    spec = spec_from_likelihood(like)
+    path = os.path.join(OUT, name + ".npz")
+    save_spec(path, spec, x=x, **res)
+    lp = res["lnprob_blobs"][:, 0]
+    print("%-18s ndim=%3d N_d=%4d W=%d  lnP range [%.3g, %.3g]  rejected=%d  size=%.0f kB"
+          % (name, x.shape[1], nd, len(x), lp[lp > -1e99].min(), lp.max(), int((lp <= -1e99).sum()), os.path.getsize(path) / 1e3))
+
 
 def make_agn_kat():
     """AGN_Model.get_contamination of the reference (AGN_model.py:93-120) on a few (z, coeff)"""
