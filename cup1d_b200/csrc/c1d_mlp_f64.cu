@@ -35,20 +35,28 @@
 
 namespace {
 
-constexpr int M64_GROUPS = 3;                         // row groups per CTA (one warp of each per SM sub-partition)
+constexpr int M64_GROUPS = 3;                         // row groups per CTA of the throughput variant (one warp of each per SM sub-partition)
 constexpr int M64_RB = 3;                             // 8-row blocks per group
 constexpr int M64_ROWS = 8 * M64_RB;                  // rows of one group's tile
-constexpr int M64_CWARPS = 4 * M64_GROUPS;            // compute warps
-constexpr int M64_THREADS = 32 * (M64_CWARPS + 1);   // + the weight streamer
-constexpr int M64_STR = M64_GROUPS * M64_ROWS + 4;   // doubles per k-row of the activation tile
-static_assert(M64_STR % 16 == 4 || M64_STR % 16 == 12, "k-row stride must spread fragments over all banks");
+// The kernel is instantiated twice: <3 groups, 2 slab buffers> for throughput (72 rows per CTA) and
+// <1 group, 4 slab buffers> for small batches, where a CTA holds one 24-row tile, the rows spread over
+// up to 148 CTAs and four slabs in flight hide the L2 latency that otherwise paces a single tile.
+template <int G> struct M64Geom {
+  static constexpr int CWARPS = 4 * G;             // compute warps
+  static constexpr int THREADS = 32 * (CWARPS + 1);  // + the weight streamer
+  static constexpr int STR = G * M64_ROWS + 4;     // doubles per k-row of the activation tile
+  static_assert(STR % 16 == 4 || STR % 16 == 12, "k-row stride must spread fragments over all banks");
+};
 constexpr int M64_MAXW = 256;       // widest layer
-constexpr int M64_NBUF = 2;         // weight slab buffers (ring)
+constexpr int M64_NBUF = 2;         // weight slab buffers (ring) of the throughput variant
+constexpr int M64_NBUF_SMALL = 4;   // ... of the small-batch variant
 constexpr int M64_SLAB = 4224;      // doubles per weight slab buffer
 constexpr int M64_MAX_SLABS = 120;
 constexpr int M64_MAXBIAS = 1024;   // doubles of padded biases kept in shared memory
-constexpr size_t M64_SMEM = ((size_t)M64_MAXW * M64_STR + M64_NBUF * (size_t)M64_SLAB + M64_MAXBIAS) * sizeof(double) + 16 * M64_NBUF;
-static_assert(M64_SMEM <= 232448, "shared memory budget");
+template <int G, int NBUF> constexpr size_t m64_smem() {
+  return ((size_t)M64_MAXW * M64Geom<G>::STR + NBUF * (size_t)M64_SLAB + M64_MAXBIAS) * sizeof(double) + 16 * NBUF;
+}
+static_assert(m64_smem<M64_GROUPS, M64_NBUF>() <= 232448 && m64_smem<1, M64_NBUF_SMALL>() <= 232448, "shared memory budget");
 
 struct M64Slab {
   uint32_t w_off;   // doubles from the start of the padded weight image
@@ -123,7 +131,7 @@ __device__ __forceinline__ void load_inputs(const M64Plan& p, const double* __re
 
 // one layer on one tile; q is the running slab index (buffer parity), returns with every
 // activation of the layer written (or, for the output layer, stored to `out`)
-template <int NB>
+template <int NB, int G, int NBUF>
 __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint32_t& q, uint32_t bar_full, uint32_t bar_empty,
                                           double* act, const double* wbuf, const double* bsm, bool is_out, int64_t row0, int64_t nrows,
                                           double* __restrict__ out, int out_stride, long long* dbg) {
@@ -157,19 +165,19 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
 
   for (;;) {
     const M64Slab sl = p.slabs[s];
-    const uint32_t buf = q % M64_NBUF;
+    const uint32_t buf = q % NBUF;
     M64_DBG(const long long tw0 = dbg ? clock64() : 0;)
-    mbar_wait(bar_full + 8 * buf, (q / M64_NBUF) & 1u);  // slab q has landed
+    mbar_wait(bar_full + 8 * buf, (q / NBUF) & 1u);  // slab q has landed
     M64_DBG(const long long tw1 = dbg ? clock64() : 0;)
     const double* wb = wbuf + buf * M64_SLAB;
     if (cnt > 0) {
-      const double* ap = act + (size_t)(sl.k0 + kq) * M64_STR + r0 + g;
+      const double* ap = act + (size_t)(sl.k0 + kq) * M64Geom<G>::STR + r0 + g;
       const double* bp = wb + kq * ns + n0 + g;
 #pragma unroll 2
       for (int kk = 0; kk < (int)sl.kc; kk += 4) {
         double af[M64_RB], bf[NB];
 #pragma unroll
-        for (int a = 0; a < M64_RB; ++a) af[a] = ap[kk * M64_STR + 8 * a];
+        for (int a = 0; a < M64_RB; ++a) af[a] = ap[kk * M64Geom<G>::STR + 8 * a];
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) bf[nb] = (nb < NB - 1 || last_blk) ? bp[kk * ns + 8 * nb] : 0.0;
 #pragma unroll
@@ -206,8 +214,8 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
           if (__double2hiint(v1) < 0) v1 *= slope;
           const double first = swap ? v1 : v0, second = swap ? v0 : v1;
           const int nf = n0 + 8 * nb + 2 * kq + (swap ? 1 : 0), nsx = n0 + 8 * nb + 2 * kq + (swap ? 0 : 1);
-          act[(size_t)nf * M64_STR + r0 + 8 * a + g] = first;
-          act[(size_t)nsx * M64_STR + r0 + 8 * a + g] = second;
+          act[(size_t)nf * M64Geom<G>::STR + r0 + 8 * a + g] = first;
+          act[(size_t)nsx * M64Geom<G>::STR + r0 + 8 * a + g] = second;
         }
       }
     }
@@ -237,36 +245,37 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
 // block size (a 144- or 152-register build fails to launch); register double buffering of the fragments
 // spills at 128 and was dropped.  Also measured: no streamer warp (the last warp out of a slab buffer
 // starts its refill, 12 warps at 168 registers): 4.96 ms against 4.78 ms, 5.05 ms with double buffering.
-__global__ void __launch_bounds__(M64_THREADS, 1)
+template <int G, int NBUF>
+__global__ void __launch_bounds__(M64Geom<G>::THREADS, 1)
 k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict__ emu_lo,
           const double* __restrict__ emu_hi, int64_t nrows, double* __restrict__ out, int out_stride) {
   extern __shared__ __align__(16) double smem_d[];
-  double* act = smem_d;                                  // [M64_MAXW][M64_STR]
-  double* wbuf = smem_d + (size_t)M64_MAXW * M64_STR;    // [M64_NBUF][M64_SLAB]
-  double* bsm = wbuf + M64_NBUF * M64_SLAB;               // [M64_MAXBIAS] padded biases of all layers
-  const uint32_t bar_full = smem_u32(bsm + M64_MAXBIAS), bar_empty = bar_full + 8 * M64_NBUF;
+  double* act = smem_d;                                  // [M64_MAXW][M64Geom<G>::STR]
+  double* wbuf = smem_d + (size_t)M64_MAXW * M64Geom<G>::STR;    // [NBUF][M64_SLAB]
+  double* bsm = wbuf + NBUF * M64_SLAB;               // [M64_MAXBIAS] padded biases of all layers
+  const uint32_t bar_full = smem_u32(bsm + M64_MAXBIAS), bar_empty = bar_full + 8 * NBUF;
   const int64_t ntiles = (nrows + M64_ROWS - 1) / M64_ROWS;
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < p.n_bias; i += M64_THREADS) bsm[i] = __ldg(p.bimg + i);
+  for (int i = threadIdx.x; i < p.n_bias; i += M64Geom<G>::THREADS) bsm[i] = __ldg(p.bimg + i);
   if (threadIdx.x == 0) {
-    for (int b = 0; b < M64_NBUF; ++b) {
+    for (int b = 0; b < NBUF; ++b) {
       mbar_init(bar_full + 8 * b, 1);
-      mbar_init(bar_empty + 8 * b, M64_CWARPS);
+      mbar_init(bar_empty + 8 * b, M64Geom<G>::CWARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   // both groups walk the same number of tiles so that they consume the same slab stream
   // (surplus tiles hold no rows)
-  const int64_t my_tiles = (ntiles + M64_GROUPS * (int64_t)gridDim.x - 1) / (M64_GROUPS * (int64_t)gridDim.x);
-  if (warp == M64_CWARPS) {
+  const int64_t my_tiles = (ntiles + G * (int64_t)gridDim.x - 1) / (G * (int64_t)gridDim.x);
+  if (warp == M64Geom<G>::CWARPS) {
     // ============================== weight streamer ==============================
     if ((threadIdx.x & 31) == 0) {
       uint32_t q = 0;
       for (int64_t it = 0; it < my_tiles; ++it)
         for (int s = 0; s < p.n_slabs; ++s, ++q) {
-          const uint32_t b = q % M64_NBUF;
-          mbar_wait(bar_empty + 8 * b, ((q / M64_NBUF) & 1u) ^ 1u);  // passes at once on the first lap
+          const uint32_t b = q % NBUF;
+          mbar_wait(bar_empty + 8 * b, ((q / NBUF) & 1u) ^ 1u);  // passes at once on the first lap
           const M64Slab sl = p.slabs[s];
           const uint32_t bytes = (uint32_t)sl.kc * (uint32_t)(p.np[sl.layer] + 4) * 8u;
           mbar_expect_tx(bar_full + 8 * b, bytes);
@@ -280,7 +289,7 @@ k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict
   uint32_t q = 0;
   double xin[2];
   for (int64_t it = 0; it < my_tiles; ++it) {
-    const int64_t tile = (it * gridDim.x + blockIdx.x) * M64_GROUPS + grp;
+    const int64_t tile = (it * gridDim.x + blockIdx.x) * G + grp;
     const int64_t row0 = tile * M64_ROWS;
     // normalised inputs (x - lo)/(hi - lo) - 0.5, k rows padded to 8 with zeros; they were fetched
     // while the previous tile was in its last hidden layers
@@ -289,7 +298,7 @@ k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int t = gtid + 128 * u;
-      if (t < 8 * M64_ROWS) act[(t / M64_ROWS) * M64_STR + M64_ROWS * grp + (t % M64_ROWS)] = xin[u];
+      if (t < 8 * M64_ROWS) act[(t / M64_ROWS) * M64Geom<G>::STR + M64_ROWS * grp + (t % M64_ROWS)] = xin[u];
     }
     group_sync(grp);
     int s = 0;
@@ -303,23 +312,23 @@ k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict
       M64_DBG(dbg = dbg_on ? dbg_store + 3 * l : nullptr; if (dbg) dbg[0] = dbg[1] = dbg[2] = 0;)
       const bool is_out = l == p.n_layers - 1;
       if (l == p.n_layers - 2 && it + 1 < my_tiles)
-        load_inputs(p, emu_in, emu_lo, emu_hi, (((it + 1) * gridDim.x + blockIdx.x) * M64_GROUPS + grp) * M64_ROWS, nrows, gtid, xin);
+        load_inputs(p, emu_in, emu_lo, emu_hi, (((it + 1) * gridDim.x + blockIdx.x) * G + grp) * M64_ROWS, nrows, gtid, xin);
       const int nb = (p.nbt[l] + 3) >> 2;
       switch (nb) {
-        case 1: m64_layer<1>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
-        case 2: m64_layer<2>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
-        case 3: m64_layer<3>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
-        case 4: m64_layer<4>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
-        case 5: m64_layer<5>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
-        case 6: m64_layer<6>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
-        case 7: m64_layer<7>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
-        default: m64_layer<8>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        case 1: m64_layer<1, G, NBUF>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        case 2: m64_layer<2, G, NBUF>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        case 3: m64_layer<3, G, NBUF>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        case 4: m64_layer<4, G, NBUF>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        case 5: m64_layer<5, G, NBUF>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        case 6: m64_layer<6, G, NBUF>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        case 7: m64_layer<7, G, NBUF>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
+        default: m64_layer<8, G, NBUF>(p, l, s, q, bar_full, bar_empty, act, wbuf, bsm, is_out, row0, nrows, out, out_stride, dbg); break;
       }
     }
 #ifdef C1D_MLP64_TIMING
     if (dbg_on) {
       const long long tt1 = clock64();
-      for (int w = 0; w < M64_CWARPS; ++w) {
+      for (int w = 0; w < M64Geom<G>::CWARPS; ++w) {
         if (w == warp) {
           printf("mlp64 warp %d tile cycles %lld | per layer wait/compute/epilogue:", warp, tt1 - tt0);
           for (int l = 0; l < p.n_layers; ++l) printf(" L%d %lld/%lld/%lld", l, dbg_store[3 * l], dbg_store[3 * l + 1], dbg_store[3 * l + 2]);
@@ -420,7 +429,10 @@ int c1d_mlp64_prepare(c1d_ctx* ctx) {
   C1D_CUDA(ctx, cudaMemcpy(st->d_b, bimg.data(), bimg.size() * sizeof(double), cudaMemcpyHostToDevice));
   p.wimg = st->d_w;
   p.bimg = st->d_b;
-  C1D_CUDA(ctx, cudaFuncSetAttribute(k_mlp_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M64_SMEM));
+  C1D_CUDA(ctx, cudaFuncSetAttribute(k_mlp_f64<M64_GROUPS, M64_NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)m64_smem<M64_GROUPS, M64_NBUF>()));
+  C1D_CUDA(ctx, cudaFuncSetAttribute(k_mlp_f64<1, M64_NBUF_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)m64_smem<1, M64_NBUF_SMALL>()));
   return C1D_OK;
 }
 
@@ -430,9 +442,20 @@ int c1d_mlp64_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* 
     snprintf(ctx->err, sizeof(ctx->err), "fp64 MLP not prepared");
     return C1D_ERR_STATE;
   }
-  const int64_t npairs = (nrows + M64_GROUPS * M64_ROWS - 1) / (M64_GROUPS * M64_ROWS);
-  const int grid = (int)(npairs < ctx->num_sms ? npairs : ctx->num_sms);
-  k_mlp_f64<<<grid, M64_THREADS, M64_SMEM, s>>>(st->p, emu_in, ctx->d.emu_lo, ctx->d.emu_hi, nrows, out, out_stride);
+  const int64_t ntiles = (nrows + M64_ROWS - 1) / M64_ROWS;  // 24-row tiles
+  // measured on C4: the small-batch variant wins up to ~2 waves of 24-row tiles (64 walkers: 84 -> 47 us),
+  // ties at 1024 walkers and loses beyond
+  if (ntiles <= 2 * (int64_t)ctx->num_sms) {
+    // small batch: one tile per CTA spreads the rows over the machine, four slabs in flight
+    const int grid = (int)(ntiles < ctx->num_sms ? ntiles : ctx->num_sms);
+    k_mlp_f64<1, M64_NBUF_SMALL><<<grid, M64Geom<1>::THREADS, m64_smem<1, M64_NBUF_SMALL>(), s>>>(
+        st->p, emu_in, ctx->d.emu_lo, ctx->d.emu_hi, nrows, out, out_stride);
+  } else {
+    const int64_t ntriples = (ntiles + M64_GROUPS - 1) / M64_GROUPS;
+    const int grid = (int)(ntriples < ctx->num_sms ? ntriples : ctx->num_sms);
+    k_mlp_f64<M64_GROUPS, M64_NBUF><<<grid, M64Geom<M64_GROUPS>::THREADS, m64_smem<M64_GROUPS, M64_NBUF>(), s>>>(
+        st->p, emu_in, ctx->d.emu_lo, ctx->d.emu_hi, nrows, out, out_stride);
+  }
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return C1D_OK;
