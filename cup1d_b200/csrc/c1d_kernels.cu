@@ -33,9 +33,28 @@ __global__ void __launch_bounds__(128)
 k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ status,
          double* __restrict__ lnprior, double* __restrict__ blobs, double* __restrict__ emu_in,
          double* __restrict__ amp, uint32_t flags) {
+  // the z-function rows of this block's redshift (ELL weights with the parameter offset and scale they
+  // multiply) are staged in shared memory: the inner loop then has one dependent global load (the
+  // walker's coordinate) instead of four
+  extern __shared__ __align__(16) double s1[];
+  const int z = blockIdx.y;
+  const int nt = C1D_NQ * c.ell_width;
+  double* s_wgt = s1;            // [NQ * ell]
+  double* s_pm = s_wgt + nt;     // pmin[idx]
+  double* s_ps = s_pm + nt;      // pscale[idx]
+  int* s_idx = reinterpret_cast<int*>(s_ps + nt);
+  for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+    const int iq = t / c.ell_width, e = t - iq * c.ell_width;
+    const int g = (iq * c.nz + z) * c.ell_width + e;
+    const int idx = c.zidx[g];
+    s_idx[t] = idx;
+    s_wgt[t] = c.zwgt[g];
+    s_pm[t] = idx >= 0 ? c.pmin[idx] : 0.0;
+    s_ps[t] = idx >= 0 ? c.pscale[idx] : 0.0;
+  }
+  __syncthreads();
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= W) return;
-  const int z = blockIdx.y;
   const double* xw = x + w * c.ndim;
 
   // primordial-power rescaling (lya_theory.py:281-307, 542-580)
@@ -90,8 +109,9 @@ k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ st
       int row = iq * c.nz + z;
       double lin = c.zbase[row];
       for (int e = 0; e < c.ell_width; ++e) {
-        int idx = c.zidx[row * c.ell_width + e];
-        if (idx >= 0) lin += c.zwgt[row * c.ell_width + e] * param_value(c, xw, idx);
+        const int t = iq * c.ell_width + e;
+        const int idx = s_idx[t];
+        if (idx >= 0) lin += s_wgt[t] * (s_pm[t] + xw[idx] * s_ps[t]);  // wgt * value_from_cube (likelihood_parameter.py:58-61)
       }
       // zero the '<= null' values (si_mult.py:170-176), then the output type
       double v = c.zotype[iq] ? exp(lin) : lin;
@@ -173,7 +193,8 @@ int c1d_launch_stage1(c1d_ctx* ctx, const double* x, int64_t W, double* blobs_ou
   int threads = 128;
   int64_t blocks = (W + threads - 1) / threads;
   C1D_CUDA(ctx, cudaMemsetAsync(ctx->ws.status, 0, (size_t)W * sizeof(int), s));
-  k_stage1<<<dim3((unsigned)blocks, (unsigned)ctx->cfg.nz), threads, 0, s>>>(ctx->d, x, W, ctx->ws.status, ctx->ws.lnprior,
+  const size_t smem1 = (size_t)C1D_NQ * ctx->cfg.ell_width * (3 * sizeof(double) + sizeof(int));
+  k_stage1<<<dim3((unsigned)blocks, (unsigned)ctx->cfg.nz), threads, smem1, s>>>(ctx->d, x, W, ctx->ws.status, ctx->ws.lnprior,
                                                  blobs_out, ctx->ws.emu_in, ctx->ws.amp, flags);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
