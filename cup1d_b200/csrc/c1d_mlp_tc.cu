@@ -22,7 +22,9 @@
 // Measured limits (tools/tc_issue_probe.py): one kind::tf32 MMA (M=128, K=8) holds the tensor pipe
 // for max(92, 128 N / 256 + 11) cycles with A in TMEM and 108 / 140 / 172 cycles at N = 128 / 192 / 256
 // with A in shared memory; a tile needs ~290 of them (41 k cycles) plus a 14-18 k cycle epilogue that
-// cannot overlap, because TMEM holds exactly one tile (256 D + 256 A_lo columns).
+// cannot overlap, because TMEM holds exactly one tile (256 D + 256 A_lo columns).  Measured without gain:
+// cluster multicast of the weight stream, and folding a_hi . b_hi and a_hi . b_lo of the narrow layers
+// into one MMA over the stacked [b_hi; b_lo] rows (2 instead of 3 MMAs per k-step; layer times unchanged).
 #include <math.h>
 #include <stdlib.h>
 
