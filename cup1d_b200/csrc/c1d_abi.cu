@@ -247,7 +247,7 @@ static int ws_reserve(c1d_ctx* ctx, int64_t W) {
   C1D_CUDA(ctx, cudaMalloc(&w.dvec, (size_t)cap * ctx->d.ldd * sizeof(double)));
   C1D_CUDA(ctx, cudaMemset(w.dvec, 0, (size_t)cap * ctx->d.ldd * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.chi2z, (size_t)cap * c.nz * sizeof(double)));
-  C1D_CUDA(ctx, cudaMalloc(&w.chi2p, (size_t)cap * ((ctx->d.ldd / 64 + 1) / 2) * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.chi2p, (size_t)cap * (ctx->d.ldd / 64) * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.lnp, cap * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.xdev, (size_t)cap * c.ndim * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.out7, (size_t)cap * 7 * sizeof(double)));

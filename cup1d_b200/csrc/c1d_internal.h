@@ -67,7 +67,7 @@ struct Workspace {
   double* dvec;    // [cap*ldd], pad columns stay zero
   double* chi2z;   // [cap*nz]
   double* dvz;     // [cap*nz*tzw] residuals with every z block at a 64-aligned offset (lazily allocated), pads zero
-  double* chi2p;   // [cap*npairs] partial dense chi2 per column-tile pair
+  double* chi2p;   // [cap*(ldd/64)] partial dense chi2 per 64-column tile
   double* lnp;     // [cap]   (host-variant staging on the device)
   double* xdev;    // [cap*ndim]
   double* out7;    // [cap*7] packed (lnP, blob[6]) rows for the host variant

@@ -652,9 +652,10 @@ int c1d_launch_stage3(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int
 // tiled fp64 GEMM on the tensor cores (mma.sync m8n8k4 f64) with the row-dot fused into the
 // epilogue.  CTA tile = 128 walkers x 64 columns j; the K loop runs over rows i of C^-1 in
 // chunks of 16 staged with cp.async (double buffered).  C^-1 is symmetric: for column tile
-// jt only i < (jt+1)*64 is visited, the strictly-lower part counted twice; column tiles are
-// paired (jt, ntj-1-jt) so that every CTA does the same amount of work.  Both operands are
-// zero-padded to ndp = multiple of 64, so there is no edge handling.
+// jt only i < (jt+1)*64 is visited, the strictly-lower part counted twice; the grid runs the
+// costliest column tiles first and every (walker, column tile) leaves one partial sum that
+// k_finalize adds in a fixed order.  Both operands are zero-padded to ndp = multiple of 64, so
+// there is no edge handling.
 // ---------------------------------------------------------------------------------------
 #define Q_TW 128
 #define Q_TJ 64
@@ -674,25 +675,24 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 __global__ void __launch_bounds__(256)
 k_chi2_dmma(int64_t W, int ndp, const double* __restrict__ dvec, const double* __restrict__ Cp,
-            double* __restrict__ partial, int npairs) {
+            double* __restrict__ partial) {
   extern __shared__ __align__(16) double qsm[];
   double (*As)[Q_TW][Q_ASTR] = reinterpret_cast<double (*)[Q_TW][Q_ASTR]>(qsm);
   double (*Bs)[Q_KC][Q_BSTR] = reinterpret_cast<double (*)[Q_KC][Q_BSTR]>(qsm + 2 * Q_TW * Q_ASTR);
   double (*red)[Q_TW] = reinterpret_cast<double (*)[Q_TW]>(qsm + 2 * Q_TW * Q_ASTR + 2 * Q_KC * Q_BSTR);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;
-  // walker tiles are the fast grid index: all CTAs in flight stream the same two column tiles of C^-1.
+  // walker tiles are the fast grid index: all CTAs in flight stream the same column tile of C^-1.
   // (Measured alternative, column-tile pairs fastest: the residuals are then read from HBM once, 371 MB
   // instead of 1.94 GB per launch, but the kernel takes 1.28 ms instead of 1.10 ms — it is DMMA-bound,
   // the extra reads are hidden — so the faster order stays.)
   const int64_t w0 = (int64_t)blockIdx.x * Q_TW;
   const int ntj = ndp / Q_TJ;
-  const int pair = blockIdx.y;
-  double tot = 0.0;  // thread r < 128 owns walker w0 + r
-
-  for (int half = 0; half < 2; ++half) {
-    const int jt = half == 0 ? pair : ntj - 1 - pair;
-    if (half == 1 && jt == pair) break;  // the middle tile pairs with itself
+  // one column tile per CTA, the costliest (last) tiles first.  (Measured against pairing tiles
+  // (y, ntj-1-y) for equal work per CTA: the smaller units balance medium batches over the SMs, 0.135 ->
+  // 0.088 ms at 4096 walkers and 0.199 -> 0.164 ms at 8192 on C4, and tie at 65 536.)
+  {
+    const int jt = ntj - 1 - (int)blockIdx.y;
     const int j0 = jt * Q_TJ;
     const int nk = (jt + 1) * (Q_TJ / Q_KC);
     const int kdiag = jt * (Q_TJ / Q_KC);
@@ -774,10 +774,9 @@ k_chi2_dmma(int64_t W, int ndp, const double* __restrict__ dvec, const double* _
       for (int a = 0; a < 4; ++a) red[wn][32 * wm + 8 * a + (lane >> 2)] = ps[a];
     }
     __syncthreads();
-    if (tid < Q_TW) tot += red[0][tid] + red[1][tid];
+    if (tid < Q_TW && w0 + tid < W) partial[(w0 + tid) * ntj + jt] = red[0][tid] + red[1][tid];  // thread r < 128 owns walker w0 + r
     __syncthreads();
   }
-  if (tid < Q_TW && w0 + tid < W) partial[(w0 + tid) * npairs + pair] = tot;
 }
 
 // Per-z chi2_z = d_z^T C_z^-1 d_z (likelihood.py:939-940) for the walker-per-lane stage 3: the residuals
@@ -894,12 +893,11 @@ int c1d_launch_chi2z(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
 int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
   const int ndp = ctx->d.ldd;
   const int ntj = ndp / Q_TJ;
-  const int npairs = (ntj + 1) / 2;
-  dim3 grid((unsigned)((W + Q_TW - 1) / Q_TW), (unsigned)npairs);
+  dim3 grid((unsigned)((W + Q_TW - 1) / Q_TW), (unsigned)ntj);
   const size_t smem = (size_t)(2 * Q_TW * Q_ASTR + 2 * Q_KC * Q_BSTR + 2 * Q_TW) * sizeof(double);
   // per launch, not once per process: the attribute is per device and a process may own several contexts
   C1D_CUDA(ctx, cudaFuncSetAttribute(k_chi2_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_chi2_dmma<<<grid, 256, smem, s>>>(W, ndp, ctx->ws.dvec, ctx->icov_pad, ctx->ws.chi2p, npairs);
+  k_chi2_dmma<<<grid, 256, smem, s>>>(W, ndp, ctx->ws.dvec, ctx->icov_pad, ctx->ws.chi2p);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return C1D_OK;
@@ -910,7 +908,7 @@ int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_finalize(DevCtx c, int64_t W, const int* __restrict__ status, const double* __restrict__ lnprior,
-           const double* __restrict__ chi2z, const double* __restrict__ chi2p, int npairs, int use_full,
+           const double* __restrict__ chi2z, const double* __restrict__ chi2p, int ntj, int use_full,
            double* __restrict__ lnp, double* __restrict__ lnl_z, double* __restrict__ blobs,
            double* __restrict__ chi2_out, uint32_t flags) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -920,8 +918,12 @@ k_finalize(DevCtx c, int64_t W, const int* __restrict__ status, const double* __
   double loglike = ninf;
   if (st == ST_OK) {
     if (use_full) {
-      double chi2 = 0.0;  // fixed summation order over the column-tile pairs
-      for (int p = 0; p < npairs; ++p) chi2 += chi2p[w * npairs + p];
+      double chi2 = 0.0;  // fixed summation order: column tiles (p, ntj-1-p) first, then over p
+      for (int p = 0; 2 * p < ntj; ++p) {
+        double v = chi2p[w * ntj + p];
+        if (ntj - 1 - p != p) v += chi2p[w * ntj + ntj - 1 - p];
+        chi2 += v;
+      }
       loglike = -0.5 * chi2;
     } else {
       double sum = 0.0;
@@ -961,9 +963,9 @@ int c1d_launch_finalize(c1d_ctx* ctx, int64_t W, double* lnp, double* lnl_z, dou
   int use_full = ctx->cfg.has_full && !(flags & C1D_FLAG_ZMASK);
   int threads = 256;
   unsigned grid = (unsigned)((W + threads - 1) / threads);
-  const int npairs = (ctx->d.ldd / Q_TJ + 1) / 2;
+  const int ntj = ctx->d.ldd / Q_TJ;
   k_finalize<<<grid, threads, 0, s>>>(ctx->d, W, ctx->ws.status, ctx->ws.lnprior, ctx->ws.chi2z,
-                                      ctx->ws.chi2p, npairs, use_full, lnp, lnl_z, blobs, chi2, flags);
+                                      ctx->ws.chi2p, ntj, use_full, lnp, lnl_z, blobs, chi2, flags);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return C1D_OK;

@@ -15,6 +15,13 @@
 // written to a z-aligned buffer and a small tensor-core kernel (k_chi2z_dmma) forms d_z^T C_z^-1 d_z.
 // Small batches, and rebinning operators that are not of the two-bin form, fall back to the
 // warp-per-walker kernel in c1d_launch_stage3.
+//
+// Medium batches (fewer than ~4 waves of (z, 32 walkers) items) cut every redshift bin into up to 8
+// segments along k: a segment starts on a recurrence anchor (multiple of PL_ANCHOR fine points), owns the
+// data bins whose first fine point lies in it and runs on to the last fine point those bins need, so the
+// few points around a cut are evaluated by both neighbours.  Every model value and every bin sum is formed
+// by the same operations in the same order as in the uncut kernel: the results are bit-identical for any
+// number of segments (tests/test_gpu_parity.py), only the work items get finer.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,18 +38,30 @@ constexpr int PL_ANCHOR = 64;  // fine points between exact re-evaluations of th
 // U=4 x 384 2.78 ms, U=4 x 256 3.57 ms, and U=1 with 640 / 768 / 1024 threads (spilling) 2.96 / 3.23 /
 // 3.88 ms: warps beat unrolling, and 16 warps at the 128-register cap is the optimum.
 constexpr int PL_U = 1;
+// Cut the redshift bins until the batch holds PL_WAVES waves of items, and hand batches below PL_MIN_WAVES2 / 2
+// waves of the finest items to the warp-per-walker kernel.  Measured on B200 (C4, stage 3 in ms, warp-per-walker
+// kernel | 1, 2, 4, 8 segments): 2048 walkers 0.126 | 0.391 0.224 0.176 0.142; 4096: 0.223 | 0.405 0.274 0.233 0.207;
+// 8192: 0.413 | 0.466 0.385 0.349 0.349; 16 384: 0.778 | 0.744 0.628 0.610 0.622; 32 768: 1.519 | 1.177 1.129 1.120
+// 1.176; 65 536: 2.979 | 2.169 2.113 2.155 2.281 - the optimum sits at 10-20 waves of items.
+constexpr int PL_WAVES = 12;
+constexpr int PL_MIN_WAVES2 = 7;
 __host__ __device__ constexpr int pl_threads(int U) { return U == 1 ? 512 : (U == 2 ? 384 : 256); }
+
+constexpr int PL_NPART = 4;    // segment tables for 1, 2, 4 and 8 segments per redshift bin
+constexpr int PL_SEGW = 8;     // ints per segment record: z, i_lo, i_hi (fine points), j_lo, j_hi (data bins)
 
 struct P1dwState {
   int* d_ja;       // [nf] local index of the first data bin a fine point feeds
   double* d_wa;    // [nf] weight into bin ja
   double* d_wb;    // [nf] weight into bin ja + 1
+  int* d_seg[PL_NPART];  // [nseg][PL_SEGW]
+  int nseg[PL_NPART];
 };
 
 template <int NC, int KIND, int METAL, bool UNI, int U>
 __global__ void __launch_bounds__(pl_threads(U), 1)
-k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restrict__ rwa_g,
-                  const double* __restrict__ rwb_g, int64_t W, const int* __restrict__ status,
+k_fused_p1d_lanes(DevCtx c, const int* __restrict__ seg, int nseg, const int* __restrict__ rja_g,
+                  const double* __restrict__ rwa_g, const double* __restrict__ rwb_g, int64_t W, const int* __restrict__ status,
                   const double* __restrict__ amp, double* __restrict__ dvec, double* __restrict__ p_out,
                   double* __restrict__ dvz, int tzw, int nfz_max, int ndz_max) {
   constexpr int PL_WARPS = pl_threads(U) / 32;
@@ -58,40 +77,46 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restr
   if (threadIdx.x < 32) etab[threadIdx.x] = c_exp2_tab[threadIdx.x];  // visible after the first __syncthreads below
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-  // cost-balanced contiguous range of this CTA in units of fine points, items = (z, 32 walkers)
+  // cost-balanced contiguous range of this CTA in units of fine points, items = (segment, 32 walkers)
   const int64_t nitems = (W + 31) / 32;
   int64_t total = 0;
-  for (int z = 0; z < c.nz; ++z) total += nitems * (int64_t)(c.zoff_f[z + 1] - c.zoff_f[z]);
+  for (int sg = 0; sg < nseg; ++sg) total += nitems * (int64_t)(seg[sg * PL_SEGW + 2] - seg[sg * PL_SEGW + 1]);
   const int64_t t0 = total * blockIdx.x / gridDim.x, t1 = total * (blockIdx.x + 1) / gridDim.x;
 
   int64_t cum = 0;
-  for (int z = 0; z < c.nz; ++z) {
+  for (int sg = 0; sg < nseg; ++sg) {
+    const int z = seg[sg * PL_SEGW], i_lo = seg[sg * PL_SEGW + 1], np = seg[sg * PL_SEGW + 2] - i_lo;
+    const int j_lo = seg[sg * PL_SEGW + 3], j_hi = seg[sg * PL_SEGW + 4];
     const int f0 = c.zoff_f[z], nfz = c.zoff_f[z + 1] - f0;
     const int d0 = c.zoff_d[z], ndz = c.zoff_d[z + 1] - d0;
-    const int64_t cost = nfz;
+    const int64_t cost = np;
     const int64_t zend = cum + nitems * cost;
     const int64_t c_lo = (t0 > cum) ? (t0 - cum + cost - 1) / cost : 0;
     const int64_t c_hi = (t1 < zend) ? ((t1 > cum) ? (t1 - cum + cost - 1) / cost : 0) : nitems;
     cum = zend;
     if (c_lo >= c_hi) continue;
 
-    __syncthreads();  // previous z fully processed before its tables are overwritten
-    // the grid of this z is padded to a multiple of U with copies of its last point that carry no
+    __syncthreads();  // previous segment fully processed before its tables are overwritten
+    // the segment is padded to a multiple of U with copies of its last point that carry no
     // rebinning weight, so the loop body needs no bounds tests
-    const int nfp = (nfz + U - 1) / U * U;
+    const int nfp = (np + U - 1) / U * U;
+    const int g0 = f0 + i_lo;  // first fine point of the segment in the packed tables
     for (int t = threadIdx.x; t < C1D_NCOL * nfp; t += blockDim.x) {
       const int col = t / nfp, i = t - col * nfp;
-      tabw[i * C1D_NCOL + col] = c.tab[(size_t)col * c.nf + f0 + (i < nfz ? i : nfz - 1)];
+      tabw[i * C1D_NCOL + col] = c.tab[(size_t)col * c.nf + g0 + (i < np ? i : np - 1)];
     }
     for (int t = threadIdx.x; t < nfp; t += blockDim.x) {
-      const bool in = t < nfz;
-      rwa[t] = in ? rwa_g[f0 + t] : 0.0;
-      rwb[t] = in ? rwb_g[f0 + t] : 0.0;
-      rja[t] = rja_g[f0 + (in ? t : nfz - 1)];
+      const bool in = t < np;
+      rwa[t] = in ? rwa_g[g0 + t] : 0.0;
+      rwb[t] = in ? rwb_g[g0 + t] : 0.0;
+      rja[t] = rja_g[g0 + (in ? t : np - 1)];
     }
     for (int t = threadIdx.x; t < ndz; t += blockDim.x) dat[t] = c.data[d0 + t];
     __syncthreads();
-    const double dk = UNI ? (tabw[(nfz - 1) * C1D_NCOL + C1D_COL_K] - tabw[C1D_COL_K]) / (double)(nfz - 1) : 0.0;
+    // spacing of the whole bin's grid (the same value in every segment)
+    const double* kcol = c.tab + (size_t)C1D_COL_K * c.nf + f0;
+    const double dk = UNI ? (kcol[nfz - 1] - kcol[0]) / (double)(nfz - 1) : 0.0;
+    const int jc0 = (i_lo == 0) ? 0 : rja[0];  // bins before j_lo are accumulated but never stored
 
     for (int64_t item = c_lo + warp; item < c_hi; item += PL_WARPS) {
       const int64_t w = item * 32 + lane;
@@ -104,7 +129,7 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restr
       if (!__any_sync(0xffffffffu, ok)) {
         // rejected walkers carry no model (the reference returns None)
         if (live)
-          for (int j = 0; j < ndz; ++j) {
+          for (int j = j_lo; j < j_hi; ++j) {
             if (dv) dv[j] = 0.0;
             if (dzp) dzp[j] = 0.0;
             if (po) po[j] = qnan;
@@ -144,11 +169,11 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restr
         R2 = exp_poly(-s2 * dk);
         gq = exp_poly(-2.0 * sa2 * (dk * dk));
       }
-      int jc = 0;
+      int jc = jc0;
       double acc0 = 0.0, acc1 = 0.0;
       auto flush = [&](int j, double m) {
         const double dj = dat[j] - m;
-        if (live) {
+        if (live && j >= j_lo) {
           if (dv) dv[j] = ok ? dj : 0.0;
           if (dzp) dzp[j] = ok ? dj : 0.0;
           if (po) po[j] = ok ? m : qnan;
@@ -230,7 +255,7 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ rja_g, const double* __restr
           acc1 = fma(rwb[i0 + u], P[u], acc1);
         }
       }
-      while (jc < ndz) {
+      while (jc < j_hi) {
         flush(jc, acc0);
         acc0 = acc1;
         acc1 = 0.0;
@@ -251,6 +276,7 @@ void c1d_p1dw_destroy(c1d_ctx* ctx) {
   cudaFree(st->d_ja);
   cudaFree(st->d_wa);
   cudaFree(st->d_wb);
+  for (int q = 0; q < PL_NPART; ++q) cudaFree(st->d_seg[q]);
   delete st;
   ctx->p1dw_state = nullptr;
 }
@@ -269,6 +295,7 @@ int c1d_p1dw_prepare(c1d_ctx* ctx) {
   C1D_CUDA(ctx, cudaMemcpy(wg.data(), ctx->dev[C1D_F_RB_WGT], wg.size() * sizeof(double), cudaMemcpyDeviceToHost));
   std::vector<int> ja(c.nf, 0);
   std::vector<double> wa(c.nf, 0.0), wb(c.nf, 0.0);
+  std::vector<int> segs[PL_NPART];
   for (int z = 0; z < c.nz; ++z) {
     const int f0 = zf[z], nfz = zf[z + 1] - f0, d0 = zd[z], ndz = zd[z + 1] - d0;
     std::vector<int> first(nfz, -1), count(nfz, 0);
@@ -294,6 +321,43 @@ int c1d_p1dw_prepare(c1d_ctx* ctx) {
       last = first[i];
       ja[f0 + i] = first[i];
     }
+    // segments of this z for 1, 2, 4, 8 cuts: first and last fine point that feed each data bin
+    std::vector<int> bfirst(ndz, nfz), blast(ndz, -1);
+    for (int i = 0; i < nfz; ++i) {
+      const int j = ja[f0 + i];
+      if (wa[f0 + i] != 0.0 && j < ndz) {
+        if (i < bfirst[j]) bfirst[j] = i;
+        blast[j] = i;
+      }
+      if (wb[f0 + i] != 0.0 && j + 1 < ndz) {
+        if (i < bfirst[j + 1]) bfirst[j + 1] = i;
+        blast[j + 1] = i;
+      }
+    }
+    // a bin no fine point feeds goes with the next bin that is fed
+    for (int j = ndz - 2; j >= 0; --j)
+      if (blast[j] < 0) bfirst[j] = bfirst[j + 1];
+    const int nblk = (nfz + PL_ANCHOR - 1) / PL_ANCHOR;
+    for (int q = 0; q < PL_NPART; ++q) {
+      const int want = 1 << q;
+      const int P = want < nblk ? want : nblk;
+      std::vector<int> jl(P + 1, ndz), il(P + 1, nfz);
+      for (int p = 0; p < P; ++p) {
+        il[p] = PL_ANCHOR * (int)(((long long)p * nblk) / P);
+        int j = 0;
+        while (j < ndz && bfirst[j] < il[p]) ++j;
+        jl[p] = (p == 0) ? 0 : j;
+      }
+      for (int p = 0; p < P; ++p) {
+        if (jl[p + 1] <= jl[p]) continue;  // owns no bin: its points are covered by the neighbours
+        int ih = il[p] + 1;
+        for (int j = jl[p]; j < jl[p + 1]; ++j)
+          if (blast[j] + 1 > ih) ih = blast[j] + 1;
+        if (p == P - 1 || jl[p + 1] >= ndz) ih = nfz;
+        const int rec[PL_SEGW] = {z, il[p], ih, jl[p], jl[p + 1], 0, 0, 0};
+        segs[q].insert(segs[q].end(), rec, rec + PL_SEGW);
+      }
+    }
   }
   P1dwState* s = new P1dwState();
   memset(s, 0, sizeof(*s));
@@ -304,6 +368,11 @@ int c1d_p1dw_prepare(c1d_ctx* ctx) {
   C1D_CUDA(ctx, cudaMemcpy(s->d_ja, ja.data(), c.nf * sizeof(int), cudaMemcpyHostToDevice));
   C1D_CUDA(ctx, cudaMemcpy(s->d_wa, wa.data(), c.nf * sizeof(double), cudaMemcpyHostToDevice));
   C1D_CUDA(ctx, cudaMemcpy(s->d_wb, wb.data(), c.nf * sizeof(double), cudaMemcpyHostToDevice));
+  for (int q = 0; q < PL_NPART; ++q) {
+    s->nseg[q] = (int)(segs[q].size() / PL_SEGW);
+    C1D_CUDA(ctx, cudaMalloc(&s->d_seg[q], segs[q].size() * sizeof(int)));
+    C1D_CUDA(ctx, cudaMemcpy(s->d_seg[q], segs[q].data(), segs[q].size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   return C1D_OK;
 }
 
@@ -321,8 +390,8 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int w
   const int nfp_max = (nfz_max + 3) & ~3;
   const size_t smem = ((size_t)nfp_max * (C1D_NCOL + 2) + ndz_max + 32) * sizeof(double) + (size_t)nfp_max * sizeof(int) + 16;
   if (smem > 227 * 1024) return 0;
-  typedef void (*kern_t)(DevCtx, const int*, const double*, const double*, int64_t, const int*, const double*, double*, double*, double*, int,
-                         int, int);
+  typedef void (*kern_t)(DevCtx, const int*, int, const int*, const double*, const double*, int64_t, const int*, const double*, double*,
+                         double*, double*, int, int, int);
   kern_t kern = nullptr;
   const int nc = (cfg.nc >= 5 && cfg.nc <= 7) ? cfg.nc : 0;
   const int sel = ((nc ? nc - 4 : 0) << 3) | (cfg.emu_kind << 2) | (cfg.metal_model << 1) | (cfg.uniform_k ? 1 : 0);
@@ -347,10 +416,19 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int w
   if (!kern) return 0;
   C1D_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = pl_threads(U), warps = threads / 32;
-  const int64_t items = ((W + 31) / 32) * cfg.nz;
-  // a warp-item is 32 walkers long: small batches do not fill the machine in this form (measured
-  // crossover on C4: between 4096 and 8192 walkers), the warp-per-walker kernel takes them
-  if (items < (int64_t)ctx->num_sms * warps && !force_lanes) return 0;
+  const int64_t zitems = ((W + 31) / 32) * cfg.nz;
+  // a warp-item is 32 walkers long; batches below PL_WAVES waves of (z, 32 walkers) items cut the redshift
+  // bins into 2, 4 or 8 segments (bit-identical results, finer items), and below PL_MIN_WAVES2 / 2 waves of
+  // the finest items the warp-per-walker kernel takes over (C1D_P1D_PARTS=1|2|4|8 forces the cut)
+  const int64_t wave = (int64_t)ctx->num_sms * warps;
+  int q = 0;
+  while (q + 1 < PL_NPART && (zitems << q) < PL_WAVES * wave) ++q;
+  if (const char* e = getenv("C1D_P1D_PARTS")) {
+    const int v = atoi(e);
+    q = v >= 8 ? 3 : (v >= 4 ? 2 : (v >= 2 ? 1 : 0));
+  }
+  const int64_t items = ((W + 31) / 32) * st->nseg[q];
+  if (2 * items < PL_MIN_WAVES2 * wave && !force_lanes) return 0;
   int64_t grid = (int64_t)ctx->num_sms;
   if (grid > (items + warps - 1) / warps) grid = (items + warps - 1) / warps;
   if (grid < 1) grid = 1;
@@ -365,7 +443,7 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int w
     }
     dvz = ctx->ws.dvz;
   }
-  kern<<<(unsigned)grid, threads, smem, s>>>(ctx->d, st->d_ja, st->d_wa, st->d_wb, W, ctx->ws.status, ctx->ws.amp, dvec, p_out,
+  kern<<<(unsigned)grid, threads, smem, s>>>(ctx->d, st->d_seg[q], st->nseg[q], st->d_ja, st->d_wa, st->d_wb, W, ctx->ws.status, ctx->ws.amp, dvec, p_out,
                                                 dvz, ctx->tzw, nfp_max, ndz_max);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());

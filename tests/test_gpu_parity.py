@@ -203,10 +203,10 @@ def test_full_size_properties():
             assert torch.equal(like.log_prob_batch(xd[:4096][perm]), lnp_all[:4096][perm])
         finally:
             del os.environ["C1D_P1D_LAYOUT"]
-    big = like.log_prob_batch(xd)           # walker-per-lane form
-    small = like.log_prob_batch(xd[:1000])  # warp-per-walker form
-    fin = torch.isfinite(big[:1000]) & (big[:1000] > -1e99)
-    assert float(((big[:1000] - small)[fin].abs() / big[:1000][fin].abs().clamp(min=1.0)).max()) < 1e-10
+    big = like.log_prob_batch(xd)          # walker-per-lane form
+    small = like.log_prob_batch(xd[:200])  # warp-per-walker form
+    fin = torch.isfinite(big[:200]) & (big[:200] > -1e99)
+    assert float(((big[:200] - small)[fin].abs() / big[:200][fin].abs().clamp(min=1.0)).max()) < 1e-10
     like.close()
     # (d) noise-free mock: chi2 at the truth is zero (mock generation round trip)
     like = _like(spec)
@@ -316,6 +316,37 @@ def test_edge_batches(golden):
     np.testing.assert_array_equal(like.log_prob_batch(x32), like.log_prob_batch(x32.astype(np.float64)))
     # scalar API on a rejected point keeps the reference's conventions
     assert ora.log_prob(bad[0].copy()) == like.log_prob(bad[0].copy()) == like.min_log_like
+    like.close()
+
+
+@pytest.mark.parametrize("name", ["c1", "c3", "c4"])
+def test_stage3_segments_are_bit_identical(monkeypatch, name):
+    """medium batches cut every redshift bin of the walker-per-lane stage 3 into 2, 4 or 8 k-segments
+    (C1D_P1D_PARTS forces the cut): log-posteriors, per-z log-likelihoods and the model P1D must not
+    change by a single bit, rejected and ragged rows included"""
+    import torch
+
+    from cup1d_b200 import synth
+
+    spec = _synthetic(name)
+    like = _like(spec)
+    x = np.concatenate([synth.walkers_sweep(spec, 1500, seed=21, frac_out=0.02), synth.walkers_ball(spec, 77, seed=3)])
+    x[40:72] = 1.5  # one whole 32-walker item outside the cube
+    xd = torch.as_tensor(x, device="cuda:0")
+    monkeypatch.setenv("C1D_P1D_LAYOUT", "lanes")
+    ref = None
+    for parts in (1, 2, 4, 8):
+        monkeypatch.setenv("C1D_P1D_PARTS", str(parts))
+        lnp, blobs = like.log_prob_and_blobs_batch(xd)
+        lnl, lnl_z = like.get_log_like_batch(xd)
+        p = like.get_p1d_kms_batch(xd)
+        out = [t.clone() for t in (lnp, blobs, lnl, lnl_z, p)]
+        if ref is None:
+            ref = out
+            assert int(torch.isfinite(lnl).sum()) > 1000
+            continue
+        for a, b in zip(ref, out):
+            assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)) and torch.equal(torch.isnan(a), torch.isnan(b))
     like.close()
 
 
