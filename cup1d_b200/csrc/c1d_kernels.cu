@@ -29,7 +29,8 @@ __device__ __forceinline__ double param_value(const DevCtx& c, const double* xw,
 // One thread per (walker, z): blockIdx.y is the redshift bin.  The z = 0 thread of a walker also does
 // the walker-level work (cube test, Gaussian prior, blobs, star-prior box).  The status word is zeroed
 // before the launch and combined with atomicMax (out of cube > rejected > ok).
-__global__ void __launch_bounds__(128)
+#define S1_THREADS 128
+__global__ void __launch_bounds__(S1_THREADS)
 k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ status,
          double* __restrict__ lnprior, double* __restrict__ blobs, double* __restrict__ emu_in,
          double* __restrict__ amp, uint32_t flags) {
@@ -53,8 +54,15 @@ k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ st
     s_ps[t] = idx >= 0 ? c.pscale[idx] : 0.0;
   }
   __syncthreads();
-  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= W) return;
+  // the per-(walker, z) records of a block are contiguous in memory ([z][walker][slot]): they are
+  // assembled in shared memory and written as whole sectors (one thread's 208-byte record scattered
+  // as 8-byte stores costs read-modify-write traffic in the memory system: 445 MB against 224 MB)
+  __shared__ double s_rec[S1_THREADS * (C1D_NAMP + 1)];
+  __shared__ double s_emu[S1_THREADS * (C1D_MAX_EMU + 1)];
+  const int64_t wb0 = (int64_t)blockIdx.x * S1_THREADS;
+  const int64_t w = wb0 + threadIdx.x;
+  const bool live = w < W;
+  if (live) {
   const double* xw = x + w * c.ndim;
 
   // primordial-power rescaling (lya_theory.py:281-307, 542-580)
@@ -149,10 +157,12 @@ k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ st
         if (!(val <= c.hull_tol)) { rej = true; break; }
       }
     }
-    double* eo = emu_in + ((int64_t)z * W + w) * C1D_MAX_EMU;
+    double* eo = s_emu + threadIdx.x * (C1D_MAX_EMU + 1);
     for (int j = 0; j < C1D_MAX_EMU; ++j) eo[j] = ev[j];
 
-    double* a = amp + ((int64_t)z * W + w) * C1D_NAMP;
+    double* a = s_rec + threadIdx.x * (C1D_NAMP + 1);
+    for (int j = 0; j < A_S3; ++j) a[j] = 0.0;  // coefficient slots: stage 2 fills them
+    a[C1D_NAMP - 1] = 0.0;
     double om = 1.0 - mF;
     a[A_S3] = q[C1D_Q_S_SIIII];
     a[A_S2] = q[C1D_Q_S_SIII];
@@ -186,11 +196,24 @@ k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ st
     a[A_AGN] = (q[C1D_Q_AGN_CONST] > 0.0) ? q[C1D_Q_AGN] : 0.0;  // AGN_model.py:81-91
   }
   if (rej) atomicMax(status + w, (int)ST_REJECTED);
+  }  // live
+  __syncthreads();
+  const int nrec = (int)((W - wb0 < S1_THREADS) ? (W - wb0) : S1_THREADS);
+  double* ga = amp + ((int64_t)z * W + wb0) * C1D_NAMP;
+  for (int t = threadIdx.x; t < nrec * C1D_NAMP; t += S1_THREADS) {
+    const int r = t / C1D_NAMP;
+    ga[t] = s_rec[r * (C1D_NAMP + 1) + (t - r * C1D_NAMP)];
+  }
+  double* ge = emu_in + ((int64_t)z * W + wb0) * C1D_MAX_EMU;
+  for (int t = threadIdx.x; t < nrec * C1D_MAX_EMU; t += S1_THREADS) {
+    const int r = t / C1D_MAX_EMU;
+    ge[t] = s_emu[r * (C1D_MAX_EMU + 1) + (t - r * C1D_MAX_EMU)];
+  }
 }
 
 int c1d_launch_stage1(c1d_ctx* ctx, const double* x, int64_t W, double* blobs_out, uint32_t flags,
                       cudaStream_t s) {
-  int threads = 128;
+  int threads = S1_THREADS;
   int64_t blocks = (W + threads - 1) / threads;
   C1D_CUDA(ctx, cudaMemsetAsync(ctx->ws.status, 0, (size_t)W * sizeof(int), s));
   const size_t smem1 = (size_t)C1D_NQ * ctx->cfg.ell_width * (3 * sizeof(double) + sizeof(int));
