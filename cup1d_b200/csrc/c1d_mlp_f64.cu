@@ -245,6 +245,8 @@ __device__ __forceinline__ void m64_layer(const M64Plan& p, int l, int& s, uint3
 // block size (a 144- or 152-register build fails to launch); register double buffering of the fragments
 // spills at 128 and was dropped.  Also measured: no streamer warp (the last warp out of a slab buffer
 // starts its refill, 12 warps at 168 registers): 4.96 ms against 4.78 ms, 5.05 ms with double buffering.
+// A non-blocking mbarrier.test_wait for the next slab issued two k-steps before the end of the current one
+// (to skip the ~100-cycle blocking poll): 5.01 ms - the extra live state spills in the DMMA loop.
 template <int G, int NBUF>
 __global__ void __launch_bounds__(M64Geom<G>::THREADS, 1)
 k_mlp_f64(M64Plan p, const double* __restrict__ emu_in, const double* __restrict__ emu_lo,
