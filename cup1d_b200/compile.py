@@ -69,7 +69,15 @@ def family_z_weights(fam, zs):
         nodes = np.asarray(fam["znodes"], dtype=float)
         if len(nodes) != n:
             raise ValueError("znodes / coefficient count mismatch")
-        for iz, z in enumerate(zs):
+        if n > 1 and np.any(np.diff(nodes) <= 0):
+            # repeated nodes (a one-redshift data set): whatever the reference's routine returns for them is
+            # linear in the coefficients, so its response to unit vectors gives the weights
+            if ztype == "interp_spl":
+                raise ValueError("interp_spl needs strictly increasing znodes (scipy.interpolate.make_interp_spline)")
+            for j in range(n):
+                Wz[:, j] = np.interp(zs, nodes, np.eye(n)[j])
+            nodes = None
+        for iz, z in enumerate(zs if nodes is not None else []):
             if n == 1:
                 Wz[iz, 0] = 1.0
                 continue
@@ -114,6 +122,9 @@ def compile_z_functions(spec):
             fam = dict(src)
             fam.update(ztype="pivot", znodes=np.zeros(0), coeffs=np.asarray(src["coeffs"], dtype=float)[-1:],
                        param_idx=np.asarray(src["param_idx"])[-1:], zmax=np.nan, otype="exp")
+        elif q == "HCD_const" and spec["cont"]["hcd_model"] != "rogers":
+            # HCD_BOSS has the one amplitude HCD_damp1 (hcd_boss.py:66-91): a stray HCD_const family has no effect
+            fam = _neutral_family(0.0, "const")
         elif q in fams:
             fam = fams[q]
         elif q in ("tau_eff", "sigT_kms", "gamma", "kF_kms"):

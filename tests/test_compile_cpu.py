@@ -71,3 +71,21 @@ def test_synthetic_c3_with_agn_compiles_to_the_oracle():
     p_with = np.concatenate(ora.get_p1d_kms(values=x[0])[0])
     p_without = np.concatenate(OracleLikelihood(spec2).get_p1d_kms(values=x[0])[0])
     assert np.max(np.abs(p_with / p_without - 1)) > 1e-4
+
+
+def test_repeated_nodes_follow_np_interp():
+    """a one-redshift data set gives interp_lin families with repeated nodes: the compiled weights
+    must reproduce what np.interp (the reference's routine, base_igm.py:253-254) returns for them"""
+    import numpy as np
+
+    from cup1d_b200.compile import family_z_weights
+    from oracle.model import family_value
+
+    zs = np.array([2.2])
+    for nodes in ([2.2, 2.2], [2.2, 2.2, 2.2, 2.2], [2.0, 2.2, 2.2, 3.0]):
+        n = len(nodes)
+        fam = {"ztype": "interp_lin", "otype": "const", "znodes": np.array(nodes), "coeffs": np.arange(1.0, n + 1.0),
+               "param_idx": np.full(n, -1), "z0": 3.0, "null": np.nan, "zmax": np.nan}
+        Wz, forced = family_z_weights(fam, zs)
+        assert not forced.any()
+        np.testing.assert_allclose(Wz @ fam["coeffs"], family_value(fam, zs, np.zeros(0)), rtol=0, atol=1e-15)
