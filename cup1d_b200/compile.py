@@ -67,9 +67,15 @@ def family_z_weights(fam, zs):
             Wz[:, j] = xz ** (n - 1 - j)
     elif ztype in ("interp_lin", "interp_spl"):
         nodes = np.asarray(fam["znodes"], dtype=float)
-        if len(nodes) != n:
+        if len(nodes) == 0 and n == 1:
+            # a family switched off in the baseline (n_<name> = 0: no nodes, one fixed coefficient, e.g. R_coeff
+            # under name_variation="no_contaminants", input_pipeline.py:1096-1098): the reference never
+            # evaluates it, the constant stands in
+            Wz[:, 0] = 1.0
+            nodes = None
+        elif len(nodes) != n:
             raise ValueError("znodes / coefficient count mismatch")
-        if n > 1 and np.any(np.diff(nodes) <= 0):
+        if nodes is not None and n > 1 and np.any(np.diff(nodes) <= 0):
             # repeated nodes (a one-redshift data set): whatever the reference's routine returns for them is
             # linear in the coefficients, so its response to unit vectors gives the weights
             if ztype == "interp_spl":
@@ -122,6 +128,9 @@ def compile_z_functions(spec):
             fam = dict(src)
             fam.update(ztype="pivot", znodes=np.zeros(0), coeffs=np.asarray(src["coeffs"], dtype=float)[-1:],
                        param_idx=np.asarray(src["param_idx"])[-1:], zmax=np.nan, otype="exp")
+        elif q == "R_coeff" and not spec["cont"]["apply_resolution"]:
+            # the resolution term is applied only if some R_coeff is free (lya_theory.py:712-722)
+            fam = _neutral_family(0.0, "const")
         elif q == "HCD_const" and spec["cont"]["hcd_model"] != "rogers":
             # HCD_BOSS has the one amplitude HCD_damp1 (hcd_boss.py:66-91): a stray HCD_const family has no effect
             fam = _neutral_family(0.0, "const")

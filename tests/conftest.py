@@ -17,6 +17,15 @@ GOLDEN_NAMES = [
     "hcd_const",
     "global_all",
     "chab2019_real",  # the reference's measured Chabanier et al. (2019) data set and covariance
+    # further Args.set_baseline variations (tools/make_golden.py:VARIATIONS)
+    "var_metal_trad",
+    "var_no_contaminants",
+    "var_gaikwad21",
+    "var_turner24",
+    "var_lls_nz4",
+    "var_zmin",
+    "var_global_igm",
+    "var_at_a_time",
 ]
 
 

@@ -195,6 +195,25 @@ CONFIGS = {
 }
 
 
+# further baselines of Args.set_baseline (input_pipeline.py:830-1112, 685-766, 1114-1180): parameter sets and
+# node layouts that differ structurally from the ones above (families without free parameters, one-node
+# pivots, four-node LLS, no contaminants / no resolution, IGM-only and one-z-at-a-time fits)
+VARIATIONS = {
+    "var_metal_trad": ("global_opt", "metal_trad"),
+    "var_no_contaminants": ("global_opt", "no_contaminants"),
+    "var_gaikwad21": ("global_opt", "Gaikwad21"),
+    "var_turner24": ("global_opt", "Turner24"),
+    "var_lls_nz4": ("global_opt", "LLS_nz4"),
+    "var_zmin": ("global_opt", "zmin"),
+    "var_global_igm": ("global_igm", None),
+    "var_at_a_time": ("at_a_time_global", None),
+}
+for _i, (_nm, (_ft, _var)) in enumerate(VARIATIONS.items()):
+    CONFIGS[_nm] = (lambda nm=_nm, ft=_ft, var=_var, i=_i: make(
+        nm, RefMLPEmulator(small_nn(40 + i, "mpg"), "synthetic_mpg_nn", "mpg"), "dr1c", nz=5, rebin_k=2, seed=900 + 10 * i,
+        fit_type=ft, name_variation=var, use_ic=False, n=(8, 8, 2), width=0.1))
+
+
 def make_real_chabanier(name="chab2019_real", nz=11, rebin_k=2, seed=800, n=(24, 20, 4)):
     """The reference's own measured data set: Chabanier et al. (2019) P1D, statistical + systematic
     covariance with its correlation matrices, parsed by the reference's read_from_file
