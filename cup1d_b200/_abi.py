@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 FLAG_ZMASK = 1
 FLAG_NO_HULL = 2
 FLAG_EMU_TC = 4
+FLAG_NO_CUBE = 8
 
 # every symbol include/cup1d_b200.h declares
 SYMBOLS = (

@@ -87,7 +87,7 @@ k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ st
         lp += d * d * c.prior_w[i];
       }
     }
-    if (out) {
+    if (out && !(flags & C1D_FLAG_NO_CUBE)) {
       atomicMax(status + w, (int)ST_OUT_OF_CUBE);
       lnprior[w] = 0.0;
       double qnan = __longlong_as_double(0x7ff8000000000000LL);

@@ -26,12 +26,13 @@ import torch
 from . import _abi
 from .compile import compile_spec
 from .spec import spec_from_likelihood, spec_sizes
+from .theory import B200Theory
 
 BLOB_NAMES = ("Delta2_star", "n_star", "alpha_star", "f_star", "g_star", "H0")
 
 
 class B200Likelihood(object):
-    def __init__(self, like, device=None, emulator_precision="fp64"):
+    def __init__(self, like, device=None, emulator_precision="fp64", _with_theory=True):
         """like: a reference ``Likelihood`` (any object with its attributes) or
         a model spec dict.  emulator_precision: "fp64" (CUDA cores, exact
         parity with an fp64 evaluation of the weights) or "3xtf32"
@@ -57,6 +58,8 @@ class B200Likelihood(object):
         self.zs = np.asarray(self.spec["zs"], dtype=float)
         self.zoff_d = fields["ZOFF_D"].astype(int)
         self._zmask_key = None
+        # Theory.get_p1d_kms on other (z, k) grids (derived contexts, built on demand)
+        self.theory = B200Theory(self) if _with_theory else None
         self.set_emulator_precision(emulator_precision)
         self._set_logdet()
 
@@ -126,10 +129,12 @@ class B200Likelihood(object):
         return self.fid_cube.copy()
 
     # ------------------------------------------------------------------
-    def _flags(self, zmask=None, apply_hull=True):
+    def _flags(self, zmask=None, apply_hull=True, cube_test=True):
         flags = self._base_flags
         if not apply_hull:
             flags |= _abi.FLAG_NO_HULL
+        if not cube_test:
+            flags |= _abi.FLAG_NO_CUBE
         if zmask is not None:
             zmask = np.atleast_1d(np.asarray(zmask, dtype=float))
             sel = np.array([int(np.any(np.abs(zmask - z) < 1e-3)) for z in self.zs], dtype=np.int32)
@@ -152,7 +157,7 @@ class B200Likelihood(object):
         x = x.to(device=self.device, dtype=torch.float64).contiguous()
         return x, was_numpy, was_1d
 
-    def _evaluate(self, values, want_z=False, want_chi2=False, zmask=None, apply_hull=True):
+    def _evaluate(self, values, want_z=False, want_chi2=False, zmask=None, apply_hull=True, cube_test=True):
         x, was_numpy, _ = self._as_device(values)
         W = x.shape[0]
         with torch.cuda.device(self.device):
@@ -165,7 +170,7 @@ class B200Likelihood(object):
                 x.data_ptr(), W, lnp.data_ptr(),
                 lnl_z.data_ptr() if want_z else None, blobs.data_ptr(),
                 chi2.data_ptr() if want_chi2 else None,
-                self._flags(zmask, apply_hull), stream,
+                self._flags(zmask, apply_hull, cube_test), stream,
             )
         return lnp, blobs, lnl_z, chi2, was_numpy
 
@@ -229,10 +234,17 @@ class B200Likelihood(object):
         _, _, _, chi2, was_numpy = self._evaluate(values, want_chi2=True, zmask=zmask)
         return self._out(chi2, was_numpy)
 
-    def get_p1d_kms_batch(self, values, apply_hull=True, return_emu_params=False):
+    def blobs_batch(self, values):
+        """blobs[W, 6] (Theory.get_blob_fixed_background, lya_theory.py:536-584) without the unit-cube
+        test; zeros where the star-prior box or the hulls reject the point"""
+        _, blobs, _, _, was_numpy = self._evaluate(values, cube_test=False)
+        return self._out(blobs, was_numpy)
+
+    def get_p1d_kms_batch(self, values, apply_hull=True, return_emu_params=False, cube_test=True):
         """P[W, N_d]: the rebinned model concatenated over z in the order of
         ``data.full_Pk_kms`` (likelihood.py:957); NaN rows where the reference
-        returns None.  With return_emu_params also emu[W, Nz, n_emu]."""
+        returns None (and, with ``cube_test``, outside the unit cube).  With
+        return_emu_params also emu[W, Nz, n_emu]."""
         x, was_numpy, _ = self._as_device(values)
         W = x.shape[0]
         with torch.cuda.device(self.device):
@@ -240,7 +252,7 @@ class B200Likelihood(object):
             emu = torch.empty((W, self.nz, self.n_emu), dtype=torch.float64, device=self.device) if return_emu_params else None
             stream = torch.cuda.current_stream(self.device).cuda_stream
             self.ctx.p1d_batch(x.data_ptr(), W, p.data_ptr(), emu.data_ptr() if return_emu_params else None,
-                               self._flags(None, apply_hull), stream)
+                               self._flags(None, apply_hull, cube_test), stream)
         if return_emu_params:
             return self._out(p, was_numpy), self._out(emu, was_numpy)
         return self._out(p, was_numpy)
@@ -286,28 +298,50 @@ class B200Likelihood(object):
 
     # ---- scalar API with the reference's conventions ------------------
     def _values_or_fid(self, values):
+        """values=None means like_params=[] in the reference (likelihood.py:749-753): every model at the
+        coefficients it holds and no resolution term.  On the likelihood's own context that is the same
+        evaluation whenever the held R_coeff coefficients are zero (the term is then exactly 1)."""
         if values is None:
-            if (self.fid_cube > 1).any() or (self.fid_cube < 0).any():
-                raise NotImplementedError("values=None with a fiducial point outside the unit cube")
-            return self.fid_cube.copy()
+            x, _ = self.theory.cube_from_like_params([])
+            names = self.free_param_names
+            held_res = [self.theory._held[i] for i, n in enumerate(names) if n.startswith("R_coeff")]
+            if self.spec["cont"]["apply_resolution"] and np.any(np.asarray(held_res) != 0.0):
+                raise NotImplementedError("values=None with non-zero R_coeff coefficients held by the resolution model")
+            if (x > 1).any() or (x < 0).any():
+                raise NotImplementedError("values=None with model coefficients outside the priors")
+            return x
         return np.asarray(values, dtype=float)
 
     def get_p1d_kms(self, zs=None, _k_kms=None, values=None, return_covar=False, return_blob=False,
                     return_emu_params=False, apply_hull=True, remove=None):
-        """likelihood.py:722-785 on the data redshifts and k bins"""
-        if zs is not None or _k_kms is not None or remove is not None or return_covar:
-            raise NotImplementedError("only the data grid, all contaminant terms and no emulator covariance")
-        v = self._values_or_fid(values)
-        if values is not None and ((v > 1).any() or (v < 0).any()):
-            # the reference evaluates outside the cube here; the device path rejects
-            raise NotImplementedError("get_p1d_kms outside the unit cube")
-        p, emu = self.get_p1d_kms_batch(v[None, :], apply_hull=apply_hull, return_emu_params=True)
+        """likelihood.py:722-785.  As in the reference: ``values=None`` evaluates the models at the
+        coefficients they hold, without the resolution term (``like_params=[]``, lya_theory.py:712-722);
+        with rebinning the k grid is always the rebinning grid of the nearest data redshift and
+        ``_k_kms`` is ignored (:741-747); there is no unit-cube test here.  ``None`` when the priors reject
+        the point, otherwise ``[p1ds(, blob)(, emu_call)]``."""
+        if remove is not None or return_covar:
+            raise NotImplementedError("remove and return_covar are not on the device path")
+        rebinned = self.spec["rebin"] is not None
+        if zs is None:
+            iz = list(range(self.nz))
+        else:
+            iz = [int(np.argmin(np.abs(z - self.zs))) for z in np.atleast_1d(np.asarray(zs, dtype=float))]
+        custom_k = (_k_kms is not None) and not rebinned
+        if values is None:
+            x, apply_res = self.theory.cube_from_like_params([])
+        else:
+            x, apply_res = np.asarray(values, dtype=float), bool(self.spec["cont"]["apply_resolution"])
+        if values is not None and not custom_k and iz == list(range(self.nz)):
+            sub = self
+        else:
+            k_list = self.theory._k_list(_k_kms, len(iz)) if custom_k else None
+            sub = self.theory._context(iz, k_list, apply_res)
+        p, emu = sub.get_p1d_kms_batch(x[None, :], apply_hull=apply_hull, return_emu_params=True, cube_test=False)
         if np.isnan(p[0]).all():
             return None
-        out = [[p[0, self.zoff_d[iz] : self.zoff_d[iz + 1]].copy() for iz in range(self.nz)]]
+        out = [[p[0, sub.zoff_d[i] : sub.zoff_d[i + 1]].copy() for i in range(len(iz))]]
         if return_blob:
-            _, blobs = self.log_prob_and_blobs_batch(v[None, :])
-            out.append(tuple(blobs[0]))
+            out.append(tuple(sub.blobs_batch(x[None, :])[0]))
         if return_emu_params:
             names = self.spec["emulator"]["emu_params"]
             out.append({n: emu[0, :, j].copy() for j, n in enumerate(names)})
@@ -386,4 +420,6 @@ class B200Likelihood(object):
 
     # ------------------------------------------------------------------
     def close(self):
+        if self.theory is not None:
+            self.theory.close()
         self.ctx.close()

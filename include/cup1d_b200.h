@@ -159,6 +159,7 @@ typedef struct c1d_ctx c1d_ctx;
 /* evaluation flags */
 #define C1D_FLAG_ZMASK 1u     /* use the uploaded C1D_F_ZMASK: per-z chi2 of the selected bins only (likelihood.py:844-863, 953-954) */
 #define C1D_FLAG_NO_HULL 2u   /* apply_hull=False (likelihood.py:730) */
+#define C1D_FLAG_NO_CUBE 8u   /* no unit-cube test: Theory.get_p1d_kms evaluates any parameter values (lya_theory.py:610-814; the test lives in Likelihood, likelihood.py:989-994) */
 #define C1D_FLAG_EMU_TC 4u    /* emulator layers on tcgen05 tensor cores (3xTF32) instead of fp64 CUDA cores */
 
 int c1d_abi_version(void);

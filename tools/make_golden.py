@@ -269,6 +269,76 @@ def make_agn_kat():
     print("agn_kat          %d cases" % len(cases))
 
 
+def make_theory_kat(name, emu, grid, nz, rebin_k, seed, **kw):
+    """Theory.get_p1d_kms (lya_theory.py:610-814) and Likelihood.get_p1d_kms (likelihood.py:722-785) of the
+    reference off the likelihood's own grid: a redshift subset, a custom k grid, full / partial / empty
+    like_params (absent parameters keep the models' coefficients, the resolution term needs an R_coeff
+    parameter in the list), points outside the unit cube, values=None."""
+    zs = np.round(2.2 + 0.2 * np.arange(nz), 10)
+    ks, kmins, kmaxs = grids(grid, nz)
+    nd = sum(len(k) for k in ks)
+
+    def data_ns(Pk_full, cov_full):
+        Pk, cov, off = [], [], 0
+        for k in ks:
+            Pk.append(Pk_full[off : off + len(k)])
+            cov.append(cov_full[off : off + len(k), off : off + len(k)])
+            off += len(k)
+        return rh.make_data_namespace(zs, ks, kmins, kmaxs, Pk, cov, [0.8 * c for c in cov])
+
+    rng = np.random.default_rng(seed)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        like, args = rh.build_reference_likelihood(emu, data_ns(np.ones(nd), np.eye(nd) * 0.01), rebin_k=rebin_k, **kw)
+        x = walkers(like, 4, 4, 0, seed + 2, width=0.08)
+        x = np.concatenate([x, x[:2]])
+        x[-2, 3] = 1.07   # outside the unit cube: Theory has no cube test
+        x[-1, 0] = -0.04
+        izs = [1, 3, 2] if nz > 3 else [0]
+        zsub = zs[izs]
+        kc = [np.linspace(0.0012 + 0.0003 * j, 0.035 - 0.002 * j, 23 + 5 * j) for j in range(len(izs))]
+        ndc = sum(len(k) for k in kc)
+        out = {"x": x, "izs": np.array(izs), "kc": np.concatenate(kc), "kc_len": np.array([len(k) for k in kc]),
+               "p_full": np.full((len(x), ndc), np.nan), "blob_full": np.zeros((len(x), 6)),
+               "emu_full": np.zeros((len(x), len(izs), len(emu.emu_params))),
+               "p_empty": np.zeros(ndc), "p_partial": np.full((len(x), ndc), np.nan), "p_res_only": np.full((len(x), ndc), np.nan),
+               "p_like_sub": np.full((len(x), sum(len(ks[i]) for i in izs)), np.nan), "p_like_none": np.zeros(nd)}
+        names = [p.name for p in like.free_params]
+        # whole families only: the reference raises "number of params mismatch" otherwise (base_igm.py:306-308)
+        fams = sorted({n.rsplit("_", 1)[0] for n in names if n not in ("As", "ns", "nrun")})
+        keep = [n for n in names if (n in ("As",)) or (n.rsplit("_", 1)[0] in fams[::2] and not n.startswith("R_coeff"))]
+        out["partial_names"] = np.array(keep, dtype=str)
+        for i, v in enumerate(x):
+            lp = like.parameters_from_sampling_point(v.copy())
+            r = like.theory.get_p1d_kms(zsub, kc, like_params=lp, return_emu_params=True)
+            if r is not None:
+                out["p_full"][i] = np.concatenate(r[0])
+                out["blob_full"][i] = r[1]
+                for j, nm in enumerate(emu.emu_params):
+                    out["emu_full"][i, :, j] = r[2][nm]
+            r = like.theory.get_p1d_kms(zsub, kc, like_params=[p for p in lp if p.name in keep], return_blob=False)
+            if r is not None:
+                out["p_partial"][i] = np.concatenate(r)
+            r = like.theory.get_p1d_kms(zsub, kc, like_params=[p for p in lp if p.name.startswith("R_coeff")], return_blob=False)
+            if r is not None:
+                out["p_res_only"][i] = np.concatenate(r)
+            r = like.get_p1d_kms(zs=zsub, _k_kms=(kc if rebin_k == 1 else None), values=v.copy())
+            if r is not None and rebin_k != 1:
+                out["p_like_sub"][i] = np.concatenate(r[0])
+            elif r is not None:
+                out["p_like_sub"] = out["p_like_sub"] if out["p_like_sub"].shape[1] == ndc else np.full((len(x), ndc), np.nan)
+                out["p_like_sub"][i] = np.concatenate(r[0])
+        out["p_empty"] = np.concatenate(like.theory.get_p1d_kms(zsub, kc, like_params=[], return_blob=False))
+        out["p_like_none"] = np.concatenate(like.get_p1d_kms()[0])
+    spec = spec_from_likelihood(like)
+    save_spec(os.path.join(OUT, name + ".npz"), spec, **out)
+    print("%-18s ndim=%3d  %d points, %d rejected, custom grid %d bins over z = %s" % (name, x.shape[1], len(x), int(np.isnan(out["p_full"]).all(axis=1).sum()), ndc, zsub))
+
+
+CONFIGS["theory_kat_chab"] = lambda: make_theory_kat("theory_kat_chab", RefMLPEmulator(small_nn(51, "mpg"), "synthetic_mpg_nn", "mpg"), "chab", 6, 1, 1100)
+CONFIGS["theory_kat_nyx"] = lambda: make_theory_kat(
+    "theory_kat_nyx", RefGPEmulator(small_gp(52, "nyx"), "synthetic_nyx_gp", "nyx"), "dr1c", 5, 4, 1200,
+    use_hull=True, vary_alphas=True, use_star_priors={"Delta2_star": [0.2, 0.6]}, use_ic=False)
 CONFIGS["agn_kat"] = make_agn_kat
 
 if __name__ == "__main__":
