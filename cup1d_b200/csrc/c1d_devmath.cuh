@@ -84,6 +84,26 @@ __device__ __forceinline__ double exp_tab_neg(double x, const double* __restrict
   return p * tab[ni & 31] * __longlong_as_double((long long)((ni >> 5) + 1023) << 52);
 }
 
+// the same without a branch for the GP kernel-vector product: arguments below -700 are clamped (e^-700 = 1e-304
+// stands in for 0: the terms it multiplies are O(1), the sum they enter is O(1))
+__device__ __forceinline__ double exp_tab_neg_clamped(double x, const double* __restrict__ tab) {
+  x = fmax(x, -700.0);
+  const double L_HI = 46.16624130844683, L_LO = 6.513687597097931e-16;  // 32 log2(e)
+  const int ni = __double2int_rn(x * L_HI);
+  const double n = (double)ni;
+  double r = fma(x, L_HI, -n);
+  r = fma(x, L_LO, r);
+  const double r2 = r * r;
+  const double a0 = fma(0.02166084939249829, r, 1.0);
+  const double a1 = fma(1.693850972437182e-06, r, 0.0002345961982022468);
+  const double a2 = fma(3.973709984549416e-11, r, 9.172562701824643e-09);
+  const double r4 = r2 * r2;
+  const double b0 = fma(a1, r2, a0);
+  const double b1 = fma(1.4345655584131934e-13, r2, a2);
+  const double p = fma(b1, r4, b0);
+  return p * tab[ni & 31] * __longlong_as_double((long long)((ni >> 5) + 1023) << 52);
+}
+
 // e^x with the same 2^r polynomial (log2 e in two terms); |x| < 700, else the library function.
 // Used for the per-(walker, z) ratio set-up of the exp recurrences.
 __device__ __forceinline__ double exp_poly(double x) {

@@ -15,6 +15,9 @@
 //   stage 5      k_finalize    regulate + prior, blobs conventions
 //
 // Reference lines are cited next to each formula.
+#include <cstdlib>
+#include <cstring>
+
 #include "c1d_internal.h"
 #include "c1d_devmath.cuh"
 
@@ -363,6 +366,114 @@ k_gp_f64_smem(DevCtx c, const double* __restrict__ emu_in, int64_t nrows, double
   }
 }
 
+// The same product with lane = row: a group of GPL_SPLIT warps owns 32 rows, each warp of the group walks
+// its quarter of the training set and every training-point value is ONE broadcast shared-memory read for
+// 32 rows (the two-rows-per-warp kernel above reads 13 doubles per lane and training point for 2 rows:
+// its shared-memory wavefronts, not the fp64 pipe, pace it).  The partial sums of the group are added in
+// a fixed order (part 0 + 1 + 2 + 3), so a row's result does not depend on the batch it travels in.
+// Measured on B200 (C2: 1320 training points, 6 inputs, 6 outputs; two-rows-per-warp kernel | this one):
+// 65 536 walkers 4.12 | 2.47 ms, 16 384: 1.06 | 0.67, 4096: 0.29 | 0.19, 1024: 0.100 | 0.105 (the older form
+// keeps the batches below one item per group slot).  512 threads: 2.50 ms; run-time input / output counts
+// (predicated loads and FMAs) and a branch in the exponential: 3.17 ms.
+#define GPL_THREADS 640
+#define GPL_SPLIT 4
+#define GPL_GROUPS (GPL_THREADS / 32 / GPL_SPLIT)
+// NE / NO: emulator inputs / outputs at compile time (0 = run-time counts)
+template <int NE, int NO>
+__global__ void __launch_bounds__(GPL_THREADS, 1)
+k_gp_f64_lanes(DevCtx c, const double* __restrict__ emu_in, int64_t nrows, double* __restrict__ out,
+               int out_stride, int ntp) {
+  const int n_emu = NE ? NE : c.n_emu, nc = NO ? NO : c.nc;
+  extern __shared__ __align__(16) double gsm[];
+  double* Xs = gsm;                                   // [ntp][8]: inputs of a training point, pre-divided by the length scales
+  double* As = Xs + (size_t)C1D_MAX_EMU * ntp;        // [ntp][8]: sigma^2 alpha of a training point
+  double* etab = As + (size_t)C1D_MAX_COEF * ntp;     // [32]
+  double* part = etab + 32;                           // [GPL_GROUPS][GPL_SPLIT - 1][C1D_MAX_COEF][32]
+  for (int t = threadIdx.x; t < C1D_MAX_EMU * ntp; t += blockDim.x) {
+    const int i = t / C1D_MAX_EMU, d = t - i * C1D_MAX_EMU;
+    // pad points sit far away (kernel value 0) and carry alpha = 0; unused input slots are 0 on both sides
+    Xs[t] = (d < n_emu) ? ((i < c.gp_ntrain) ? c.gp_x[(size_t)i * n_emu + d] * c.gp_invell[d] : 1.0e3) : 0.0;
+  }
+  for (int t = threadIdx.x; t < C1D_MAX_COEF * ntp; t += blockDim.x) {
+    const int i = t / C1D_MAX_COEF, o = t - i * C1D_MAX_COEF;
+    As[t] = (o < nc && i < c.gp_ntrain) ? c.gp_sigma2 * c.gp_alpha[(size_t)i * nc + o] : 0.0;
+  }
+  if (threadIdx.x < 32) etab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = warp / GPL_SPLIT, prt = warp % GPL_SPLIT;
+  const int chunk = ntp / GPL_SPLIT;  // ntp is a multiple of 32
+  const int i0 = prt * chunk, i1 = i0 + chunk;
+  const int64_t nitems = (nrows + 31) / 32;
+  for (int64_t item = (int64_t)blockIdx.x * GPL_GROUPS + grp; item < nitems; item += (int64_t)gridDim.x * GPL_GROUPS) {
+    const int64_t row = item * 32 + lane;
+    const int64_t rv = row < nrows ? row : nrows - 1;
+    double u[C1D_MAX_EMU];
+#pragma unroll
+    for (int d = 0; d < C1D_MAX_EMU; ++d) {
+      u[d] = 0.0;
+      if (d < n_emu) {
+        const double lo = c.emu_lo[d], sc = c.gp_invell[d] / (c.emu_hi[d] - lo);
+        u[d] = (emu_in[rv * C1D_MAX_EMU + d] - lo) * sc;
+      }
+    }
+    double acc[C1D_MAX_COEF];
+#pragma unroll
+    for (int o = 0; o < C1D_MAX_COEF; ++o) acc[o] = 0.0;
+    const double2* xp = reinterpret_cast<const double2*>(Xs) + (size_t)i0 * (C1D_MAX_EMU / 2);
+    const double2* ap = reinterpret_cast<const double2*>(As) + (size_t)i0 * (C1D_MAX_COEF / 2);
+#pragma unroll 2
+    for (int i = i0; i < i1; ++i, xp += C1D_MAX_EMU / 2, ap += C1D_MAX_COEF / 2) {
+      double s2 = 0.0;
+#pragma unroll
+      for (int h = 0; h < C1D_MAX_EMU / 2; ++h) {
+        if (2 * h < n_emu) {
+          const double2 xv = xp[h];  // broadcast
+          const double t0 = u[2 * h] - xv.x, t1 = u[2 * h + 1] - xv.y;
+          s2 = fma(t0, t0, s2);
+          s2 = fma(t1, t1, s2);
+        }
+      }
+      const double kv = exp_tab_neg_clamped(-0.5 * s2, etab);
+#pragma unroll
+      for (int h = 0; h < C1D_MAX_COEF / 2; ++h) {
+        if (2 * h < nc) {
+          const double2 av = ap[h];  // broadcast
+          acc[2 * h] = fma(kv, av.x, acc[2 * h]);
+          acc[2 * h + 1] = fma(kv, av.y, acc[2 * h + 1]);
+        }
+      }
+    }
+    // fixed-order reduction over the parts of the group
+    double* pg = part + (size_t)grp * (GPL_SPLIT - 1) * C1D_MAX_COEF * 32;
+    if (prt > 0) {
+#pragma unroll
+      for (int o = 0; o < C1D_MAX_COEF; ++o) pg[((prt - 1) * C1D_MAX_COEF + o) * 32 + lane] = acc[o];
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(32 * GPL_SPLIT) : "memory");
+    if (prt == 0) {
+#pragma unroll
+      for (int q = 0; q < GPL_SPLIT - 1; ++q)
+#pragma unroll
+        for (int o = 0; o < C1D_MAX_COEF; ++o) acc[o] += pg[(q * C1D_MAX_COEF + o) * 32 + lane];
+      if (row < nrows) {
+        const double mF = emu_in[row * C1D_MAX_EMU + c.gp_imf];
+        double lnn = 0.0;  // ln norm(mF), Horner
+        for (int j = c.gp_nnorm - 1; j >= 0; --j) lnn = lnn * mF + c.gp_norm[j];
+#pragma unroll
+        for (int o = 0; o < C1D_MAX_COEF; ++o) {
+          if (o < nc) {
+            double y = c.gp_ymean[o] + c.gp_ystd[o] * acc[o];
+            if (o == 0) y += lnn;
+            out[row * out_stride + o] = y;
+          }
+        }
+      }
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(32 * GPL_SPLIT) : "memory");  // partials consumed before the next item
+  }
+}
+
 int c1d_launch_emulator(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out,
                         int out_stride, uint32_t flags, cudaStream_t s) {
   if (nrows <= 0) return C1D_OK;
@@ -374,7 +485,25 @@ int c1d_launch_emulator(c1d_ctx* ctx, const double* emu_in, int64_t nrows, doubl
     const int ntp = (cfg.gp_ntrain + 31) & ~31;
     const size_t smem = ((size_t)(cfg.n_emu + cfg.nc) * ntp + 32) * sizeof(double);
     const int64_t pairs = (nrows + 1) / 2;
-    if (smem <= 227 * 1024 && pairs >= (int64_t)ctx->num_sms * (GP_THREADS / 32) / 2) {
+    // lane = row kernel: tables [ntp][8] + [ntp][8], the partial sums of the groups
+    const size_t smem_l = ((size_t)(C1D_MAX_EMU + C1D_MAX_COEF) * ntp + 32 + (size_t)GPL_GROUPS * (GPL_SPLIT - 1) * C1D_MAX_COEF * 32) * sizeof(double);
+    const int64_t items = (nrows + 31) / 32;
+    const char* gk = getenv("C1D_GP_KERNEL");  // lanes | pairs | global: forces one form (tests, measurements)
+    const bool want_lanes = gk ? !strcmp(gk, "lanes") : (items >= (int64_t)ctx->num_sms * GPL_GROUPS);
+    if (smem_l <= 227 * 1024 && want_lanes) {
+      void (*kern)(DevCtx, const double*, int64_t, double*, int, int) = k_gp_f64_lanes<0, 0>;
+      const int ne = cfg.n_emu, no = cfg.nc;
+      if (ne == 6 && no == 5) kern = k_gp_f64_lanes<6, 5>;
+      else if (ne == 6 && no == 6) kern = k_gp_f64_lanes<6, 6>;
+      else if (ne == 6 && no == 7) kern = k_gp_f64_lanes<6, 7>;
+      else if (ne == 7 && no == 5) kern = k_gp_f64_lanes<7, 5>;
+      else if (ne == 7 && no == 6) kern = k_gp_f64_lanes<7, 6>;
+      else if (ne == 7 && no == 7) kern = k_gp_f64_lanes<7, 7>;
+      C1D_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+      int64_t blocks = (items + GPL_GROUPS - 1) / GPL_GROUPS;
+      int grid = (int)(blocks < ctx->num_sms ? blocks : ctx->num_sms);
+      kern<<<grid, GPL_THREADS, smem_l, s>>>(ctx->d, emu_in, nrows, out, out_stride, ntp);
+    } else if (smem <= 227 * 1024 && (gk ? !strcmp(gk, "pairs") : pairs >= (int64_t)ctx->num_sms * (GP_THREADS / 32) / 2)) {
       // training set resident in shared memory, two rows per warp
       C1D_CUDA(ctx, cudaFuncSetAttribute(k_gp_f64_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int64_t blocks = (pairs + GP_THREADS / 32 - 1) / (GP_THREADS / 32);

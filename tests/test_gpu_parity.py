@@ -319,6 +319,34 @@ def test_edge_batches(golden):
     like.close()
 
 
+@pytest.mark.parametrize("kernel", ["lanes", "pairs", "global"])
+@pytest.mark.parametrize("name", ["nyx_gp_priors", "hcd_const"])
+def test_every_gp_kernel_on_goldens(golden, monkeypatch, name, kernel):
+    """the three forms of the GP emulator kernel (lane = row with the training set split over four warps,
+    two rows per warp, row per warp from global memory; chosen by batch size in production) are all held
+    to the reference goldens, and a row's result does not depend on the batch it travels in"""
+    import torch
+
+    monkeypatch.setenv("C1D_GP_KERNEL", kernel)
+    spec, ref = golden(name)
+    like = _like(spec)
+    x, exp = ref["x"], ref["lnprob_blobs"]
+    got = like.log_prob_and_blobs_vectorized(x)
+    bad = exp[:, 0] <= -1e99
+    np.testing.assert_array_equal(got[bad, 0], exp[bad, 0])
+    assert np.all(np.abs(got[~bad, 0] - exp[~bad, 0]) <= _tol(exp[~bad, 0]))
+    incube = ~((x > 1).any(axis=1) | (x < 0).any(axis=1))
+    p = like.get_p1d_kms_batch(x[incube])
+    refp = ref["p1d"][incube]
+    none = np.isnan(refp).all(axis=1)
+    assert np.max(np.abs(p[~none] / refp[~none] - 1)) <= RTOL_P1D
+    big = torch.as_tensor(np.tile(x, (40, 1)), device="cuda:0")
+    out = like.log_prob_batch(big).view(40, len(x))
+    assert torch.equal(out, out[:1].expand(40, len(x)))
+    np.testing.assert_array_equal(out[0].cpu().numpy(), got[:, 0])
+    like.close()
+
+
 @pytest.mark.parametrize("name", ["c1", "c3", "c4"])
 def test_stage3_segments_are_bit_identical(monkeypatch, name):
     """medium batches cut every redshift bin of the walker-per-lane stage 3 into 2, 4 or 8 k-segments
