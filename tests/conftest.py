@@ -26,6 +26,7 @@ GOLDEN_NAMES = [
     "var_zmin",
     "var_global_igm",
     "var_at_a_time",
+    "var_fix_cosmo",
 ]
 
 

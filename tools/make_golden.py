@@ -208,6 +208,15 @@ VARIATIONS = {
     "var_global_igm": ("global_igm", None),
     "var_at_a_time": ("at_a_time_global", None),
 }
+def hook_fix_cosmo(args):
+    args.fix_cosmo = True
+
+
+# no cosmological parameter free (fix_cosmo=True, set_like_params.py): the rescaling of stage 1 is the identity
+CONFIGS["var_fix_cosmo"] = lambda: make(
+    "var_fix_cosmo", RefMLPEmulator(small_nn(49, "mpg"), "synthetic_mpg_nn", "mpg"), "dr1c", nz=5, rebin_k=2, seed=990,
+    use_ic=False, n=(8, 8, 2), width=0.1, args_hook=hook_fix_cosmo)
+
 for _i, (_nm, (_ft, _var)) in enumerate(VARIATIONS.items()):
     CONFIGS[_nm] = (lambda nm=_nm, ft=_ft, var=_var, i=_i: make(
         nm, RefMLPEmulator(small_nn(40 + i, "mpg"), "synthetic_mpg_nn", "mpg"), "dr1c", nz=5, rebin_k=2, seed=900 + 10 * i,
