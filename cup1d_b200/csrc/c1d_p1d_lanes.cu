@@ -36,7 +36,8 @@ constexpr int PL_ANCHOR = 64;  // fine points between exact re-evaluations of th
 // U fine points per loop trip as independent instruction streams, with 64K / threads registers per
 // thread.  Measured on B200 (C4, 65 536 walkers): U=1 x 512 threads 2.52 ms, U=2 x 384 3.00 ms,
 // U=4 x 384 2.78 ms, U=4 x 256 3.57 ms, and U=1 with 640 / 768 / 1024 threads (spilling) 2.96 / 3.23 /
-// 3.88 ms: warps beat unrolling, and 16 warps at the 128-register cap is the optimum.
+// 3.88 ms: warps beat unrolling, and 16 warps at the 128-register cap is the optimum.  (Later, with the table-based
+// 10^x: U=1 x 512 2.11 ms, U=2 x 512 - no spills at 128 registers, but the two streams are serialised - 2.36 ms.)
 constexpr int PL_U = 1;
 // Cut the redshift bins until the batch holds PL_WAVES waves of items, and hand batches below PL_MIN_WAVES2 / 2
 // waves of the finest items to the warp-per-walker kernel.  Measured on B200 (C4, stage 3 in ms, warp-per-walker
