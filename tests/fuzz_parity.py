@@ -5,7 +5,7 @@ AGN, metal / HCD model variants, NN shape or GP, block or dense covariance, conv
 priors), both forms of stage 3 and every k-segment cut; then the z-masked calls, the per-z
 log-likelihoods (with and without log det C) and chi2.  Needs a B200; the oracle is the checker.
 
-    python tools/fuzz_parity.py [n_configs] [seed]
+    python tests/fuzz_parity.py [n_configs] [seed]
 """
 import os
 import sys
