@@ -38,9 +38,11 @@ namespace {
 constexpr int M64_GROUPS = 3;                         // row groups per CTA of the throughput variant (one warp of each per SM sub-partition)
 constexpr int M64_RB = 3;                             // 8-row blocks per group
 constexpr int M64_ROWS = 8 * M64_RB;                  // rows of one group's tile
-// The kernel is instantiated twice: <3 groups, 2 slab buffers> for throughput (72 rows per CTA) and
+// The kernel is instantiated three times: <3 groups, 2 slab buffers> for throughput (72 rows per CTA),
 // <1 group, 4 slab buffers> for small batches, where a CTA holds one 24-row tile, the rows spread over
-// up to 148 CTAs and four slabs in flight hide the L2 latency that otherwise paces a single tile.
+// up to 148 CTAs and four slabs in flight hide the L2 latency that otherwise paces a single tile, and
+// <2 groups, 2 slab buffers> for the batch sizes in between whose last round of 72-row units would run
+// nearly empty (the launcher picks by estimated time).
 template <int G> struct M64Geom {
   static constexpr int CWARPS = 4 * G;             // compute warps
   static constexpr int THREADS = 32 * (CWARPS + 1);  // + the weight streamer
@@ -435,6 +437,8 @@ int c1d_mlp64_prepare(c1d_ctx* ctx) {
                                      (int)m64_smem<M64_GROUPS, M64_NBUF>()));
   C1D_CUDA(ctx, cudaFuncSetAttribute(k_mlp_f64<1, M64_NBUF_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)m64_smem<1, M64_NBUF_SMALL>()));
+  C1D_CUDA(ctx, cudaFuncSetAttribute(k_mlp_f64<2, M64_NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)m64_smem<2, M64_NBUF>()));
   return C1D_OK;
 }
 
@@ -445,19 +449,37 @@ int c1d_mlp64_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* 
     return C1D_ERR_STATE;
   }
   const int64_t ntiles = (nrows + M64_ROWS - 1) / M64_ROWS;  // 24-row tiles
-  // measured on C4: the small-batch variant wins up to ~2 waves of 24-row tiles (64 walkers: 84 -> 47 us),
-  // ties at 1024 walkers and loses beyond
-  if (ntiles <= 2 * (int64_t)ctx->num_sms) {
-    // small batch: one tile per CTA spreads the rows over the machine, four slabs in flight
-    const int grid = (int)(ntiles < ctx->num_sms ? ntiles : ctx->num_sms);
+  // One, two or three 24-row tiles per CTA and round: the variant with the shortest estimated time
+  // = rounds x time per round.  Measured on C4 (us per round): one tile (four slabs in flight) 41, two 53,
+  // three 72; e.g. 64 walkers 84 -> 47 us with one tile per CTA, 512 walkers 82 -> 64 us and 1024 walkers
+  // 154 -> 115 us with two, three from ~3000 walkers on.  C1D_MLP64_G=1|2|3 forces a variant.
+  const int64_t sms = ctx->num_sms;
+  const double t_round[3] = {41.0, 53.0, 72.0};
+  int g = 3;
+  double best = 1e300;
+  for (int cand = 3; cand >= 1; --cand) {
+    const int64_t units = (ntiles + cand - 1) / cand;
+    const double t = (double)((units + sms - 1) / sms) * t_round[cand - 1];
+    if (t < 0.98 * best) {
+      best = t;
+      g = cand;
+    }
+  }
+  if (const char* fg = getenv("C1D_MLP64_G")) {
+    const int v = atoi(fg);
+    if (v >= 1 && v <= 3) g = v;
+  }
+  const int64_t units = (ntiles + g - 1) / g;
+  const int grid = (int)(units < sms ? units : sms);
+  if (g == 1)
     k_mlp_f64<1, M64_NBUF_SMALL><<<grid, M64Geom<1>::THREADS, m64_smem<1, M64_NBUF_SMALL>(), s>>>(
         st->p, emu_in, ctx->d.emu_lo, ctx->d.emu_hi, nrows, out, out_stride);
-  } else {
-    const int64_t ntriples = (ntiles + M64_GROUPS - 1) / M64_GROUPS;
-    const int grid = (int)(ntriples < ctx->num_sms ? ntriples : ctx->num_sms);
+  else if (g == 2)
+    k_mlp_f64<2, M64_NBUF><<<grid, M64Geom<2>::THREADS, m64_smem<2, M64_NBUF>(), s>>>(
+        st->p, emu_in, ctx->d.emu_lo, ctx->d.emu_hi, nrows, out, out_stride);
+  else
     k_mlp_f64<M64_GROUPS, M64_NBUF><<<grid, M64Geom<M64_GROUPS>::THREADS, m64_smem<M64_GROUPS, M64_NBUF>(), s>>>(
         st->p, emu_in, ctx->d.emu_lo, ctx->d.emu_hi, nrows, out, out_stride);
-  }
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return C1D_OK;
