@@ -19,6 +19,11 @@ The same object is injected into the *reference* ``Theory`` when golden
 vectors are generated (tools/make_golden.py), so parity of the whole path is
 measured against the reference's own code for stages 1, 3, 4, 5.
 
+The arithmetic of the restatement is cross-checked against independent implementations of the
+same algorithms (tests/test_emulators_cpu.py): torch.nn Linear + LeakyReLU stacks in float64 and
+float32 (LaCE's own precision) and scikit-learn's GaussianProcessRegressor with the same fixed
+ARD kernel.  That pins the formulas, not LaCE's trained models.
+
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs may import this package.
 """
