@@ -88,6 +88,11 @@ extern "C" int c1d_ctx_create(const c1d_config* cfg, c1d_ctx** out) {
     return C1D_ERR_CUDA;
   }
   for (int i = 0; i < 9; ++i) C1D_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+  C1D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    C1D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming));
+    C1D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+  }
   return C1D_OK;
 }
 
@@ -391,16 +396,34 @@ extern "C" int c1d_loglike_batch_host(c1d_ctx* ctx, const double* x_host, int64_
   int64_t chunk = W < CHUNK_MAX ? W : CHUNK_MAX;
   rc = ws_reserve(ctx, chunk);
   if (rc) return rc;
+  cudaStream_t sc = ctx->copy_stream;
   for (int64_t w0 = 0; w0 < W; w0 += chunk) {
     int64_t n = (W - w0 < chunk) ? (W - w0) : chunk;
-    C1D_CUDA(ctx, cudaMemcpyAsync(ctx->ws.xdev, x_host + w0 * c.ndim, (size_t)n * c.ndim * sizeof(double),
-                                  cudaMemcpyHostToDevice, s));
-    rc = c1d_loglike_batch(ctx, ctx->ws.xdev, n, ctx->ws.lnp, nullptr, ctx->ws.blobs, nullptr, flags, s);
-    if (rc) return rc;
-    // out_host rows are (lnP, blob[6]): pack on the device, one contiguous copy back
-    if ((rc = c1d_launch_pack7(ctx, n, s))) return rc;
-    C1D_CUDA(ctx, cudaMemcpyAsync(out_host + w0 * 7, ctx->ws.out7, (size_t)n * 7 * sizeof(double),
-                                  cudaMemcpyDeviceToHost, s));
+    // A large chunk goes up in two pieces (a quarter, then the rest) on the copy stream: the kernels of the
+    // first piece hide the upload of the second, and the rows of the first piece come down under the kernels
+    // of the second.  Small chunks keep one piece (their kernels are launch-bound, not copy-bound).
+    const int np = (n >= 32768) ? 2 : 1;
+    const int64_t n0 = (np == 2) ? ((n / 4 + 1023) / 1024) * 1024 : n;
+    const int64_t off[3] = {0, n0, n};
+    for (int p = 0; p < np; ++p) {
+      C1D_CUDA(ctx, cudaMemcpyAsync(ctx->ws.xdev + off[p] * c.ndim, x_host + (w0 + off[p]) * c.ndim,
+                                    (size_t)(off[p + 1] - off[p]) * c.ndim * sizeof(double), cudaMemcpyHostToDevice, sc));
+      C1D_CUDA(ctx, cudaEventRecord(ctx->ev_up[p], sc));
+    }
+    for (int p = 0; p < np; ++p) {
+      const int64_t m = off[p + 1] - off[p];
+      C1D_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_up[p], 0));
+      rc = c1d_loglike_batch(ctx, ctx->ws.xdev + off[p] * c.ndim, m, ctx->ws.lnp + off[p], nullptr, ctx->ws.blobs + off[p] * 6, nullptr,
+                             flags, s);
+      if (rc) return rc;
+      // out_host rows are (lnP, blob[6]): pack on the device, one contiguous copy back
+      if ((rc = c1d_launch_pack7(ctx, off[p], m, s))) return rc;
+      C1D_CUDA(ctx, cudaEventRecord(ctx->ev_done[p], s));
+      C1D_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_done[p], 0));
+      C1D_CUDA(ctx, cudaMemcpyAsync(out_host + (w0 + off[p]) * 7, ctx->ws.out7 + off[p] * 7, (size_t)m * 7 * sizeof(double),
+                                    cudaMemcpyDeviceToHost, sc));
+    }
+    C1D_CUDA(ctx, cudaStreamSynchronize(sc));
     C1D_CUDA(ctx, cudaStreamSynchronize(s));
   }
   return C1D_OK;
@@ -432,6 +455,11 @@ extern "C" int c1d_ctx_destroy(c1d_ctx* ctx) {
     if (ctx->dev[f]) cudaFree(ctx->dev[f]);
   for (int i = 0; i < 9; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
   return C1D_OK;
 }

@@ -87,6 +87,9 @@ struct c1d_ctx {
   int64_t launches;
   int timing;
   cudaEvent_t ev[9];
+  // host-buffer entry point: copy stream and events that order its uploads / downloads against the kernels
+  cudaStream_t copy_stream;
+  cudaEvent_t ev_up[2], ev_done[2];
   double last_ms[8];
   double* icov_pad;  // [ldd*ldd] zero-padded copy of the dense inverse covariance
   double* icovz_pad; // [nz][tzw*tzw] zero-padded per-z inverse covariance blocks, tzw = ndz_max rounded up to 64
@@ -121,7 +124,7 @@ int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, cudaStream_t s);
 int c1d_launch_finalize(c1d_ctx* ctx, int64_t W, double* lnp, double* lnl_z, double* blobs,
                         double* chi2, uint32_t flags, cudaStream_t s);
 
-int c1d_launch_pack7(c1d_ctx* ctx, int64_t W, cudaStream_t s);
+int c1d_launch_pack7(c1d_ctx* ctx, int64_t w0, int64_t W, cudaStream_t s);  // rows [w0, w0 + W) of ws.lnp / ws.blobs -> ws.out7
 
 // fp64 (DMMA) MLP: padded weight image + slab plan, built at finalize
 int c1d_mlp64_prepare(c1d_ctx* ctx);

@@ -1132,9 +1132,9 @@ k_pack7(int64_t W, const double* __restrict__ lnp, const double* __restrict__ bl
   out7[t] = (j == 0) ? lnp[w] : blobs[w * 6 + j - 1];
 }
 
-int c1d_launch_pack7(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
+int c1d_launch_pack7(c1d_ctx* ctx, int64_t w0, int64_t W, cudaStream_t s) {
   unsigned grid = (unsigned)((W * 7 + 255) / 256);
-  k_pack7<<<grid, 256, 0, s>>>(W, ctx->ws.lnp, ctx->ws.blobs, ctx->ws.out7);
+  k_pack7<<<grid, 256, 0, s>>>(W, ctx->ws.lnp + w0, ctx->ws.blobs + w0 * 6, ctx->ws.out7 + w0 * 7);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return C1D_OK;
