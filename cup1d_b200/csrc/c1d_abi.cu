@@ -87,7 +87,8 @@ extern "C" int c1d_ctx_create(const c1d_config* cfg, c1d_ctx** out) {
              prop.name, prop.major, prop.minor);
     return C1D_ERR_CUDA;
   }
-  for (int i = 0; i < 9; ++i) C1D_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+  for (int r = 0; r < C1D_TRING; ++r)
+    for (int i = 0; i < 6; ++i) C1D_CUDA(ctx, cudaEventCreate(&ctx->evr[r][i]));
   C1D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
     C1D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming));
@@ -292,9 +293,23 @@ static int check_ready(c1d_ctx* ctx, uint32_t flags) {
   return C1D_OK;
 }
 
-#define TICK(i)                                                        \
-  do {                                                                 \
-    if (ctx->timing) C1D_CUDA(ctx, cudaEventRecord(ctx->ev[i], s));    \
+// reads the pending event sets (waits for the last one) and adds their stage times to last_ms
+static int timing_drain(c1d_ctx* ctx) {
+  for (int r = 0; r < ctx->ev_pending; ++r) {
+    C1D_CUDA(ctx, cudaEventSynchronize(ctx->evr[r][5]));
+    for (int i = 0; i < 5; ++i) {
+      float ms = 0.f;
+      C1D_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->evr[r][i], ctx->evr[r][i + 1]));
+      ctx->last_ms[i] += ms;
+    }
+  }
+  ctx->ev_pending = 0;
+  return C1D_OK;
+}
+
+#define TICK(i)                                                                          \
+  do {                                                                                   \
+    if (ctx->timing) C1D_CUDA(ctx, cudaEventRecord(ctx->evr[ctx->ev_pending][i], s));    \
   } while (0)
 
 extern "C" int c1d_loglike_batch(c1d_ctx* ctx, const double* x_dev, int64_t W, double* lnp_dev,
@@ -315,10 +330,10 @@ extern "C" int c1d_loglike_batch(c1d_ctx* ctx, const double* x_dev, int64_t W, d
   if (rc) return rc;
   const int use_full = c.has_full && !(flags & C1D_FLAG_ZMASK);
   const int want_chi2z = !use_full || lnl_z_dev != nullptr;
-  if (ctx->timing) for (int i = 0; i < 8; ++i) ctx->last_ms[i] = 0.0;
   for (int64_t w0 = 0; w0 < W; w0 += chunk) {
     int64_t n = (W - w0 < chunk) ? (W - w0) : chunk;
     double* blobs = blobs_dev ? blobs_dev + w0 * 6 : ctx->ws.blobs;
+    if (ctx->timing && ctx->ev_pending == C1D_TRING && (rc = timing_drain(ctx))) return rc;
     TICK(0);
     if ((rc = c1d_launch_stage1(ctx, x_dev + w0 * c.ndim, n, blobs, flags, s))) return rc;
     TICK(1);
@@ -332,14 +347,7 @@ extern "C" int c1d_loglike_batch(c1d_ctx* ctx, const double* x_dev, int64_t W, d
                                   chi2_dev ? chi2_dev + w0 : nullptr, flags, s)))
       return rc;
     TICK(5);
-    if (ctx->timing) {
-      C1D_CUDA(ctx, cudaEventSynchronize(ctx->ev[5]));
-      for (int i = 0; i < 5; ++i) {
-        float ms = 0.f;
-        C1D_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
-        ctx->last_ms[i] += ms;
-      }
-    }
+    if (ctx->timing) ctx->ev_pending++;
   }
   return C1D_OK;
 }
@@ -431,13 +439,23 @@ extern "C" int c1d_loglike_batch_host(c1d_ctx* ctx, const double* x_host, int64_
 
 extern "C" int c1d_set_timing(c1d_ctx* ctx, int enable) {
   if (!ctx) return C1D_ERR_ARG;
+  C1D_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  int rc = timing_drain(ctx);
+  if (rc) return rc;
+  for (int i = 0; i < 8; ++i) ctx->last_ms[i] = 0.0;
   ctx->timing = enable ? 1 : 0;
   return C1D_OK;
 }
 
 extern "C" int c1d_get_timing(c1d_ctx* ctx, double* ms_out) {
   if (!ctx || !ms_out) return C1D_ERR_ARG;
-  for (int i = 0; i < 8; ++i) ms_out[i] = ctx->last_ms[i];
+  C1D_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  int rc = timing_drain(ctx);
+  if (rc) return rc;
+  for (int i = 0; i < 8; ++i) {
+    ms_out[i] = ctx->last_ms[i];
+    ctx->last_ms[i] = 0.0;
+  }
   return C1D_OK;
 }
 
@@ -453,8 +471,9 @@ extern "C" int c1d_ctx_destroy(c1d_ctx* ctx) {
   if (ctx->icovz_pad) cudaFree(ctx->icovz_pad);
   for (int f = 0; f < C1D_F_COUNT; ++f)
     if (ctx->dev[f]) cudaFree(ctx->dev[f]);
-  for (int i = 0; i < 9; ++i)
-    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int r = 0; r < C1D_TRING; ++r)
+    for (int i = 0; i < 6; ++i)
+      if (ctx->evr[r][i]) cudaEventDestroy(ctx->evr[r][i]);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
     if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);

@@ -30,6 +30,8 @@ enum {
 // combined with atomicMax by the (walker, z) threads of stage 1: out-of-cube wins over a rejection
 enum { ST_OK = 0, ST_REJECTED = 1, ST_OUT_OF_CUBE = 2 };
 
+#define C1D_TRING 64
+
 struct DevCtx {
   int nz, ndim, n_emu, nd, nf, ell_width, rebin_width, emu_kind, nc, n_layers;
   int ldd;  // row stride of the residual buffer = nd rounded up to a multiple of 64 (zero padded)
@@ -86,7 +88,10 @@ struct c1d_ctx {
   int nfz_max, ndz_max;  // largest z-bin of the model grid / data vector
   int64_t launches;
   int timing;
-  cudaEvent_t ev[9];
+  // stage timing: a ring of event sets (six events per evaluated chunk) read back lazily, so that enabling
+  // it does not make the evaluation calls synchronous
+  cudaEvent_t evr[C1D_TRING][6];
+  int ev_pending;  // sets recorded and not yet read
   // host-buffer entry point: copy stream and events that order its uploads / downloads against the kernels
   cudaStream_t copy_stream;
   cudaEvent_t ev_up[2], ev_done[2];

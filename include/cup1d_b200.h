@@ -225,8 +225,10 @@ int c1d_philox_u01(uint64_t seed, int64_t step, int half, int64_t walker, int wh
 /* number of kernels launched by this context since creation */
 int64_t c1d_launch_count(const c1d_ctx* ctx);
 
-/* device time [ms] of the last *_batch call, per stage, measured with CUDA
- * events on the caller's stream when enabled (0 = off, default) */
+/* per-stage device time [ms], measured with CUDA events on the caller's stream when enabled
+ * (0 = off, default).  The events are read back lazily, so the evaluation calls stay
+ * asynchronous: c1d_get_timing waits for the evaluations recorded so far, returns the times
+ * summed over them since the previous c1d_get_timing / c1d_set_timing and resets the sums. */
 int c1d_set_timing(c1d_ctx* ctx, int enable);
 int c1d_get_timing(c1d_ctx* ctx, double* ms_out /* [8] */);
 
