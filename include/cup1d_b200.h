@@ -199,7 +199,11 @@ int c1d_emulator_only(c1d_ctx* ctx, const double* emu_in_dev, int64_t nrows,
 
 /* host-buffer variant of c1d_loglike_batch: the call a Python caller with
  * NumPy arrays makes.  Copies x to the device, evaluates, copies
- * out_host[W,7] = (lnP, blob[6]) back and synchronises. */
+ * out_host[W,7] = (lnP, blob[6]) back and synchronises.  Batches of 32 768
+ * walkers or more go up in two pieces on the context's own copy stream, so
+ * that the upload of the second piece and the download of the first run under
+ * the kernels (pinned host buffers make the copies asynchronous; pageable
+ * ones work, without the overlap).  The kernels run on the legacy default stream. */
 int c1d_loglike_batch_host(c1d_ctx* ctx, const double* x_host, int64_t W,
                            double* out_host, uint32_t flags);
 
