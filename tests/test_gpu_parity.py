@@ -319,6 +319,33 @@ def test_edge_batches(golden):
     like.close()
 
 
+def test_host_entry_point_pipelines_large_batches():
+    """c1d_loglike_batch_host uploads batches of 32 768 walkers or more in two pieces on its copy stream
+    (and splits beyond 131 072 walkers into chunks): the rows must equal the device-tensor path bit for bit,
+    with pinned and with pageable host buffers"""
+    import torch
+
+    from cup1d_b200 import synth
+
+    spec = _synthetic("c4")
+    like = _like(spec)
+    for W in (40000, 140000):
+        x = synth.walkers_sweep(spec, W, seed=31, frac_out=0.01)
+        xd = torch.as_tensor(x, device="cuda:0")
+        lnp, blobs = like.log_prob_and_blobs_batch(xd)
+        want = torch.cat([lnp[:, None], blobs], dim=1).cpu().numpy()
+        got = like.log_prob_and_blobs_vectorized(x)  # pageable
+        np.testing.assert_array_equal(np.nan_to_num(got, nan=-7.0), np.nan_to_num(want, nan=-7.0))
+        xp = torch.from_numpy(x).pin_memory()
+        out = torch.empty((W, 7), dtype=torch.float64).pin_memory()
+        like.log_prob_and_blobs_vectorized(xp.numpy(), out=out.numpy())
+        np.testing.assert_array_equal(np.nan_to_num(out.numpy(), nan=-7.0), np.nan_to_num(want, nan=-7.0))
+        # a second call reuses the staging buffers: still the same rows
+        like.log_prob_and_blobs_vectorized(xp.numpy(), out=out.numpy())
+        np.testing.assert_array_equal(np.nan_to_num(out.numpy(), nan=-7.0), np.nan_to_num(want, nan=-7.0))
+    like.close()
+
+
 @pytest.mark.parametrize("kernel", ["lanes", "pairs", "global"])
 @pytest.mark.parametrize("name", ["nyx_gp_priors", "hcd_const"])
 def test_every_gp_kernel_on_goldens(golden, monkeypatch, name, kernel):
