@@ -5,7 +5,7 @@ objects through tools/ref_harness.py; on seeded walkers the oracle must reproduc
 log_prob_and_blobs (bit for bit in practice) and the compiled device tables, run through the NumPy mirror
 of the kernels (tests/devsim.py), must agree to rounding.
 
-    python tests/ref_sweep.py [n_configs]
+    python tests/ref_sweep.py [n_configs] [seed]
 """
 import sys, io, contextlib, numpy as np, traceback
 sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
@@ -18,7 +18,7 @@ from oracle.model import OracleLikelihood
 sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.abspath(__file__)))
 import devsim
 
-rng = np.random.default_rng(77)
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 77)
 vars_ = [None,"metal_trad","metal_si2","metal_deco","metal_thin","DLAs","no_contaminants","less_igm","more_igm","Gaikwad21","Gaikwad21T","Turner24","LLS_nz4","no_res","zmin","zmax","HCD0","HCD_BOSS","Metals_Ma2025"]
 nfail=0
 for it in range(int(sys.argv[1]) if len(sys.argv)>1 else 24):
