@@ -24,6 +24,8 @@ nfail=0
 for it in range(int(sys.argv[1]) if len(sys.argv)>1 else 24):
     var = vars_[rng.integers(len(vars_))]
     fit_type = "global_opt"
+    if rng.integers(4) == 0:
+        fit_type, var = [("global_all", None), ("at_a_time_global", None), ("at_a_time_global", "metal_thin"), ("global_igm", None)][rng.integers(4)]
     suite = ["mpg","nyx"][rng.integers(2)]
     gp = bool(rng.integers(2))
     rebin_k = int(rng.choice([1,2,3,5,8]))

@@ -112,3 +112,45 @@ def test_derived_grid_spec_reproduces_reference_theory():
     x = ref["x"][:8]  # the in-cube rows (the mirror keeps the cube test)
     out = devsim.simulate(cfg, F, x)
     assert np.max(np.abs(out["p1d"] / ref["p_full"][:8] - 1)) < 1e-10
+
+
+def test_theory_like_params_mapping(golden):
+    """B200Theory's translation of like_params (lya_theory.py:610-814 conventions) needs no device: absent
+    parameters keep the coefficient their model holds, the resolution term needs an R_coeff parameter in
+    the list, a family comes whole or not at all"""
+    from types import SimpleNamespace
+
+    import numpy as np
+    import pytest
+
+    from cup1d_b200.theory import B200Theory
+
+    spec, _ = golden("c1_chab_nn")
+    th = B200Theory(SimpleNamespace(spec=spec, device=None))
+    names = list(spec["params"]["names"])
+    pmin, pmax = np.asarray(spec["params"]["min"]), np.asarray(spec["params"]["max"])
+    x0, res0 = th.cube_from_like_params([])
+    assert not res0 and x0.shape == (len(names),)
+    held = pmin + x0 * (pmax - pmin)
+    for fam in spec["families"].values():
+        idx = np.asarray(fam["param_idx"])
+        for j in np.nonzero(idx >= 0)[0]:
+            assert held[idx[j]] == pytest.approx(float(np.asarray(fam["coeffs"])[j]), rel=1e-14, abs=1e-300)
+    assert held[names.index("As")] == pytest.approx(spec["cosmo"]["As_fid"], rel=1e-14)
+    # every free parameter, three spellings
+    vals = pmin + 0.37 * (pmax - pmin)
+    xa, ra = th.cube_from_like_params(vals)
+    xb, rb = th.cube_from_like_params(dict(zip(names, vals)))
+    xc, rc = th.cube_from_like_params([SimpleNamespace(name=n, value=v) for n, v in zip(names, vals)])
+    np.testing.assert_allclose(xa, 0.37, rtol=1e-12)
+    np.testing.assert_array_equal(xa, xb)
+    np.testing.assert_array_equal(xa, xc)
+    assert ra and rb and rc  # R_coeff parameters are free in this baseline
+    # only the resolution family: resolution on, everything else held
+    rn = [n for n in names if n.startswith("R_coeff")]
+    xr, rr = th.cube_from_like_params({n: 0.01 for n in rn})
+    assert rr and all(xr[names.index(n)] == x0[names.index(n)] for n in names if n not in rn)
+    with pytest.raises(ValueError, match="number of params mismatch"):
+        th.cube_from_like_params({rn[0]: 0.01})
+    with pytest.raises(ValueError, match="not a free parameter"):
+        th.cube_from_like_params({"no_such_parameter": 1.0})
