@@ -9,8 +9,8 @@ Everything else the ``Fitter`` reads from the likelihood (``free_params``, ``dat
 ``theory.model_igm``, plotting helpers, fitter.py:158-1097) keeps working because the object is
 still the reference's; only the seven methods of the hot path (likelihood.py:722-1072) and
 ``theory.get_p1d_kms`` (lya_theory.py:610-814) are replaced on the instance.  Calls that use a
-switch outside the device path (``remove=``, ``return_covar=``, ``hires=``,
-``return_contaminants=``: plot-only) go to the reference's own method.  ``detach`` restores the
+switch outside the device path (``return_covar=``, ``hires=``, ``return_contaminants=``:
+plot-only) go to the reference's own method.  ``detach`` restores the
 instance.
 """
 

@@ -319,8 +319,8 @@ class B200Likelihood(object):
         with rebinning the k grid is always the rebinning grid of the nearest data redshift and
         ``_k_kms`` is ignored (:741-747); there is no unit-cube test here.  ``None`` when the priors reject
         the point, otherwise ``[p1ds(, blob)(, emu_call)]``."""
-        if remove is not None or return_covar:
-            raise NotImplementedError("remove and return_covar are not on the device path")
+        if return_covar:
+            raise NotImplementedError("return_covar is not on the device path")
         rebinned = self.spec["rebin"] is not None
         if zs is None:
             iz = list(range(self.nz))
@@ -331,11 +331,11 @@ class B200Likelihood(object):
             x, apply_res = self.theory.cube_from_like_params([])
         else:
             x, apply_res = np.asarray(values, dtype=float), bool(self.spec["cont"]["apply_resolution"])
-        if values is not None and not custom_k and iz == list(range(self.nz)):
+        if values is not None and not custom_k and not remove and iz == list(range(self.nz)):
             sub = self
         else:
             k_list = self.theory._k_list(_k_kms, len(iz)) if custom_k else None
-            sub = self.theory._context(iz, k_list, apply_res)
+            sub = self.theory._context(iz, k_list, apply_res, remove)
         p, emu = sub.get_p1d_kms_batch(x[None, :], apply_hull=apply_hull, return_emu_params=True, cube_test=False)
         if np.isnan(p[0]).all():
             return None

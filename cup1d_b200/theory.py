@@ -21,8 +21,9 @@ likelihood uses.  The reference's conventions are kept:
   (:647-670); otherwise ``[p1ds(, blob)(, emu_call)]``, a bare list of per-z arrays when
   nothing else is requested; ``return_blob`` defaults to True as in the reference.
 
-Not available on the device path: ``return_covar``, ``hires``, ``remove`` and
-``return_contaminants`` (plot-only switches).
+``remove`` (a dict of metal-term switches, si_mult.py:185-206, si_add.py:156-159) compiles a derived
+context with those switches.  Not available on the device path: ``return_covar``, ``hires`` and
+``return_contaminants`` (plot-only).
 """
 
 from __future__ import annotations
@@ -34,10 +35,11 @@ import numpy as np
 BLOB_NAMES = ("Delta2_star", "n_star", "alpha_star", "f_star", "g_star", "H0")
 
 
-def grid_spec(spec, iz_sel, k_kms, apply_resolution):
+def grid_spec(spec, iz_sel, k_kms, apply_resolution, remove=None):
     """The likelihood's spec restricted to the redshift bins ``iz_sel`` with ``k_kms`` (one array
     per bin) as the evaluation grid: no rebinning, unit metric, zero data.  ``k_kms=None`` keeps the
-    likelihood's own k bins and rebinning tables for those redshifts."""
+    likelihood's own k bins and rebinning tables for those redshifts.  ``remove`` overrides the switch
+    tables of the metal models for this context (si_mult.py:185-206, si_add.py:156-159)."""
     iz = np.asarray(iz_sel, dtype=int)
     s = dict(spec)
     s["zs"] = np.asarray(spec["zs"], dtype=float)[iz]
@@ -48,6 +50,11 @@ def grid_spec(spec, iz_sel, k_kms, apply_resolution):
     s["igm_fid"] = {k: np.asarray(v, dtype=float)[iz] for k, v in spec["igm_fid"].items()}
     cont = dict(spec["cont"])
     cont["apply_resolution"] = bool(apply_resolution)
+    if remove:
+        for model in ("si_mult", "si_add"):
+            m = dict(cont[model])
+            m["off"] = {k: (remove[k] if k in remove else v) for k, v in cont[model]["off"].items()}
+            cont[model] = m
     s["cont"] = cont
     if k_kms is None:
         ks = [np.asarray(spec["data"]["k_kms"][i], dtype=float) for i in iz]
@@ -148,13 +155,14 @@ class B200Theory(object):
             iz.append(int(hit[0]))
         return iz
 
-    def _context(self, iz, k_kms, apply_res):
+    def _context(self, iz, k_kms, apply_res, remove=None):
         from .likelihood import B200Likelihood
 
-        key = (tuple(iz), bool(apply_res), None if k_kms is None else tuple(np.ascontiguousarray(k, dtype=float).tobytes() for k in k_kms))
+        rkey = None if not remove else tuple(sorted((str(k), float(v)) for k, v in remove.items()))
+        key = (tuple(iz), bool(apply_res), None if k_kms is None else tuple(np.ascontiguousarray(k, dtype=float).tobytes() for k in k_kms), rkey)
         sub = self._cache.get(key)
         if sub is None:
-            sub = B200Likelihood(grid_spec(self._like.spec, iz, k_kms, apply_res), device=self._like.device.index, _with_theory=False)
+            sub = B200Likelihood(grid_spec(self._like.spec, iz, k_kms, apply_res, remove), device=self._like.device.index, _with_theory=False)
             self._cache[key] = sub
             while len(self._cache) > self.MAX_CACHED:
                 _, old = self._cache.popitem(last=False)
@@ -193,13 +201,13 @@ class B200Theory(object):
     def get_p1d_kms(self, zs, k_kms, like_params=[], return_covar=False, return_blob=True, return_emu_params=False,
                     apply_hull=True, hires=False, remove=None, return_contaminants=False):
         """lya_theory.py:610-814"""
-        if return_covar or hires or remove is not None or return_contaminants:
-            raise NotImplementedError("return_covar, hires, remove and return_contaminants are not on the device path")
+        if return_covar or hires or return_contaminants:
+            raise NotImplementedError("return_covar, hires and return_contaminants are not on the device path")
         vals, apply_res = self._values_from_like_params(like_params)
         x = (vals - self._pmin) / (self._pmax - self._pmin)
         iz = self._z_index(zs)
         k_list = self._k_list(k_kms, len(iz))
-        sub = self._context(iz, k_list, apply_res)
+        sub = self._context(iz, k_list, apply_res, remove)
         p, emu = sub.get_p1d_kms_batch(x[None, :], apply_hull=apply_hull, return_emu_params=True, cube_test=False)
         if np.isnan(p[0]).all():
             return None

@@ -154,3 +154,28 @@ def test_theory_like_params_mapping(golden):
         th.cube_from_like_params({rn[0]: 0.01})
     with pytest.raises(ValueError, match="not a free parameter"):
         th.cube_from_like_params({"no_such_parameter": 1.0})
+
+
+def test_remove_switches_through_a_derived_spec(golden):
+    """``remove=`` (si_mult.py:185-206, si_add.py:156-159) is served by a derived spec with the metal switch
+    tables overridden: compiled and run through the NumPy mirror, it must match the oracle's remove path"""
+    import numpy as np
+
+    import devsim
+    from cup1d_b200.compile import compile_spec
+    from cup1d_b200.theory import grid_spec
+    from oracle.model import OracleLikelihood
+
+    spec, ref = golden("c1_chab_nn")
+    ora = OracleLikelihood(spec)
+    x = ref["x"][:6]
+    nz = len(spec["zs"])
+    for remove in ({"SiIII_Lya": 0}, {"SiIIa_Lya": 0, "SiIIb_Lya": 0}, {"SiIIb_SiIIa": 0}, {"SiIII_SiIIa": 0, "SiIIc_Lya": 1}):
+        cfg, F = compile_spec(grid_spec(spec, np.arange(nz), None, spec["cont"]["apply_resolution"], remove))
+        out = devsim.simulate(cfg, F, x)
+        changed = False
+        for i, v in enumerate(x):
+            want = np.concatenate(ora.get_p1d_kms(values=v.copy(), remove=remove)[0])
+            assert np.max(np.abs(out["p1d"][i] / want - 1)) < 1e-11
+            changed |= bool(np.max(np.abs(want / ref["p1d"][i] - 1)) > 1e-6)
+        assert changed  # the switch does something

@@ -53,7 +53,11 @@ def test_attach_rebinds_the_hot_path(golden):
     pt = like.theory.get_p1d_kms(zs, ks, like_params=glike.parameters_from_sampling_point(x[i]), return_blob=False)
     assert np.max(np.abs(np.concatenate(pt) / ref["p1d"][i] - 1)) <= 1e-5
     # plot-only switches stay with the object's own methods
-    assert like.get_p1d_kms(values=x[i].copy(), remove={"SiIII_Lya": 0}) == "reference get_p1d_kms"
+    assert like.get_p1d_kms(values=x[i].copy(), return_covar=True) == "reference get_p1d_kms"
+    # ... while remove= is served by a derived device context
+    pr = like.get_p1d_kms(values=x[i].copy(), remove={"SiIII_Lya": 0})[0]
+    want = np.concatenate(ora.get_p1d_kms(values=x[i].copy(), remove={"SiIII_Lya": 0})[0])
+    assert np.max(np.abs(np.concatenate(pr) / want - 1)) <= 1e-5 and np.max(np.abs(want / ref["p1d"][i] - 1)) > 1e-6
     assert like.theory.get_p1d_kms(zs, ks, like_params=[], return_contaminants=True) == "reference theory"
     with pytest.raises(RuntimeError):
         attach(like, device=0, spec=spec)
