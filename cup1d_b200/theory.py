@@ -169,6 +169,10 @@ class B200Theory(object):
                 old.close()
         else:
             self._cache.move_to_end(key)
+        # derived contexts follow the emulator arithmetic of the likelihood they belong to
+        mode = getattr(self._like, "emulator_precision", "fp64")
+        if sub.emulator_precision != mode:
+            sub.set_emulator_precision(mode)
         return sub
 
     def close(self):
