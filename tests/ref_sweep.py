@@ -59,6 +59,12 @@ for it in range(int(sys.argv[1]) if len(sys.argv)>1 else 24):
             like,args = rh.build_reference_likelihood(emu, data_ns(dvec, cov), rebin_k=rebin_k, fit_type=fit_type, name_variation=var, emu_cov_type=("full" if full else "block"), **kw)
             x = mg.walkers(like, 5, 5, 2, 7, width=0.06)
             ref = np.array([like.log_prob_and_blobs(v.copy()) for v in x])
+            zm = [zs[0], zs[-1]]
+            refz = np.full(len(x), np.nan)
+            if not kw.get("ic_correction"):  # the reference itself fails for zmask + ic_correction (model_contaminants.py:319)
+                refz = np.array([like.log_prob(v.copy(), zmask=zm) for v in x])
+            refp = [like.get_p1d_kms(values=v.copy()) if ((v <= 1).all() and (v >= 0).all()) else None for v in x]
+            refll = [like.get_log_like(v.copy(), return_blob=True) for v in x]
         spec = spec_from_likelihood(like)
         ora = OracleLikelihood(spec)
         got = ora.log_prob_and_blobs_many(x)
@@ -70,6 +76,24 @@ for it in range(int(sys.argv[1]) if len(sys.argv)>1 else 24):
         sim = devsim.simulate(cfg, F, x)
         err2 = np.max(np.abs(sim["lnp"][ok]-ref[ok,0])/np.maximum(1,np.abs(ref[ok,0]))) if ok.any() else 0
         same2 = np.array_equal(sim["lnp"][~ok], ref[~ok,0])
+        # z-masked log-posterior, model P1D and per-z log-likelihoods
+        if not np.isnan(refz).any():
+            gz = np.array([ora.log_prob(v.copy(), zmask=zm) for v in x])
+            sz = devsim.simulate(cfg, F, x, zmask=np.array([int(np.any(np.abs(np.array(zm) - z) < 1e-3)) for z in zs]))["lnp"]
+            okz = refz > -1e99
+            err = max(err, np.max(np.abs(gz[okz]-refz[okz])/np.maximum(1,np.abs(refz[okz]))) if okz.any() else 0)
+            err2 = max(err2, np.max(np.abs(sz[okz]-refz[okz])/np.maximum(1,np.abs(refz[okz]))) if okz.any() else 0)
+            same_rej &= np.array_equal(gz[~okz], refz[~okz]); same2 &= np.array_equal(sz[~okz], refz[~okz])
+        for i, v in enumerate(x):
+            if refp[i] is None:
+                continue
+            pr = np.concatenate(refp[i][0])
+            po = np.concatenate(ora.get_p1d_kms(values=v.copy())[0])
+            err = max(err, np.max(np.abs(po/pr-1))); err2 = max(err2, np.max(np.abs(sim["p1d"][i]/pr-1)))
+            if np.isfinite(refll[i][0]):
+                lo = ora.get_log_like(v.copy(), return_blob=True)
+                err = max(err, np.max(np.abs(np.asarray(lo[1]).reshape(-1)[:nz] - np.asarray(refll[i][1]).reshape(-1)[:nz]) / np.maximum(1, np.abs(np.asarray(refll[i][1]).reshape(-1)[:nz]))))
+                err2 = max(err2, np.max(np.abs(sim["lnl_z"][i] - np.asarray(refll[i][1]).reshape(-1)[:nz]) / np.maximum(1, np.abs(np.asarray(refll[i][1]).reshape(-1)[:nz]))))
         flag = "ok  " if (err < 1e-10 and same_rej and err2 < 1e-9 and same2) else "BAD "
         if flag != "ok  ": nfail += 1
         print("%s %-100s ndim=%3d ok=%2d oracle %.1e mirror %.1e rej %s %s" % (flag, name, x.shape[1], ok.sum(), err, err2, same_rej, same2), flush=True)
