@@ -297,20 +297,20 @@ class B200Likelihood(object):
         return out
 
     # ---- scalar API with the reference's conventions ------------------
-    def _values_or_fid(self, values):
-        """values=None means like_params=[] in the reference (likelihood.py:749-753): every model at the
-        coefficients it holds and no resolution term.  On the likelihood's own context that is the same
-        evaluation whenever the held R_coeff coefficients are zero (the term is then exactly 1)."""
-        if values is None:
-            x, _ = self.theory.cube_from_like_params([])
-            names = self.free_param_names
-            held_res = [self.theory._held[i] for i, n in enumerate(names) if n.startswith("R_coeff")]
-            if self.spec["cont"]["apply_resolution"] and np.any(np.asarray(held_res) != 0.0):
-                raise NotImplementedError("values=None with non-zero R_coeff coefficients held by the resolution model")
-            if (x > 1).any() or (x < 0).any():
-                raise NotImplementedError("values=None with model coefficients outside the priors")
-            return x
-        return np.asarray(values, dtype=float)
+    def _eval_target(self, values):
+        """(cube point, likelihood object to evaluate it on, cube test).  ``values=None`` means
+        ``like_params=[]`` in the reference (likelihood.py:749-753): every model at the coefficients it holds,
+        no resolution term and no unit-cube test.  On this context that is the same evaluation whenever the
+        held R_coeff coefficients are zero (the term is then exactly 1); otherwise a derived context without
+        the resolution term, with the same data and metric, serves the call."""
+        if values is not None:
+            return np.asarray(values, dtype=float), self, True
+        x, _ = self.theory.cube_from_like_params([])
+        names = self.free_param_names
+        held_res = [self.theory._held[i] for i, n in enumerate(names) if n.startswith("R_coeff")]
+        if self.spec["cont"]["apply_resolution"] and np.any(np.asarray(held_res) != 0.0):
+            return x, self.theory._context(list(range(self.nz)), None, False, None, keep_data=True), False
+        return x, self, False
 
     def get_p1d_kms(self, zs=None, _k_kms=None, values=None, return_covar=False, return_blob=False,
                     return_emu_params=False, apply_hull=True, remove=None):
@@ -349,13 +349,16 @@ class B200Likelihood(object):
 
     def get_log_like(self, values=None, ignore_log_det_cov=True, return_blob=False, zmask=None):
         """likelihood.py:822-972: [log_like, log_like_all[1, Nz](, blob)]"""
-        v = self._values_or_fid(values)
-        lnp, blobs, lnl_z, chi2, _ = self._evaluate(v[None, :], want_z=True, want_chi2=True, zmask=zmask)
-        if not ignore_log_det_cov:
-            lnl, lz = self.get_log_like_batch(v[None, :], ignore_log_det_cov=False, zmask=zmask)
-            ll, llz = float(lnl[0]), lz[0]
-        else:
-            ll, llz = float(-0.5 * chi2[0]), lnl_z[0].cpu().numpy()
+        v, tgt, cube_test = self._eval_target(values)
+        lnp, blobs, lnl_z, chi2, _ = tgt._evaluate(v[None, :], want_z=True, want_chi2=True, zmask=zmask, cube_test=cube_test)
+        ll, llz = float(-0.5 * chi2[0]), lnl_z[0].cpu().numpy()
+        if not ignore_log_det_cov and np.isfinite(ll):
+            # log det C per redshift and of the dense matrix (likelihood.py:950, 962)
+            sel = np.ones(self.nz, dtype=bool)
+            if zmask is not None:
+                sel = np.array([bool(np.any(np.abs(np.atleast_1d(zmask) - z) < 1e-3)) for z in self.zs])
+            llz = llz - 0.5 * self._logdet_z * sel
+            ll = ll - 0.5 * self._logdet_full if (self.has_full and zmask is None) else float(np.sum(llz))
         if not np.isfinite(ll):
             out = [-np.inf, -np.inf]
             if return_blob:

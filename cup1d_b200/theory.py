@@ -35,11 +35,13 @@ import numpy as np
 BLOB_NAMES = ("Delta2_star", "n_star", "alpha_star", "f_star", "g_star", "H0")
 
 
-def grid_spec(spec, iz_sel, k_kms, apply_resolution, remove=None):
+def grid_spec(spec, iz_sel, k_kms, apply_resolution, remove=None, keep_data=False):
     """The likelihood's spec restricted to the redshift bins ``iz_sel`` with ``k_kms`` (one array
     per bin) as the evaluation grid: no rebinning, unit metric, zero data.  ``k_kms=None`` keeps the
     likelihood's own k bins and rebinning tables for those redshifts.  ``remove`` overrides the switch
-    tables of the metal models for this context (si_mult.py:185-206, si_add.py:156-159)."""
+    tables of the metal models for this context (si_mult.py:185-206, si_add.py:156-159).  ``keep_data``
+    (own grid only) keeps the data vector and the inverse covariances of the selected redshifts, the dense
+    one when every redshift is selected."""
     iz = np.asarray(iz_sel, dtype=int)
     s = dict(spec)
     s["zs"] = np.asarray(spec["zs"], dtype=float)[iz]
@@ -71,6 +73,16 @@ def grid_spec(spec, iz_sel, k_kms, apply_resolution, remove=None):
         "full_Pk_kms": None,
         "full_icov": None,
     }
+    if keep_data:
+        if k_kms is not None:
+            raise ValueError("keep_data needs the likelihood's own k bins")
+        d = spec["data"]
+        s["data"]["Pk_kms"] = [np.asarray(d["Pk_kms"][i], dtype=float) for i in iz]
+        s["data"]["icov"] = [np.asarray(d["icov"][i], dtype=float) for i in iz]
+        if d["full_icov"] is not None and list(iz) == list(range(len(spec["zs"]))):
+            s["data"]["full_Pk_kms"] = d["full_Pk_kms"]
+            s["data"]["full_icov"] = d["full_icov"]
+        return s
     params = dict(spec["params"])
     params["gauss_sigma_cube"] = None
     s["params"] = params
@@ -155,14 +167,14 @@ class B200Theory(object):
             iz.append(int(hit[0]))
         return iz
 
-    def _context(self, iz, k_kms, apply_res, remove=None):
+    def _context(self, iz, k_kms, apply_res, remove=None, keep_data=False):
         from .likelihood import B200Likelihood
 
         rkey = None if not remove else tuple(sorted((str(k), float(v)) for k, v in remove.items()))
-        key = (tuple(iz), bool(apply_res), None if k_kms is None else tuple(np.ascontiguousarray(k, dtype=float).tobytes() for k in k_kms), rkey)
+        key = (tuple(iz), bool(apply_res), None if k_kms is None else tuple(np.ascontiguousarray(k, dtype=float).tobytes() for k in k_kms), rkey, bool(keep_data))
         sub = self._cache.get(key)
         if sub is None:
-            sub = B200Likelihood(grid_spec(self._like.spec, iz, k_kms, apply_res, remove), device=self._like.device.index, _with_theory=False)
+            sub = B200Likelihood(grid_spec(self._like.spec, iz, k_kms, apply_res, remove, keep_data), device=self._like.device.index, _with_theory=False)
             self._cache[key] = sub
             while len(self._cache) > self.MAX_CACHED:
                 _, old = self._cache.popitem(last=False)

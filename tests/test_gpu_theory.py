@@ -84,3 +84,45 @@ def test_theory_get_p1d_kms_matches_the_reference(name):
     with pytest.raises(ValueError):
         th.get_p1d_kms([7.7], [kc[0]], like_params=[])
     like.close()
+
+
+def test_values_none_follows_the_reference_rules(golden):
+    """values=None = like_params=[] (likelihood.py:749-753): the models' own coefficients, no resolution term,
+    no cube test - also when the resolution model holds non-zero coefficients (derived context with the same
+    data and metric); the scalar log-det path equals the batched one"""
+    import copy
+
+    from cup1d_b200.likelihood import B200Likelihood
+    from oracle.model import OracleLikelihood
+
+    spec, ref = golden("c1_chab_nn")
+    spec = copy.deepcopy(spec)
+    spec["families"]["R_coeff"]["coeffs"] = np.asarray(spec["families"]["R_coeff"]["coeffs"], dtype=float) + 0.03
+    like = B200Likelihood(spec, device=0)
+    spec0 = copy.deepcopy(spec)
+    spec0["cont"]["apply_resolution"] = False
+    ora0 = OracleLikelihood(spec0)
+    for ign in (True, False):
+        got = like.get_log_like(None, ignore_log_det_cov=ign, return_blob=True)
+        want = ora0.get_log_like(None, ignore_log_det_cov=ign, return_blob=True)
+        assert abs(got[0] - want[0]) <= 1e-4 + 1e-11 * abs(want[0])
+        np.testing.assert_allclose(got[1][0], want[1][0], rtol=1e-10, atol=1e-4)
+        np.testing.assert_allclose(got[2], want[2], rtol=1e-12)
+    assert abs(like.get_chi2() - ora0.get_chi2()) <= 2e-4 + 1e-11 * abs(ora0.get_chi2())
+    p = np.concatenate(like.get_p1d_kms()[0])
+    assert np.max(np.abs(p / np.concatenate(ora0.get_p1d_kms()[0]) - 1)) <= RTOL_P1D
+    # scalar log-det path == batched
+    ora = OracleLikelihood(spec)
+    zm = [spec["zs"][1], spec["zs"][3]]
+    for v in ref["x"][:5]:
+        for zmask in (None, zm):
+            a = like.get_log_like(v.copy(), ignore_log_det_cov=False, zmask=zmask)
+            b = like.get_log_like_batch(v[None, :], ignore_log_det_cov=False, zmask=zmask)
+            e = ora.get_log_like(v.copy(), ignore_log_det_cov=False, zmask=zmask)
+            if np.isinf(e[0]):
+                assert np.isinf(a[0])
+                continue
+            assert a[0] == pytest.approx(float(b[0][0]), rel=1e-14)
+            np.testing.assert_allclose(a[1][0], b[1][0], rtol=1e-14)
+            assert abs(a[0] - e[0]) <= 1e-4 + 1e-11 * abs(e[0])
+    like.close()
