@@ -13,7 +13,7 @@ import numpy as np
 
 from . import compile as _cmp
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 LIB_NAME = "libcup1d_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
@@ -21,12 +21,13 @@ FLAG_ZMASK = 1
 FLAG_NO_HULL = 2
 FLAG_EMU_TC = 4
 FLAG_NO_CUBE = 8
+FLAG_EMU_I8 = 16
 
 # every symbol include/cup1d_b200.h declares
 SYMBOLS = (
     "c1d_abi_version", "c1d_ctx_create", "c1d_ctx_upload", "c1d_ctx_finalize",
     "c1d_loglike_batch", "c1d_p1d_batch", "c1d_emulator_only", "c1d_loglike_batch_host",
-    "c1d_sampler_run", "c1d_philox_u01", "c1d_launch_count", "c1d_set_timing", "c1d_get_timing", "c1d_tc_selftest", "c1d_ctx_destroy", "c1d_last_error",
+    "c1d_sampler_run", "c1d_philox_u01", "c1d_emulator_paths", "c1d_launch_count", "c1d_set_timing", "c1d_get_timing", "c1d_tc_selftest", "c1d_ctx_destroy", "c1d_last_error",
 )
 
 
@@ -85,6 +86,8 @@ def load_library(path=None):
     lib.c1d_sampler_run.restype = C.c_int
     lib.c1d_philox_u01.argtypes = [C.c_uint64, i64, C.c_int, i64, C.c_int, C.POINTER(C.c_double)]
     lib.c1d_philox_u01.restype = C.c_int
+    lib.c1d_emulator_paths.argtypes = [vp]
+    lib.c1d_emulator_paths.restype = C.c_int
     lib.c1d_launch_count.argtypes = [vp]
     lib.c1d_launch_count.restype = i64
     lib.c1d_set_timing.argtypes = [vp, C.c_int]
@@ -165,6 +168,10 @@ class Context(object):
         rc = self.lib.c1d_sampler_run(self.handle, x_ptr, lnp_ptr, blobs_ptr, W, nsteps, step0, seed, a, int(init), thin,
                                       chain_ptr, lnp_chain_ptr, blobs_chain_ptr, naccept_ptr, flags, stream)
         self._check(rc, "c1d_sampler_run")
+
+    def emulator_paths(self):
+        """bit mask: 1 float64, FLAG_EMU_TC 3xTF32, FLAG_EMU_I8 int8 digit slices"""
+        return int(self.lib.c1d_emulator_paths(self.handle))
 
     def launch_count(self):
         return int(self.lib.c1d_launch_count(self.handle))

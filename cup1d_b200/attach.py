@@ -36,7 +36,7 @@ def _route(device_method, reference_method):
     return call
 
 
-def attach(like, device=None, emulator_precision="fp64", spec=None):
+def attach(like, device=None, emulator_precision="auto", spec=None):
     """Compile ``like`` (or the given spec of it) and rebind its hot-path methods; returns the
     ``B200Likelihood``, also kept as ``like._b200``.  The batched entry points are added to the instance."""
     if getattr(like, "_b200", None) is not None:

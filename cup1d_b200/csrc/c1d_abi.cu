@@ -227,6 +227,8 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
     if (rc != C1D_OK) return rc;
     rc = c1d_tc_prepare(ctx);  // builds the tensor-core weight images (no-op when unsupported)
     if (rc != C1D_OK) return rc;
+    rc = c1d_i8_prepare(ctx);  // int8 digit planes of the weights (leaves the path unavailable for unsupported shapes)
+    if (rc != C1D_OK) return rc;
   }
   return C1D_OK;
 }
@@ -437,6 +439,19 @@ extern "C" int c1d_loglike_batch_host(c1d_ctx* ctx, const double* x_host, int64_
   return C1D_OK;
 }
 
+extern "C" int c1d_emulator_paths(const c1d_ctx* ctx) {
+  if (!ctx || !ctx->finalized) return 0;
+  int m = 0;
+  if (ctx->cfg.emu_kind == 0) {
+    m |= 1;                                // float64 (DMMA)
+    if (ctx->tc_state) m |= (int)C1D_FLAG_EMU_TC;
+    if (c1d_i8_available(ctx)) m |= (int)C1D_FLAG_EMU_I8;
+  } else {
+    m |= 1;
+  }
+  return m;
+}
+
 extern "C" int c1d_set_timing(c1d_ctx* ctx, int enable) {
   if (!ctx) return C1D_ERR_ARG;
   C1D_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
@@ -464,6 +479,7 @@ extern "C" int c1d_ctx_destroy(c1d_ctx* ctx) {
   cudaSetDevice(ctx->cfg.device);
   cudaDeviceSynchronize();
   c1d_tc_destroy(ctx);
+  c1d_i8_destroy(ctx);
   c1d_mlp64_destroy(ctx);
   c1d_p1dw_destroy(ctx);
   ws_free(ctx);

@@ -101,6 +101,8 @@ struct c1d_ctx {
   int tzw;
   // tensor-core emulator path (c1d_mlp_tc.cu)
   void* tc_state;
+  // int8 digit-slice tensor-core emulator path (c1d_mlp_i8.cu)
+  void* i8_state;
   // fp64 tensor-core emulator path (c1d_mlp_f64.cu)
   void* mlp64_state;
   // walker-per-lane stage 3 (c1d_p1d_lanes.cu): per-fine-point rebinning maps, null when not applicable
@@ -149,3 +151,10 @@ int c1d_tc_prepare(c1d_ctx* ctx);
 int c1d_tc_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out, int out_stride,
                   cudaStream_t s);
 void c1d_tc_destroy(c1d_ctx* ctx);
+
+// int8 digit-slice tensor-core MLP (c1d_mlp_i8.cu): prepare leaves the path unavailable for unsupported shapes
+int c1d_i8_prepare(c1d_ctx* ctx);
+int c1d_i8_available(const c1d_ctx* ctx);
+int c1d_i8_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out, int out_stride,
+                  cudaStream_t s);
+void c1d_i8_destroy(c1d_ctx* ctx);

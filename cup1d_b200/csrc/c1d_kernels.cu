@@ -478,6 +478,7 @@ int c1d_launch_emulator(c1d_ctx* ctx, const double* emu_in, int64_t nrows, doubl
                         int out_stride, uint32_t flags, cudaStream_t s) {
   if (nrows <= 0) return C1D_OK;
   if (ctx->cfg.emu_kind == 0) {
+    if (flags & C1D_FLAG_EMU_I8) return c1d_i8_launch(ctx, emu_in, nrows, out, out_stride, s);
     if (flags & C1D_FLAG_EMU_TC) return c1d_tc_launch(ctx, emu_in, nrows, out, out_stride, s);
     return c1d_mlp64_launch(ctx, emu_in, nrows, out, out_stride, s);
   } else {

@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "c1d_internal.h"
+#include "c1d_tc_common.cuh"
 
 namespace {
 
@@ -101,140 +102,7 @@ struct TcState {
   int cluster;  // CTAs per cluster sharing the weight stream (C1D_TC_CLUSTER: 1, 2 or 4; default 1)
 };
 
-// ------------------------------------------------------------------------------------
-// PTX helpers
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-      "@P1 bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-// one slice of a weight unit, written to the same shared-memory offset of every CTA in cta_mask;
-// each destination CTA's mbarrier (same offset) receives the complete_tx
-__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(cta_mask)
-               : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
-  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset, bits [32,46)
-  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-  return d;
-}
-// K-major, SWIZZLE_64B (64-byte rows: 16 tf32), 8-row groups 512 B apart
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;                          // SWIZZLE_64B
-  return d;
-}
-// instruction descriptor: tf32 x tf32 -> f32, A and B K-major, M = 128
-__device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
-}
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-
-// byte offset of (row, 16-byte group g of k) inside one 128-row x 32-k SWIZZLE_128B chunk
-__device__ __host__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t g) {
-  return (row >> 3) * 1024u + (row & 7u) * 128u + ((g ^ (row & 7u)) << 4);
-}
-
-// byte offset of (row, 16-byte group g in 0..3) inside a SWIZZLE_64B tile of 64-byte rows
-__device__ __host__ __forceinline__ uint32_t sw64_off(uint32_t row, uint32_t g) {
-  return (row >> 3) * 512u + (row & 7u) * 64u + ((g ^ ((row >> 1) & 3u)) << 4);
-}
+using namespace c1d_tc;  // PTX helpers: c1d_tc_common.cuh
 
 // split 16 fp32 activations into tf32 hi (to shared memory, swizzled) and lo (to TMEM)
 __device__ __forceinline__ void store_act16(uint32_t a_smem, uint32_t tmem_lane_base, uint32_t row, int col0, const float* v) {
@@ -275,7 +143,8 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
 
   __shared__ long long dbg_t[2 * TC_MAX_TL];
-  const int tid = threadIdx.x, warp = tid >> 5;
+  // warp index through a shuffle: warp-uniform role branches keep the MMA issuer's descriptors in uniform registers
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   // CTAs of a cluster walk the same weight stream in lockstep: every unit is fetched from L2 once
   // per cluster (each CTA loads 1/csize of it and multicasts the slice to all)
   const uint32_t csize = cluster_nctarank(), crank = cluster_ctarank();
@@ -297,7 +166,7 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
   __syncthreads();
   cluster_sync_all();  // barriers of every CTA are initialised before any remote arrive / multicast
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_p;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_p, 0);
 
   const int64_t ntiles = (nrows + TC_ROWS - 1) / TC_ROWS;
   // the same trip count in every CTA keeps the cluster in lockstep (surplus tiles hold no rows)
@@ -399,8 +268,8 @@ k_mlp_tc(TcParams p, const double* __restrict__ emu_in, int64_t nrows, double* _
   } else if (warp == TC_EPI_WARPS) {
     // ================================ MMA issuer ================================
     // the whole warp runs the loop (warp-uniform values stay in uniform registers, the unit
-    // table comes from the kernel-parameter constant bank); lane 0 issues
-    const bool leader = (tid & 31) == 0;
+    // table comes from the kernel-parameter constant bank); one elected lane issues
+    const bool leader = elect_one();
     uint32_t a_phase = 0;
     uint32_t g = 0;  // running unit count: barrier pair g % TC_NBAR, phase (g / TC_NBAR) & 1
     for (int64_t it = 0; it < tiles_per_cta; ++it) {

@@ -32,11 +32,14 @@ BLOB_NAMES = ("Delta2_star", "n_star", "alpha_star", "f_star", "g_star", "H0")
 
 
 class B200Likelihood(object):
-    def __init__(self, like, device=None, emulator_precision="fp64", _with_theory=True):
+    def __init__(self, like, device=None, emulator_precision="auto", _with_theory=True):
         """like: a reference ``Likelihood`` (any object with its attributes) or
-        a model spec dict.  emulator_precision: "fp64" (CUDA cores, exact
-        parity with an fp64 evaluation of the weights) or "3xtf32"
-        (tcgen05 tensor cores, fp32-class accuracy; NN emulators only)."""
+        a model spec dict.  emulator_precision (NN emulators): "i8" = tcgen05 tensor
+        cores, int8 digit slices with exact int32 accumulation and float64 recombination
+        (log-likelihood within 1e-4 of a float64 evaluation of the weights); "fp64" = the
+        fp64 tensor cores (DMMA), bit-level parity; "3xtf32" = tcgen05 in 3xTF32
+        (float32-class accuracy, misses the log-likelihood tolerance); "auto" (default)
+        = "i8" where the network shape allows it, else "fp64"."""
         if not torch.cuda.is_available():
             raise RuntimeError("cup1d_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.spec = like if isinstance(like, dict) else spec_from_likelihood(like)
@@ -74,12 +77,18 @@ class B200Likelihood(object):
 
     # ------------------------------------------------------------------
     def set_emulator_precision(self, mode):
-        if mode not in ("fp64", "3xtf32"):
-            raise ValueError("emulator_precision must be 'fp64' or '3xtf32'")
-        if mode == "3xtf32" and self.spec["emulator"]["kind"] != "nn":
-            raise ValueError("the tensor-core path is for NN emulators")
+        if mode not in ("auto", "fp64", "i8", "3xtf32"):
+            raise ValueError("emulator_precision must be 'auto', 'i8', 'fp64' or '3xtf32'")
+        paths = self.ctx.emulator_paths()
+        if mode == "auto":
+            mode = "i8" if (paths & _abi.FLAG_EMU_I8) else "fp64"
+        if mode in ("3xtf32", "i8") and self.spec["emulator"]["kind"] != "nn":
+            raise ValueError("the tcgen05 paths are for NN emulators")
+        if mode == "i8" and not (paths & _abi.FLAG_EMU_I8):
+            raise ValueError("the int8 digit-slice kernel does not support this network shape (a layer wider than 192 "
+                             "must be followed by one of at most 64); use 'fp64'")
         self.emulator_precision = mode
-        self._base_flags = _abi.FLAG_EMU_TC if mode == "3xtf32" else 0
+        self._base_flags = {"fp64": 0, "3xtf32": _abi.FLAG_EMU_TC, "i8": _abi.FLAG_EMU_I8}[mode]
 
     def set_data(self, full_Pk_kms):
         """Replace the data vector (mock generation)"""

@@ -41,7 +41,7 @@ def finish_workload_spec(name, spec, p_truth):
     return synth.attach_mock_data(spec, p_truth, seed_cov=14, seed_noise=15, add_noise=(name != "c1"))
 
 
-def make_likelihood(name, device=0, emulator_precision="fp64"):
+def make_likelihood(name, device=0, emulator_precision="auto"):
     """(spec, B200Likelihood) with mock data generated on the device"""
     from .likelihood import B200Likelihood
 

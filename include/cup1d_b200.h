@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define C1D_ABI_VERSION 5
+#define C1D_ABI_VERSION 6
 #define C1D_MAX_LAYERS 12
 #define C1D_MAX_EMU 8     /* emulator inputs */
 #define C1D_MAX_COEF 8    /* polynomial coefficients the emulator returns */
@@ -160,7 +160,9 @@ typedef struct c1d_ctx c1d_ctx;
 #define C1D_FLAG_ZMASK 1u     /* use the uploaded C1D_F_ZMASK: per-z chi2 of the selected bins only (likelihood.py:844-863, 953-954) */
 #define C1D_FLAG_NO_HULL 2u   /* apply_hull=False (likelihood.py:730) */
 #define C1D_FLAG_NO_CUBE 8u   /* no unit-cube test: Theory.get_p1d_kms evaluates any parameter values (lya_theory.py:610-814; the test lives in Likelihood, likelihood.py:989-994) */
-#define C1D_FLAG_EMU_TC 4u    /* emulator layers on tcgen05 tensor cores (3xTF32) instead of fp64 CUDA cores */
+#define C1D_FLAG_EMU_TC 4u    /* emulator layers on tcgen05 tensor cores in 3xTF32 (float32-class accuracy: misses the 1e-4 log-likelihood tolerance) */
+#define C1D_FLAG_EMU_I8 16u   /* emulator layers on tcgen05 tensor cores as int8 digit slices with exact int32 accumulation and float64
+                                 recombination (float64-class accuracy); without either flag the layers run on the fp64 tensor cores (DMMA) */
 
 int c1d_abi_version(void);
 
@@ -225,6 +227,10 @@ int c1d_sampler_run(c1d_ctx* ctx, double* x_dev, double* lnp_dev, double* blobs_
 /* the sampler's random numbers on the host (tests replay a chain with them):
  * out2 = two uniforms in (0,1) of counter (step, half, walker, which) */
 int c1d_philox_u01(uint64_t seed, int64_t step, int half, int64_t walker, int which, double* out2);
+
+/* emulator arithmetic available to a finalised context: bit 0 = float64, C1D_FLAG_EMU_TC, C1D_FLAG_EMU_I8
+ * (the int8 digit-slice kernel needs an MLP whose layers wider than 192 are followed by one of at most 64) */
+int c1d_emulator_paths(const c1d_ctx* ctx);
 
 /* number of kernels launched by this context since creation */
 int64_t c1d_launch_count(const c1d_ctx* ctx);

@@ -34,7 +34,7 @@ def test_attach_rebinds_the_hot_path(golden):
 
     spec, ref = golden("c1_chab_nn")
     like = _FakeLike()
-    glike = attach(like, device=0, spec=spec)
+    glike = attach(like, device=0, spec=spec, emulator_precision="fp64")
     x = ref["x"]
     ora = OracleLikelihood(spec)
     i = int(np.argmax(ref["lnprob_blobs"][:, 0]))
@@ -60,7 +60,7 @@ def test_attach_rebinds_the_hot_path(golden):
     assert np.max(np.abs(np.concatenate(pr) / want - 1)) <= 1e-5 and np.max(np.abs(want / ref["p1d"][i] - 1)) > 1e-6
     assert like.theory.get_p1d_kms(zs, ks, like_params=[], return_contaminants=True) == "reference theory"
     with pytest.raises(RuntimeError):
-        attach(like, device=0, spec=spec)
+        attach(like, device=0, spec=spec, emulator_precision="fp64")
     detach(like)
     assert like.log_prob_and_blobs(x[i]) == "reference log_prob_and_blobs"
     assert like.theory.get_p1d_kms(zs, ks) == "reference theory"

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 def _like(spec):
     from cup1d_b200.likelihood import B200Likelihood
 
-    return B200Likelihood(spec, device=0)
+    return B200Likelihood(spec, device=0, emulator_precision="fp64")
 
 
 def test_batched_starts_equal_scipy_on_the_device_likelihood(golden):

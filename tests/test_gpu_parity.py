@@ -2,7 +2,9 @@
 outputs (goldens) and with the oracle on synthetic full-size configurations.
 
 Tolerances are those of BASELINE.json:north_star: model P1D within 1e-5
-relative, log-like within 1e-4 absolute (here: emulator in fp64 mode)."""
+relative, log-like within 1e-4 absolute.  The property tests of stages 1, 3, 4, 5 run with the float64
+emulator kernel (bit-level statements); the reference goldens and the full-size workloads are also checked
+with the default arithmetic (int8 digit slices on tcgen05 where the network shape allows it)."""
 
 import numpy as np
 import pytest
@@ -15,21 +17,34 @@ RTOL_P1D = 1e-5
 ATOL_LOGLIKE = 1e-4
 
 
-def _like(spec, **kw):
+def _like(spec, emulator_precision="fp64", **kw):
     from cup1d_b200.likelihood import B200Likelihood
 
-    return B200Likelihood(spec, device=0, **kw)
+    return B200Likelihood(spec, device=0, emulator_precision=emulator_precision, **kw)
 
 
-def _tol(v):
-    # 1e-4 absolute; far-from-fit walkers have |lnL| ~ 1e5..1e14 where one ulp exceeds it
-    return ATOL_LOGLIKE + 1e-11 * np.abs(v)
+REL = {"fp64": 1e-11, "i8": 1e-9}
 
 
+def _tol(v, prec="fp64"):
+    # 1e-4 absolute; far-from-fit walkers have |lnL| ~ 1e5..1e14 where one ulp exceeds it (float64 kernels: 1e-11
+    # relative).  The int8 digit-slice emulator carries a 3e-9 relative model error, which the pull of the residuals
+    # turns into ~1e-7 sqrt(chi2): 1e-4 up to |lnL| ~ 1e5 and 1e-9 relative beyond.
+    return ATOL_LOGLIKE + REL[prec] * np.abs(v)
+
+
+@pytest.mark.parametrize("prec", ["fp64", "auto"])
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-def test_golden_reference_outputs(golden, name):
+def test_golden_reference_outputs(golden, name, prec):
     spec, ref = golden(name)
-    like = _like(spec)
+    like = _like(spec, emulator_precision=prec)
+    if prec == "auto":
+        if like.emulator_precision == "fp64":
+            like.close()
+            pytest.skip("GP emulator: float64 is the only arithmetic")
+        assert like.emulator_precision == "i8"
+    prec = like.emulator_precision
+    _tol = lambda v: globals()["_tol"](v, prec)  # noqa: E731
     x = ref["x"]
     exp = ref["lnprob_blobs"]
     bad = exp[:, 0] <= -1e99
@@ -141,13 +156,19 @@ def _synthetic(kind):
     return spec
 
 
+@pytest.mark.parametrize("prec", ["fp64", "auto"])
 @pytest.mark.parametrize("kind", ["c1", "c2", "c4", "c3"])
-def test_synthetic_full_size_vs_oracle(kind):
+def test_synthetic_full_size_vs_oracle(kind, prec):
     from cup1d_b200 import synth
     from oracle.model import OracleLikelihood
 
     spec = _synthetic(kind)
-    like = _like(spec)
+    like = _like(spec, emulator_precision=prec)
+    if prec == "auto" and like.emulator_precision == "fp64":
+        like.close()
+        pytest.skip("GP emulator: float64 is the only arithmetic")
+    prec = like.emulator_precision
+    _tol = lambda v: globals()["_tol"](v, prec)  # noqa: E731
     ora = OracleLikelihood(spec)
     x = np.concatenate([synth.walkers_ball(spec, 40, seed=0), synth.walkers_sweep(spec, 88, seed=16, frac_out=0.05)])
     got = like.log_prob_and_blobs_vectorized(x)

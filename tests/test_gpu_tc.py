@@ -32,7 +32,7 @@ def test_single_mma_chain(mode, N):
 def _c4_like():
     from cup1d_b200.workloads import make_likelihood
 
-    return make_likelihood("c4", device=0)
+    return make_likelihood("c4", device=0, emulator_precision="fp64")
 
 
 def test_mlp_tc_vs_fp64():

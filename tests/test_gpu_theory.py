@@ -26,7 +26,7 @@ def test_theory_get_p1d_kms_matches_the_reference(name):
     from cup1d_b200.spec import load_spec
 
     spec, ref = load_spec(os.path.join(GOLDEN_DIR, name + ".npz"), with_extra=True)
-    like = B200Likelihood(spec, device=0)
+    like = B200Likelihood(spec, device=0, emulator_precision="fp64")
     th = like.theory
     x = ref["x"]
     zsub = np.asarray(spec["zs"])[ref["izs"]]
@@ -98,7 +98,7 @@ def test_values_none_follows_the_reference_rules(golden):
     spec, ref = golden("c1_chab_nn")
     spec = copy.deepcopy(spec)
     spec["families"]["R_coeff"]["coeffs"] = np.asarray(spec["families"]["R_coeff"]["coeffs"], dtype=float) + 0.03
-    like = B200Likelihood(spec, device=0)
+    like = B200Likelihood(spec, device=0, emulator_precision="fp64")
     spec0 = copy.deepcopy(spec)
     spec0["cont"]["apply_resolution"] = False
     ora0 = OracleLikelihood(spec0)

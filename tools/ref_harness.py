@@ -1,8 +1,8 @@
-"""Run the *reference* cup1d (from /root/reference, read-only) in the build
-container so that its own outputs can pin the oracle.
+"""Run the *reference* cup1d (from /root/reference, read-only, or from its vendored copy baseline/_ref) so
+that its own outputs can pin the oracle and so that `bench.py --impl reference` can time
+the reference's own per-walker path on the GPU box's host cores.
 
-This module only works where /root/reference exists; nothing under tests -m gpu,
-smoke() or bench.py imports it.  It
+This module only works where the reference is present; nothing under tests -m gpu or smoke() imports it.  It
 
 1. stubs the packages cup1d imports at module level but that are not
    installed here (lace, mpi4py, matplotlib),
@@ -21,7 +21,10 @@ from types import SimpleNamespace
 
 import numpy as np
 
-REF_ROOT = "/root/reference"
+# the reference itself (build container) or its vendored copy (tools/vendor_reference.py -> baseline/_ref, which
+# travels to the GPU box); C1D_REF_ROOT overrides
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_ROOT = os.environ.get("C1D_REF_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/cup1d") else os.path.join(_REPO, "baseline", "_ref"))
 _STATE = {}
 
 
