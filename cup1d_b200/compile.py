@@ -361,7 +361,10 @@ def compile_spec(spec):
     if has_full:
         if not np.array_equal(np.asarray(d["full_Pk_kms"], dtype=float), fields["DATA"]):
             raise ValueError("full_Pk_kms differs from the concatenated per-z data vector")
-        fields["ICOV_FULL"] = np.asarray(d["full_icov"], dtype=float)
+        # d^T A d only sees the symmetric part of A (np.linalg.inv output is symmetric to rounding only); the chi2
+        # kernel visits one triangle of the matrix and doubles it
+        A = np.asarray(d["full_icov"], dtype=float)
+        fields["ICOV_FULL"] = 0.5 * (A + A.T)
     else:
         fields["ICOV_FULL"] = np.zeros(0)
 

@@ -97,6 +97,44 @@ extern "C" int c1d_ctx_create(const c1d_config* cfg, c1d_ctx** out) {
   return C1D_OK;
 }
 
+// zero-padded copies of the inverse covariances for the tensor-core chi2 kernels; the allocations are kept across
+// re-uploads of same-sized fields (set_icov on a live context)
+static int refresh_icov_pad(c1d_ctx* ctx) {
+  const c1d_config& c = ctx->cfg;
+  if (!c.has_full) {
+    if (ctx->icov_pad) { cudaFree(ctx->icov_pad); ctx->icov_pad = nullptr; }
+    return C1D_OK;
+  }
+  const size_t ldd = ctx->d.ldd;
+  if (!ctx->icov_pad) {
+    C1D_CUDA(ctx, cudaMalloc(&ctx->icov_pad, ldd * ldd * sizeof(double)));
+    C1D_CUDA(ctx, cudaMemset(ctx->icov_pad, 0, ldd * ldd * sizeof(double)));
+  }
+  C1D_CUDA(ctx, cudaMemcpy2D(ctx->icov_pad, ldd * sizeof(double), ctx->dev[C1D_F_ICOV_FULL], (size_t)c.nd * sizeof(double),
+                             (size_t)c.nd * sizeof(double), c.nd, cudaMemcpyDeviceToDevice));
+  return C1D_OK;
+}
+
+static int refresh_icovz_pad(c1d_ctx* ctx, const int32_t* zd) {
+  const c1d_config& c = ctx->cfg;
+  const int tzw = (ctx->ndz_max + 63) / 64 * 64;
+  if (ctx->icovz_pad && ctx->tzw != tzw) { cudaFree(ctx->icovz_pad); ctx->icovz_pad = nullptr; }
+  ctx->tzw = tzw;
+  if (!ctx->icovz_pad) {
+    C1D_CUDA(ctx, cudaMalloc(&ctx->icovz_pad, (size_t)c.nz * tzw * tzw * sizeof(double)));
+    C1D_CUDA(ctx, cudaMemset(ctx->icovz_pad, 0, (size_t)c.nz * tzw * tzw * sizeof(double)));
+  }
+  size_t off = 0;
+  for (int z = 0; z < c.nz; ++z) {
+    const int ndz = zd[z + 1] - zd[z];
+    C1D_CUDA(ctx, cudaMemcpy2D(ctx->icovz_pad + (size_t)z * tzw * tzw, (size_t)tzw * sizeof(double),
+                               (const double*)ctx->dev[C1D_F_ICOV_BLOCKS] + off, (size_t)ndz * sizeof(double),
+                               (size_t)ndz * sizeof(double), ndz, cudaMemcpyDeviceToDevice));
+    off += (size_t)ndz * ndz;
+  }
+  return C1D_OK;
+}
+
 extern "C" int c1d_ctx_upload(c1d_ctx* ctx, int field_id, const void* host_ptr, size_t bytes) {
   if (!ctx) return C1D_ERR_ARG;
   if (field_id < 0 || field_id >= C1D_F_COUNT || (!host_ptr && bytes)) {
@@ -104,7 +142,8 @@ extern "C" int c1d_ctx_upload(c1d_ctx* ctx, int field_id, const void* host_ptr, 
     return C1D_ERR_ARG;
   }
   C1D_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-  if (ctx->dev[field_id] && ctx->bytes[field_id] != bytes) {
+  const bool same_size = ctx->dev[field_id] && ctx->bytes[field_id] == bytes;
+  if (ctx->dev[field_id] && !same_size) {
     C1D_CUDA(ctx, cudaFree(ctx->dev[field_id]));
     ctx->dev[field_id] = nullptr;
   }
@@ -114,7 +153,24 @@ extern "C" int c1d_ctx_upload(c1d_ctx* ctx, int field_id, const void* host_ptr, 
   C1D_CUDA(ctx, cudaDeviceSynchronize());
   C1D_CUDA(ctx, cudaMemcpy(ctx->dev[field_id], host_ptr, bytes, cudaMemcpyHostToDevice));
   ctx->bytes[field_id] = bytes;
-  if (ctx->finalized) return c1d_ctx_finalize(ctx);
+  if (!ctx->finalized) return C1D_OK;
+  // a live context: same-sized re-uploads of the data vector, the z mask and the inverse covariances (set_data,
+  // set_icov, zmask evaluations) refresh only what depends on them; anything else re-runs the whole finalisation
+  int rc = C1D_OK;
+  if (same_size && (field_id == C1D_F_DATA || field_id == C1D_F_ZMASK)) {
+    rc = C1D_OK;
+  } else if (same_size && field_id == C1D_F_ICOV_FULL) {
+    rc = refresh_icov_pad(ctx);
+  } else if (same_size && field_id == C1D_F_ICOV_BLOCKS) {
+    int32_t zd[1024];
+    C1D_CUDA(ctx, cudaMemcpy(zd, ctx->dev[C1D_F_ZOFF_D], (ctx->cfg.nz + 1) * 4, cudaMemcpyDeviceToHost));
+    rc = refresh_icovz_pad(ctx, zd);
+  } else {
+    return c1d_ctx_finalize(ctx);
+  }
+  if (rc) return rc;
+  // the copies above ran on the legacy default stream: order them before evaluations on any (non-blocking) stream
+  C1D_CUDA(ctx, cudaDeviceSynchronize());
   return C1D_OK;
 }
 
@@ -191,31 +247,9 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
   DP(gp_ymean, C1D_F_GP_YMEAN); DP(gp_ystd, C1D_F_GP_YSTD); DP(gp_norm, C1D_F_GP_NORM); IP(zmask, C1D_F_ZMASK);
 #undef DP
 #undef IP
-  if (ctx->icov_pad) { cudaFree(ctx->icov_pad); ctx->icov_pad = nullptr; }
-  if (c.has_full) {
-    // zero-padded [ldd x ldd] copy for the tiled chi2 GEMM
-    const size_t ldd = d.ldd;
-    C1D_CUDA(ctx, cudaMalloc(&ctx->icov_pad, ldd * ldd * sizeof(double)));
-    C1D_CUDA(ctx, cudaMemset(ctx->icov_pad, 0, ldd * ldd * sizeof(double)));
-    C1D_CUDA(ctx, cudaMemcpy2D(ctx->icov_pad, ldd * sizeof(double), ctx->dev[C1D_F_ICOV_FULL], (size_t)c.nd * sizeof(double),
-                               (size_t)c.nd * sizeof(double), c.nd, cudaMemcpyDeviceToDevice));
-  }
-  // zero-padded per-z blocks for the per-z chi2 GEMM (z blocks at 64-aligned offsets)
-  if (ctx->icovz_pad) { cudaFree(ctx->icovz_pad); ctx->icovz_pad = nullptr; }
-  {
-    const int tzw = (ctx->ndz_max + 63) / 64 * 64;
-    ctx->tzw = tzw;
-    C1D_CUDA(ctx, cudaMalloc(&ctx->icovz_pad, (size_t)c.nz * tzw * tzw * sizeof(double)));
-    C1D_CUDA(ctx, cudaMemset(ctx->icovz_pad, 0, (size_t)c.nz * tzw * tzw * sizeof(double)));
-    size_t off = 0;
-    for (int z = 0; z < c.nz; ++z) {
-      const int ndz = zd[z + 1] - zd[z];
-      C1D_CUDA(ctx, cudaMemcpy2D(ctx->icovz_pad + (size_t)z * tzw * tzw, (size_t)tzw * sizeof(double),
-                                 (const double*)ctx->dev[C1D_F_ICOV_BLOCKS] + off, (size_t)ndz * sizeof(double),
-                                 (size_t)ndz * sizeof(double), ndz, cudaMemcpyDeviceToDevice));
-      off += (size_t)ndz * ndz;
-    }
-  }
+  if (ctx->icov_pad) { cudaFree(ctx->icov_pad); ctx->icov_pad = nullptr; }  // ldd may have changed
+  { int rc = refresh_icov_pad(ctx); if (rc) return rc; }
+  { int rc = refresh_icovz_pad(ctx, zd); if (rc) return rc; }
   if (ctx->ws.dvz) { cudaFree(ctx->ws.dvz); ctx->ws.dvz = nullptr; }  // its width may have changed
   ctx->finalized = 1;
   {
@@ -230,6 +264,9 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
     rc = c1d_i8_prepare(ctx);  // int8 digit planes of the weights (leaves the path unavailable for unsupported shapes)
     if (rc != C1D_OK) return rc;
   }
+  // the memsets and copies of the finalisation ran on the legacy default stream; evaluations may be enqueued on
+  // non-blocking streams, which do not synchronise with it
+  C1D_CUDA(ctx, cudaDeviceSynchronize());
   return C1D_OK;
 }
 
@@ -264,6 +301,9 @@ static int ws_reserve(c1d_ctx* ctx, int64_t W) {
   // rows of rejected walkers are never written by stage 1: keep them finite
   C1D_CUDA(ctx, cudaMemset(w.emu_in, 0, (size_t)cap * c.nz * C1D_MAX_EMU * sizeof(double)));
   C1D_CUDA(ctx, cudaMemset(w.amp, 0, (size_t)cap * c.nz * C1D_NAMP * sizeof(double)));
+  // the memsets ran on the legacy default stream: finish them before the caller's (possibly non-blocking) stream
+  // writes into the buffers
+  C1D_CUDA(ctx, cudaDeviceSynchronize());
   w.cap = cap;
   return C1D_OK;
 }

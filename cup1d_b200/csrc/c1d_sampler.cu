@@ -65,7 +65,10 @@ k_stretch_accept(double* __restrict__ x, double* __restrict__ lnp, double* __res
   philox4x32_10((uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)half << 31), (uint32_t)s, 1u, (uint32_t)seed,
                 (uint32_t)(seed >> 32), r);
   const double lnu = log(u01(r[0], r[1]));
-  const bool acc = lnu < factors[s] + lnp_q[s] - lnp[w];
+  // lane 0 decides and broadcasts: no lane reads lnp[w] after lane 0 has overwritten it
+  int acc_i = 0;
+  if (lane == 0) acc_i = lnu < factors[s] + lnp_q[s] - lnp[w];
+  const bool acc = __shfl_sync(0xffffffffu, acc_i, 0) != 0;
   if (!acc) return;
   for (int d = lane; d < ndim; d += 32) x[w * ndim + d] = q[s * ndim + d];
   if (lane < 6) blobs[w * 6 + lane] = blobs_q[s * 6 + lane];

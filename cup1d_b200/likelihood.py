@@ -102,6 +102,8 @@ class B200Likelihood(object):
             o += len(k)
         if self.spec["data"]["full_icov"] is not None:
             self.spec["data"]["full_Pk_kms"] = v.copy()
+        if self.theory is not None:
+            self.theory.invalidate()  # derived contexts that carry the data vector and the metric
 
     def set_icov(self, icov_Pk_kms, full_icov_Pk_kms=None):
         """Replace the inverse covariances stage 4 keeps on the device: the
@@ -120,9 +122,12 @@ class B200Likelihood(object):
             full = np.ascontiguousarray(full_icov_Pk_kms, dtype=float)
             if full.shape != (self.nd, self.nd):
                 raise ValueError("full inverse covariance shape")
-            self.ctx.upload("ICOV_FULL", full)
+            # d^T A d only sees the symmetric part of A; the chi2 kernel visits one triangle and doubles it
+            self.ctx.upload("ICOV_FULL", 0.5 * (full + full.T))
             d["full_icov"] = full
         self._set_logdet()
+        if self.theory is not None:
+            self.theory.invalidate()
 
     def get_blobs_dtype(self):
         """lya_theory.py:500-512"""

@@ -47,5 +47,12 @@ def make_mock(like, cov_Pk_kms=None, values=None, add_noise=False, seed=0, insta
             cov_Pk_kms = [np.linalg.inv(c) for c in like.spec["data"]["icov"]]
         Pk = perturb_Pk(Pk, cov_Pk_kms, seed=seed)
     if install:
+        if add_noise and like.has_full:
+            import warnings
+
+            warnings.warn("make_mock(add_noise=True, install=True) on a full-covariance context: the device keeps ONE data "
+                          "vector, so the dense chi2 sees the perturbed mock, whereas the reference's Mock_P1D leaves "
+                          "full_Pk_kms noise free (mock_data.py:96-116) and its dense chi2 uses the unperturbed vector",
+                          stacklevel=2)
         like.set_data(np.concatenate(Pk))
     return {"Pk_kms": Pk, "full_Pk_kms": truth.copy(), "truth": truth}

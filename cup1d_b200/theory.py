@@ -192,6 +192,11 @@ class B200Theory(object):
             sub.close()
         self._cache.clear()
 
+    def invalidate(self):
+        """drop the derived contexts: the ones built with keep_data carry the data vector and the inverse
+        covariances of the likelihood at the time they were made (set_data / set_icov call this)"""
+        self.close()
+
     # ------------------------------------------------------------------
     def get_p1d_kms_batch(self, zs, k_kms, values, apply_hull=True, apply_resolution=True, return_emu_params=False):
         """P[W, sum_z len(k_z)] for cube points ``values[W, ndim]`` on the grid (zs, k_kms); no cube test.

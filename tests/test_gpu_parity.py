@@ -486,3 +486,29 @@ def test_gp_large_batch_kernel():
         po = np.concatenate(ora.get_p1d_kms(values=v)[0])
         assert np.max(np.abs(p[i] / po - 1)) <= RTOL_P1D
     like.close()
+
+
+def test_non_blocking_stream_first_call(golden):
+    """the first evaluation of a fresh context (workspace allocation and its memsets, the finalisation copies) and a
+    set_icov re-upload, issued on a non-blocking side stream: same rows as on the default stream"""
+    import torch
+
+    spec, ref = golden("dr1_full_nn")
+    x = np.tile(ref["x"], (40, 1))
+    want_like = _like(spec)
+    want = want_like.log_prob_and_blobs_vectorized(torch.as_tensor(x, device="cuda:0")).cpu().numpy()
+    want_like.close()
+    side = torch.cuda.Stream(device="cuda:0")
+    like = _like(spec)
+    with torch.cuda.stream(side):
+        xd = torch.as_tensor(x, device="cuda:0")
+        got = like.log_prob_and_blobs_vectorized(xd)
+        # a larger batch: the workspace grows (new allocation and memsets) under the same stream
+        big = like.log_prob_and_blobs_vectorized(torch.cat([xd] * 3))
+        like.set_icov(spec["data"]["icov"], spec["data"]["full_icov"])
+        again = like.log_prob_and_blobs_vectorized(xd)
+    side.synchronize()
+    np.testing.assert_array_equal(np.nan_to_num(got.cpu().numpy(), nan=-7.0), np.nan_to_num(want, nan=-7.0))
+    np.testing.assert_array_equal(np.nan_to_num(big[: len(x)].cpu().numpy(), nan=-7.0), np.nan_to_num(want, nan=-7.0))
+    np.testing.assert_array_equal(np.nan_to_num(again.cpu().numpy(), nan=-7.0), np.nan_to_num(want, nan=-7.0))
+    like.close()

@@ -126,3 +126,36 @@ def test_values_none_follows_the_reference_rules(golden):
             np.testing.assert_allclose(a[1][0], b[1][0], rtol=1e-14)
             assert abs(a[0] - e[0]) <= 1e-4 + 1e-11 * abs(e[0])
     like.close()
+
+
+def test_set_data_and_set_icov_reach_the_derived_contexts(golden):
+    """values=None with a non-zero held R_coeff is served by a derived context that carries the data vector and
+    the metric: set_data / set_icov on the likelihood must invalidate it (get_chi2() follows the new data)"""
+    import copy
+
+    from cup1d_b200.likelihood import B200Likelihood
+    from oracle.model import OracleLikelihood
+
+    spec, ref = golden("c1_chab_nn")
+    spec = copy.deepcopy(spec)
+    spec["families"]["R_coeff"]["coeffs"] = np.asarray(spec["families"]["R_coeff"]["coeffs"], dtype=float) + 0.03
+    like = B200Likelihood(spec, device=0, emulator_precision="fp64")
+    before = like.get_chi2()
+    new = np.concatenate(spec["data"]["Pk_kms"]) * 1.07
+    like.set_data(new)
+    spec1 = copy.deepcopy(spec)
+    spec1["cont"]["apply_resolution"] = False
+    o = 0
+    for iz, k in enumerate(spec1["data"]["k_kms"]):
+        spec1["data"]["Pk_kms"][iz] = new[o : o + len(k)].copy()
+        o += len(k)
+    want = OracleLikelihood(spec1).get_chi2()
+    after = like.get_chi2()
+    assert abs(after - want) <= 2e-4 + 1e-11 * abs(want)
+    assert abs(after - before) > 1.0
+    icov2 = [1.3 * np.asarray(c) for c in spec1["data"]["icov"]]
+    like.set_icov(icov2)
+    spec1["data"]["icov"] = icov2
+    want2 = OracleLikelihood(spec1).get_chi2()
+    assert abs(like.get_chi2() - want2) <= 2e-4 + 1e-11 * abs(want2)
+    like.close()
