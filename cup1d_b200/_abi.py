@@ -13,7 +13,7 @@ import numpy as np
 
 from . import compile as _cmp
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 LIB_NAME = "libcup1d_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
@@ -47,7 +47,8 @@ class Config(C.Structure):
         ("device", C.c_int32),
         ("uniform_k", C.c_int32),
         ("has_agn", C.c_int32),
-        ("reserved_i", C.c_int32 * 5),
+        ("gp_nm", C.c_int32), ("gp_nkn", C.c_int32),
+        ("reserved_i", C.c_int32 * 3),
         ("As_fid", C.c_double), ("ns_fid", C.c_double), ("nrun_fid", C.c_double),
         ("L_emu", C.c_double), ("L_star", C.c_double),
         ("blob_fid", C.c_double * 6), ("star_lo", C.c_double * 3), ("star_hi", C.c_double * 3),

@@ -43,7 +43,7 @@ FIELDS = [
     "PMIN", "PSCALE", "PRIOR_X0", "PRIOR_W", "ZBASE", "ZWGT", "ZIDX", "ZNULL", "ZOTYPE",
     "LINP", "MZ", "IGMFID", "EMU_LO", "EMU_HI", "HULL_ABC", "HULL_DIM", "ZOFF_F", "ZOFF_D",
     "TAB", "RB_START", "RB_WGT", "DATA", "ICOV_BLOCKS", "ICOV_FULL", "NN_W", "NN_B",
-    "GP_X", "GP_INVELL", "GP_ALPHA", "GP_YMEAN", "GP_YSTD", "GP_NORM", "ZMASK",
+    "GP_X", "GP_INVELL", "GP_ALPHA", "GP_YMEAN", "GP_YSTD", "GP_NORM", "GP_NORM_MF", "GP_NORM_TAB", "ZMASK",
 ]
 FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
 INT_FIELDS = {"ZIDX", "ZOTYPE", "HULL_DIM", "ZOFF_F", "ZOFF_D", "RB_START", "ZMASK"}
@@ -199,6 +199,17 @@ def compile_tables(spec):
         else:
             tab[COL_T, s] = k_Mpc / float(emu["kmax_Mpc"])
             scale = M[iz]
+            if emu.get("norm_table") is not None:
+                # norm = np.interp(k_Mpc, input_norm["k_Mpc"], norm_imF(mF)) (Fig3a.py:83-85): the walker-independent
+                # half of it, interval index c and weight t in the norm's k grid, packed as c + t; beyond the last node
+                # c = n - 1, t = 0 reads the padded (repeated) last column
+                kn = np.asarray(emu["norm_k_Mpc"], dtype=float)
+                cidx = np.clip(np.searchsorted(kn, k_Mpc, side="right") - 1, 0, len(kn) - 1)
+                hi = np.minimum(cidx + 1, len(kn) - 1)
+                den = np.where(hi > cidx, kn[hi] - kn[cidx], 1.0)
+                tt = np.clip(np.where(hi > cidx, (k_Mpc - kn[cidx]) / den, 0.0), 0.0, np.nextafter(1.0, 0.0))
+                tt = np.where(k_Mpc <= kn[0], 0.0, tt)
+                tab[COL_SPARE, s] = cidx + tt
         S = np.full(len(k), scale)
         if cont["ic_correction"]:
             # model_contaminants.py:310-330
@@ -385,7 +396,7 @@ def compile_spec(spec):
         "nz": nz, "ndim": ndim, "n_emu": n_emu, "nd": nd, "nf": nf,
         "ell_width": int(ell), "rebin_width": int(rwidth),
         "n_layers": 0, "layer_dims": [0] * (MAX_LAYERS + 1),
-        "gp_ntrain": 0, "gp_nnorm": 0, "gp_imf": 0,
+        "gp_ntrain": 0, "gp_nnorm": 0, "gp_imf": 0, "gp_nm": 0, "gp_nkn": 0,
         "metal_model": 0 if cont["metal_model"] == "SiMult" else 1,
         "apply_resolution": int(bool(cont["apply_resolution"])),
         "has_full": int(has_full), "has_gauss": int(has_gauss), "n_hull_facets": int(n_facets),
@@ -417,7 +428,7 @@ def compile_spec(spec):
         c0_o3c=float(off["SiIIb_Lya"] + cc**2 * off["SiIIc_Lya"]),
     )
 
-    for nm in ("NN_W", "NN_B", "GP_X", "GP_INVELL", "GP_ALPHA", "GP_YMEAN", "GP_YSTD", "GP_NORM"):
+    for nm in ("NN_W", "NN_B", "GP_X", "GP_INVELL", "GP_ALPHA", "GP_YMEAN", "GP_YSTD", "GP_NORM", "GP_NORM_MF", "GP_NORM_TAB"):
         fields[nm] = np.zeros(0)
     if emu["kind"] == "nn":
         layers = emu["layers"]
@@ -440,16 +451,27 @@ def compile_spec(spec):
         nc = alpha.shape[1]
         if nc > MAX_COEF:
             raise ValueError("too many GP outputs")
+        ncoef = np.asarray(emu.get("norm_coef", np.zeros(0)), dtype=float).reshape(-1)
         cfg.update(
-            emu_kind=1, nc=nc, gp_ntrain=int(alpha.shape[0]), gp_nnorm=len(emu["norm_coef"]),
+            emu_kind=1, nc=nc, gp_ntrain=int(alpha.shape[0]), gp_nnorm=len(ncoef),
             gp_imf=emu_params.index("mF"), gp_sigma2=float(emu["sigma2"]),
         )
+        if emu.get("norm_table") is not None:
+            if len(ncoef):
+                raise ValueError("GP emulator: give either norm_coef or norm_table")
+            nm_, T = np.asarray(emu["norm_mF"], dtype=float), np.asarray(emu["norm_table"], dtype=float)
+            kn = np.asarray(emu["norm_k_Mpc"], dtype=float)
+            if T.shape != (len(nm_), len(kn)) or len(nm_) < 2 or len(kn) < 2 or np.any(np.diff(nm_) <= 0) or np.any(np.diff(kn) <= 0):
+                raise ValueError("GP emulator: norm_table must be [len(norm_mF), len(norm_k_Mpc)] over increasing nodes")
+            cfg.update(gp_nm=len(nm_), gp_nkn=len(kn) + 1)
+            fields["GP_NORM_MF"] = nm_
+            fields["GP_NORM_TAB"] = np.concatenate([T, T[:, -1:]], axis=1)  # last column repeated, see COL_SPARE
         fields["GP_X"] = np.asarray(emu["X_train"], dtype=float)
         fields["GP_INVELL"] = 1.0 / np.asarray(emu["lengthscales"], dtype=float)
         fields["GP_ALPHA"] = alpha
         fields["GP_YMEAN"] = np.asarray(emu["ymean"], dtype=float)
         fields["GP_YSTD"] = np.asarray(emu["ystd"], dtype=float)
-        fields["GP_NORM"] = np.asarray(emu["norm_coef"], dtype=float)
+        fields["GP_NORM"] = ncoef
     else:
         raise ValueError("unknown emulator kind")
 

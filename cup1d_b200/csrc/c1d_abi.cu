@@ -50,6 +50,8 @@ static int64_t field_count(const c1d_config& c, int f, int64_t icov_blocks_n, in
     case C1D_F_GP_ALPHA: return c.emu_kind == 1 ? (int64_t)c.gp_ntrain * c.nc : 0;
     case C1D_F_GP_YMEAN: case C1D_F_GP_YSTD: return c.emu_kind == 1 ? c.nc : 0;
     case C1D_F_GP_NORM: return c.emu_kind == 1 ? c.gp_nnorm : 0;
+    case C1D_F_GP_NORM_MF: return c.emu_kind == 1 ? c.gp_nm : 0;
+    case C1D_F_GP_NORM_TAB: return c.emu_kind == 1 ? (int64_t)c.gp_nm * c.gp_nkn : 0;
     case C1D_F_ZMASK: return c.nz;
     default: return -1;
   }
@@ -73,7 +75,8 @@ extern "C" int c1d_ctx_create(const c1d_config* cfg, c1d_ctx** out) {
          c.layer_dims[c.n_layers] == c.nc;
     for (int l = 0; ok && l <= c.n_layers; ++l) ok = c.layer_dims[l] >= 1 && c.layer_dims[l] <= 256;
   }
-  if (ok && c.emu_kind == 1) ok = c.gp_ntrain > 0 && c.gp_imf >= 0 && c.gp_imf < c.n_emu && c.gp_nnorm >= 0;
+  if (ok && c.emu_kind == 1) ok = c.gp_ntrain > 0 && c.gp_imf >= 0 && c.gp_imf < c.n_emu && c.gp_nnorm >= 0 &&
+                                  ((c.gp_nm == 0 && c.gp_nkn == 0) || (c.gp_nm >= 2 && c.gp_nkn >= 3 && c.gp_nnorm == 0));
   if (!ok) {
     snprintf(ctx->err, sizeof(ctx->err), "inconsistent configuration (sizes / emulator layout; NN layers must be <= 256 wide)");
     return C1D_ERR_ARG;
@@ -226,6 +229,7 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
   d.n_layers = c.n_layers;
   for (int l = 0; l <= C1D_MAX_LAYERS; ++l) d.layer_dims[l] = c.layer_dims[l];
   d.gp_ntrain = c.gp_ntrain; d.gp_nnorm = c.gp_nnorm; d.gp_imf = c.gp_imf;
+  d.gp_nm = c.emu_kind == 1 ? c.gp_nm : 0; d.gp_nkn = c.emu_kind == 1 ? c.gp_nkn : 0;
   d.metal_model = c.metal_model; d.apply_resolution = c.apply_resolution; d.has_full = c.has_full;
   d.has_gauss = c.has_gauss; d.n_hull_facets = c.n_hull_facets; d.uniform_k = c.uniform_k; d.has_agn = c.has_agn;
   d.idx_As = c.idx_As; d.idx_ns = c.idx_ns; d.idx_nrun = c.idx_nrun;
@@ -245,6 +249,8 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
   DP(icov_blocks, C1D_F_ICOV_BLOCKS); DP(icov_full, C1D_F_ICOV_FULL); DP(nn_w, C1D_F_NN_W); DP(nn_b, C1D_F_NN_B);
   DP(gp_x, C1D_F_GP_X); DP(gp_invell, C1D_F_GP_INVELL); DP(gp_alpha, C1D_F_GP_ALPHA);
   DP(gp_ymean, C1D_F_GP_YMEAN); DP(gp_ystd, C1D_F_GP_YSTD); DP(gp_norm, C1D_F_GP_NORM); IP(zmask, C1D_F_ZMASK);
+  DP(gp_nmf, C1D_F_GP_NORM_MF); DP(gp_ntab, C1D_F_GP_NORM_TAB);
+  d.gp_emu_in = nullptr;
 #undef DP
 #undef IP
   if (ctx->icov_pad) { cudaFree(ctx->icov_pad); ctx->icov_pad = nullptr; }  // ldd may have changed

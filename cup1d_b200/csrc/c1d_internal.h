@@ -36,7 +36,7 @@ struct DevCtx {
   int nz, ndim, n_emu, nd, nf, ell_width, rebin_width, emu_kind, nc, n_layers;
   int ldd;  // row stride of the residual buffer = nd rounded up to a multiple of 64 (zero padded)
   int layer_dims[C1D_MAX_LAYERS + 1];
-  int gp_ntrain, gp_nnorm, gp_imf;
+  int gp_ntrain, gp_nnorm, gp_imf, gp_nm, gp_nkn;
   int metal_model, apply_resolution, has_full, has_gauss, n_hull_facets, uniform_k, has_agn;
   int idx_As, idx_ns, idx_nrun;
   int emu_code[C1D_MAX_EMU];
@@ -56,6 +56,8 @@ struct DevCtx {
   const double *rb_wgt, *data, *icov_blocks, *icov_full;
   const double *nn_w, *nn_b;
   const double *gp_x, *gp_invell, *gp_alpha, *gp_ymean, *gp_ystd, *gp_norm;
+  const double *gp_nmf, *gp_ntab;  // norm table of the GP emulator: mean-flux nodes, [gp_nm][gp_nkn] values
+  const double* gp_emu_in;         // workspace emulator inputs [z][w][C1D_MAX_EMU] (stage 3 reads the mean flux), set per launch
   const int* zmask;
 };
 

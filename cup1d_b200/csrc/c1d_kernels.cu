@@ -661,6 +661,16 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
         R2 = __shfl_sync(0xffffffffu, rr, 1);
         gq = __shfl_sync(0xffffffffu, rr, 2);
       }
+      // GP emulator with a k-table norm (Fig3a.py:83-85): the walker's two table rows and its weight in mean flux
+      int gj = 0;
+      double gw = 0.0;
+      const bool gnorm = (KIND == 1) && c.gp_nm > 0;
+      if (gnorm) {
+        const double mF = c.gp_emu_in[((int64_t)z * W + w) * C1D_MAX_EMU + c.gp_imf];
+        while (gj < c.gp_nm - 2 && mF >= __ldg(c.gp_nmf + gj + 1)) ++gj;
+        const double m0n = __ldg(c.gp_nmf + gj), m1n = __ldg(c.gp_nmf + gj + 1);
+        gw = fmin(fmax((mF - m0n) / (m1n - m0n), 0.0), 1.0);
+      }
       const double2* tp = tab2 + lane;  // this lane's point of the current block
       for (int i = lane; i < nfz; i += 32, tp += P1D_NPAIR * 32) {
         const double2 ks = tp[(C1D_COL_K / 2) * 32], tt1 = tp[(C1D_COL_T / 2) * 32];  // (k, S), (t, T1)
@@ -680,7 +690,16 @@ k_fused_p1d(DevCtx c, int64_t W, const int* __restrict__ status, const double* _
           for (int j = C1D_MAX_COEF - 1; j >= 0; --j)
             if (j < c.nc) pl = fma(pl, tt1.x, cf[j]);
         }
-        const double p_emu = ks.y * (KIND == 0 ? exp10_poly(pl) : exp(pl));
+        double p_emu = ks.y * (KIND == 0 ? exp10_poly(pl) : exp(pl));
+        if (gnorm) {
+          const double v = tp[(C1D_COL_AGN / 2) * 32].y;  // C1D_COL_SPARE: interval + weight in the norm's k grid
+          const int cc = (int)v, cn = cc + 1 < c.gp_nkn ? cc + 1 : cc;
+          const double* r0 = c.gp_ntab + (size_t)gj * c.gp_nkn;
+          const double* r1 = r0 + c.gp_nkn;
+          const double a0 = __ldg(r0 + cc), a1 = __ldg(r0 + cn);
+          const double n0 = fma(gw, __ldg(r1 + cc) - a0, a0), n1 = fma(gw, __ldg(r1 + cn) - a1, a1);
+          p_emu *= fma(v - (double)cc, n1 - n0, n0);
+        }
         double mult;
         if (METAL == 0) {
           // si_mult.py:212-218, 267-341:  G = 2 - 2/(1 + E)
@@ -793,6 +812,7 @@ int c1d_launch_stage3(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int
   if (grid > items) grid = items;
   double* dvec = want_dvec ? ctx->ws.dvec : nullptr;
   double* chi2z = want_chi2z ? ctx->ws.chi2z : nullptr;
+  ctx->d.gp_emu_in = ctx->ws.emu_in;
   kern<<<(unsigned)grid, P1D_THREADS, smem, s>>>(ctx->d, W, ctx->ws.status, ctx->ws.amp, dvec, p_out, chi2z, nfz_max,
                                                   ndz_max);
   ctx->launches++;

@@ -170,6 +170,21 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ seg, int nseg, const int* __
         R2 = exp_poly(-s2 * dk);
         gq = exp_poly(-2.0 * sa2 * (dk * dk));
       }
+      // GP emulator with a k-table norm (Fig3a.py:83-85): this lane's row of the table is the linear interpolation of
+      // two table rows in its mean flux; along k the fine points walk the norm's own grid, two row values at a time
+      int gj = 0, gcp = -2;
+      double gw = 0.0, gN0 = 0.0, gN1 = 0.0;
+      const bool gnorm = (KIND == 1) && c.gp_nm > 0;
+      if (gnorm) {
+        const double mF = c.gp_emu_in[((int64_t)z * W + wv) * C1D_MAX_EMU + c.gp_imf];
+        while (gj < c.gp_nm - 2 && mF >= __ldg(c.gp_nmf + gj + 1)) ++gj;
+        const double m0n = __ldg(c.gp_nmf + gj), m1n = __ldg(c.gp_nmf + gj + 1);
+        gw = fmin(fmax((mF - m0n) / (m1n - m0n), 0.0), 1.0);
+      }
+      auto grow = [&](int cc) {
+        const double a = __ldg(c.gp_ntab + (size_t)gj * c.gp_nkn + cc), b = __ldg(c.gp_ntab + (size_t)(gj + 1) * c.gp_nkn + cc);
+        return fma(gw, b - a, a);
+      };
       int jc = jc0;
       double acc0 = 0.0, acc1 = 0.0;
       auto flush = [&](int j, double m) {
@@ -219,7 +234,17 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ seg, int nseg, const int* __
             for (int j = C1D_MAX_COEF - 1; j >= 0; --j)
               if (j < c.nc) pl = fma(pl, tt1.x, cf[j]);
           }
-          const double p_emu = ks.y * (KIND == 0 ? exp10_tab(pl, etab) : exp(pl));
+          double p_emu = ks.y * (KIND == 0 ? exp10_tab(pl, etab) : exp(pl));
+          if (gnorm) {
+            const double v = tp[C1D_COL_AGN / 2].y;  // C1D_COL_SPARE: interval + weight in the norm's k grid
+            const int cc = (int)v;
+            if (cc != gcp) {  // the same interval for every lane: a uniform branch
+              gN0 = (cc == gcp + 1) ? gN1 : grow(cc);
+              gN1 = grow(cc + 1 < c.gp_nkn ? cc + 1 : cc);
+              gcp = cc;
+            }
+            p_emu *= fma(v - (double)cc, gN1 - gN0, gN0);
+          }
           double mult;
           if (METAL == 0) {
             // si_mult.py:212-218, 267-341:  G = 2 - 2/(1 + E)
@@ -444,6 +469,7 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int w
     }
     dvz = ctx->ws.dvz;
   }
+  ctx->d.gp_emu_in = ctx->ws.emu_in;
   kern<<<(unsigned)grid, threads, smem, s>>>(ctx->d, st->d_seg[q], st->nseg[q], st->d_ja, st->d_wa, st->d_wb, W, ctx->ws.status, ctx->ws.amp, dvec, p_out,
                                                 dvz, ctx->tzw, nfp_max, ndz_max);
   ctx->launches++;

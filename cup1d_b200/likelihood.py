@@ -193,20 +193,42 @@ class B200Likelihood(object):
         return t.cpu().numpy() if was_numpy else t
 
     # ---- batched entry points -----------------------------------------
-    def log_prob_batch(self, values, zmask=None):
+    def _logdet_total(self, zmask=None):
+        """log det C entering the log-likelihood with ignore_log_det_cov=False (likelihood.py:950, 962): the dense
+        matrix when it is the metric of the call, else the sum over the (selected) redshift bins"""
+        if self.has_full and zmask is None:
+            return float(self._logdet_full)
+        sel = np.ones(self.nz, dtype=bool)
+        if zmask is not None:
+            sel = np.array([bool(np.any(np.abs(np.atleast_1d(zmask) - z) < 1e-3)) for z in self.zs])
+        return float(np.sum(self._logdet_z[sel]))
+
+    def _add_logdet(self, lnp, zmask):
+        """log_like - 0.5 log det C for the rows that have a likelihood; rejected rows stay at min_log_like (+ prior),
+        as regulate_log_like leaves them (likelihood.py:974-980, 1019)"""
+        ld = 0.5 * self._logdet_total(zmask)
+        if torch.is_tensor(lnp):
+            return torch.where(lnp > 0.01 * self.min_log_like, lnp - ld, lnp)
+        return np.where(lnp > 0.01 * self.min_log_like, lnp - ld, lnp)
+
+    def log_prob_batch(self, values, zmask=None, ignore_log_det_cov=True):
         """lnP[W] = Likelihood.log_prob for every row (likelihood.py:1026)"""
         if zmask is None and not torch.is_tensor(values):
-            return self.log_prob_and_blobs_vectorized(values)[:, 0].copy()
-        lnp, _, _, _, was_numpy = self._evaluate(values, zmask=zmask)
-        return self._out(lnp, was_numpy)
+            lnp = self.log_prob_and_blobs_vectorized(values)[:, 0].copy()
+        else:
+            lnp, _, _, _, was_numpy = self._evaluate(values, zmask=zmask)
+            lnp = self._out(lnp, was_numpy)
+        return lnp if ignore_log_det_cov else self._add_logdet(lnp, zmask)
 
-    def log_prob_and_blobs_batch(self, values, zmask=None):
+    def log_prob_and_blobs_batch(self, values, zmask=None, ignore_log_det_cov=True):
         """(lnP[W], blobs[W, 6]) = Likelihood.log_prob_and_blobs per row (:1036)"""
         if zmask is None and not torch.is_tensor(values):
             out = self.log_prob_and_blobs_vectorized(values)
-            return out[:, 0].copy(), out[:, 1:].copy()
-        lnp, blobs, _, _, was_numpy = self._evaluate(values, zmask=zmask)
-        return self._out(lnp, was_numpy), self._out(blobs, was_numpy)
+            lnp, blobs = out[:, 0].copy(), out[:, 1:].copy()
+        else:
+            lnp, blobs, _, _, was_numpy = self._evaluate(values, zmask=zmask)
+            lnp, blobs = self._out(lnp, was_numpy), self._out(blobs, was_numpy)
+        return (lnp if ignore_log_det_cov else self._add_logdet(lnp, zmask)), blobs
 
     def log_prob_and_blobs_vectorized(self, values, out=None):
         """[W, 7] rows (lnP, *blob): what ``emcee.EnsembleSampler(...,
@@ -406,9 +428,8 @@ class B200Likelihood(object):
         return -np.sum((self.fid_cube - values) ** 2 / (2 * np.asarray(self.Gauss_priors) ** 2))
 
     def compute_log_prob(self, values, return_blob=False, ignore_log_det_cov=True, zmask=None):
-        """likelihood.py:982-1024"""
-        if not ignore_log_det_cov:
-            raise NotImplementedError("log|C| term: use get_log_like(ignore_log_det_cov=False)")
+        """likelihood.py:982-1024; with ignore_log_det_cov=False the log det C term of get_log_like (:950, :962)
+        enters before the regulation (:1019), through slogdet (the reference's det overflows for large matrices)"""
         v = np.asarray(values, dtype=float)
         if zmask is None:
             row = self.log_prob_and_blobs_vectorized(v[None, :])[0]
@@ -416,6 +437,8 @@ class B200Likelihood(object):
         else:
             lnp_t, blobs_t = self.log_prob_and_blobs_batch(v[None, :], zmask=zmask)
             lnp, blob = float(lnp_t[0]), tuple(blobs_t[0])
+        if not ignore_log_det_cov:
+            lnp = float(self._add_logdet(np.array([lnp]), zmask)[0])
         if return_blob:
             return lnp, blob
         return lnp

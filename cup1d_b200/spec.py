@@ -235,10 +235,170 @@ def emulator_to_spec(emulator):
             "kmax_Mpc": float(emulator.kmax_Mpc),
             "kp_Mpc": float(emulator.kp_Mpc),
         }
+    gp = _gp_emulator_to_spec(emulator)
+    if gp is not None:
+        return gp
     raise NotImplementedError(
         "cannot flatten emulator of type %s: give it a to_spec() method"
         % type(emulator).__name__
     )
+
+
+def _find_gprs(emulator):
+    """the fitted scikit-learn GaussianProcessRegressor(s) an emulator object holds: one multi-output regressor, or a
+    list / tuple / dict of single-output ones (one per polynomial coefficient, in coefficient order)"""
+    try:
+        from sklearn.gaussian_process import GaussianProcessRegressor as GPR
+    except Exception:  # noqa: BLE001
+        return None
+    found = []
+    for name, v in sorted(vars(emulator).items()):
+        if isinstance(v, GPR):
+            found.append((name, [v]))
+        elif isinstance(v, (list, tuple)) and len(v) and all(isinstance(g, GPR) for g in v):
+            found.append((name, list(v)))
+        elif isinstance(v, dict) and len(v) and all(isinstance(g, GPR) for g in v.values()):
+            found.append((name, [v[k] for k in sorted(v)]))
+    if not found:
+        return None
+    if len(found) > 1:
+        raise NotImplementedError("emulator holds several Gaussian-process attributes (%s): give it a to_spec() method" % [n for n, _ in found])
+    return found[0][1]
+
+
+def _rbf_of_kernel(kernel):
+    """(sigma2, lengthscales) of a fitted kernel of the form [ConstantKernel *] RBF [+ WhiteKernel]; anything else is
+    rejected by name (the device kernel evaluates an ARD squared exponential only)"""
+    from sklearn.gaussian_process import kernels as K
+
+    k = kernel
+    if isinstance(k, K.Sum):
+        parts = [q for q in (k.k1, k.k2) if not isinstance(q, K.WhiteKernel)]
+        if len(parts) != 1:
+            raise NotImplementedError("unsupported GP kernel %r (sums other than kernel + WhiteKernel)" % (kernel,))
+        k = parts[0]  # the white-noise term does not enter k(x*, X_train) of the predictive mean
+    sigma2 = 1.0
+    if isinstance(k, K.Product):
+        consts = [q for q in (k.k1, k.k2) if isinstance(q, K.ConstantKernel)]
+        rest = [q for q in (k.k1, k.k2) if not isinstance(q, K.ConstantKernel)]
+        if len(consts) != 1 or len(rest) != 1:
+            raise NotImplementedError("unsupported GP kernel %r" % (kernel,))
+        sigma2 = float(consts[0].constant_value)
+        k = rest[0]
+    if type(k) is not K.RBF:  # Matern and others derive from RBF
+        raise NotImplementedError("unsupported GP kernel %r: only [Constant *] RBF [+ White] is evaluated on the device" % (kernel,))
+    return sigma2, np.atleast_1d(np.asarray(k.length_scale, dtype=float))
+
+
+def _input_limits(emulator, names):
+    """[n_in, 2] limits of the unit-box scaling of the emulator inputs"""
+    for attr in ("param_lims", "paramLims", "param_limits"):
+        if hasattr(emulator, attr):
+            lims = np.asarray(getattr(emulator, attr), dtype=float)
+            if lims.shape == (len(names), 2):
+                return lims
+    if hasattr(emulator, "xmin") and hasattr(emulator, "xmax"):
+        return np.stack([np.asarray(emulator.xmin, dtype=float), np.asarray(emulator.xmax, dtype=float)], axis=1)
+    norm = getattr(emulator, "input_norm", None)
+    if isinstance(norm, dict) and all(n in norm for n in names):
+        out = []
+        for n in names:
+            v = norm[n]
+            out.append([float(v["min"]), float(v["max"])] if isinstance(v, dict) else [float(v[0]), float(v[1])])
+        return np.asarray(out)
+    raise NotImplementedError("GP emulator: cannot find the limits of the input scaling (param_lims / paramLims [n_in, 2], xmin / xmax, "
+                              "or input_norm[<parameter>] = (min, max))")
+
+
+def _poly_order(func_poly, n_out):
+    """which power of x each argument of func_poly(x, *coef) multiplies (the device evaluates sum_o c_o x^o)"""
+    x = np.array([0.3, 0.7, 1.3])
+    zero = np.asarray(func_poly(x, *([0.0] * n_out)), dtype=float)
+    powers = []
+    for o in range(n_out):
+        e = [0.0] * n_out
+        e[o] = 1.0
+        b = np.asarray(func_poly(x, *e), dtype=float) - zero
+        ok = [p for p in range(n_out) if np.allclose(b, x**p, rtol=1e-12, atol=1e-14)]
+        if len(ok) != 1:
+            raise NotImplementedError("GP emulator: func_poly is not a plain polynomial in its arguments")
+        powers.append(ok[0])
+    if sorted(powers) != list(range(n_out)) or np.any(np.abs(zero) > 1e-14):
+        raise NotImplementedError("GP emulator: func_poly is not a plain polynomial in its arguments")
+    return powers
+
+
+def _gp_emulator_to_spec(emulator):
+    """A LaCE-style GP emulator (the reference's default, ``CH24_mpgcen_gpr``: input_pipeline.py:21,
+    set_emulator.py:4-38) read through what the reference itself uses of it - ``emu_params``, ``kp_Mpc``, ``kmax_Mpc``,
+    ``input_norm["k_Mpc"]``, ``norm_imF(mF)``, ``func_poly`` (notebooks/figures_CM26/Fig3a.py:75-88) - and through its
+    fitted scikit-learn ``GaussianProcessRegressor`` (``X_train_``, ``alpha_``, ``kernel_``, the target normalisation).
+    Returns None when the object holds no such regressor.  [LaCE's source is absent: attribute names beyond the ones
+    the reference reads are looked up generically; anything that cannot be represented is rejected loudly.]"""
+    gprs = _find_gprs(emulator)
+    if gprs is None:
+        return None
+    names = [str(p) for p in emulator.emu_params]
+    X = np.asarray(gprs[0].X_train_, dtype=float)
+    if X.shape[1] != len(names):
+        raise NotImplementedError("GP emulator: X_train_ has %d columns for %d emulator parameters" % (X.shape[1], len(names)))
+    sig, ell = [], []
+    alphas, ymean, ystd = [], [], []
+    for g in gprs:
+        if np.asarray(g.X_train_).shape != X.shape or not np.array_equal(np.asarray(g.X_train_, dtype=float), X):
+            raise NotImplementedError("GP emulator: the regressors do not share one training set")
+        s2, l = _rbf_of_kernel(g.kernel_)
+        sig.append(s2)
+        ell.append(np.broadcast_to(l, (X.shape[1],)).astype(float))
+        a = np.asarray(g.alpha_, dtype=float)
+        a = a[:, None] if a.ndim == 1 else a
+        alphas.append(a)
+        ymean.append(np.broadcast_to(np.atleast_1d(np.asarray(getattr(g, "_y_train_mean", 0.0), dtype=float)), (a.shape[1],)))
+        ystd.append(np.broadcast_to(np.atleast_1d(np.asarray(getattr(g, "_y_train_std", 1.0), dtype=float)), (a.shape[1],)))
+    if any(not np.array_equal(l, ell[0]) for l in ell):
+        raise NotImplementedError("GP emulator: per-output length scales (one kernel-vector product per output) are not supported")
+    # different amplitudes per regressor fold into alpha (the posterior mean is linear in sigma2 * alpha)
+    alpha = np.concatenate([a * (s / sig[0]) for a, s in zip(alphas, sig)], axis=1)
+    ymean, ystd = np.concatenate(ymean), np.concatenate(ystd)
+    n_out = alpha.shape[1]
+    powers = _poly_order(emulator.func_poly, n_out)
+    order = np.argsort(powers)  # device coefficient o multiplies x^o
+    lims = _input_limits(emulator, names)
+    # the regressor works on the unit box of the limits: check it on the training set itself
+    if X.min() < -1e-6 or X.max() > 1 + 1e-6:
+        raise NotImplementedError("GP emulator: X_train_ is not in the unit box of the input limits")
+    kn = np.asarray(emulator.input_norm["k_Mpc"], dtype=float)
+    f = emulator.norm_imF
+    if hasattr(f, "x") and hasattr(f, "y") and str(getattr(f, "_kind", "linear")) == "linear" and np.ndim(f.y) == 2:
+        # a scipy interp1d over mean flux: its own nodes, exactly
+        mF = np.asarray(f.x, dtype=float)
+        T = np.asarray(f.y, dtype=float)
+        T = T if T.shape == (len(mF), len(kn)) else T.T
+    else:
+        # any other callable: tabulated on a fine mean-flux grid (read linearly in between)
+        imf = names.index("mF")
+        mF = np.linspace(lims[imf, 0], lims[imf, 1], 1025)
+        T = np.stack([np.asarray(f(m), dtype=float).reshape(-1) for m in mF])
+    if T.shape != (len(mF), len(kn)):
+        raise NotImplementedError("GP emulator: norm_imF(mF) does not return one value per input_norm['k_Mpc'] node")
+    return {
+        "kind": "gp",
+        "emu_params": names,
+        "xmin": lims[:, 0].copy(),
+        "xmax": lims[:, 1].copy(),
+        "X_train": X,
+        "lengthscales": ell[0].copy(),
+        "sigma2": float(sig[0]),
+        "alpha": alpha[:, order],
+        "ymean": ymean[order],
+        "ystd": ystd[order],
+        "norm_coef": np.zeros(0),
+        "norm_mF": mF,
+        "norm_k_Mpc": kn,
+        "norm_table": T,
+        "kmax_Mpc": float(emulator.kmax_Mpc),
+        "kp_Mpc": float(emulator.kp_Mpc),
+    }
 
 
 def spec_from_likelihood(like):

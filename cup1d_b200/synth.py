@@ -157,9 +157,11 @@ def synth_nn_emulator(seed=11, suite="mpg", nhidden=5, max_neurons=250, ndeg=5, 
     }
 
 
-def synth_gp_emulator(seed=12, suite="mpg", n_train=1320, n_out=5):
+def synth_gp_emulator(seed=12, suite="mpg", n_train=1320, n_out=5, norm="ktable", n_norm_mF=24, n_norm_k=48):
     """Seeded GP restatement: ARD squared-exponential kernel on unit-box
-    inputs, alpha = K^-1 y for a smooth synthetic target."""
+    inputs, alpha = K^-1 y for a smooth synthetic target.  norm="ktable": the norm of the
+    reference's own uses, a table over (mF, k_Mpc) read with np.interp in k (Fig3a.py:83-85); norm="poly": the
+    k-independent ln norm(mF) polynomial of the first fixtures."""
     rng = np.random.default_rng(seed)
     emu_params = MPG_PARAMS if suite == "mpg" else NYX_PARAMS
     n_in = len(emu_params)
@@ -177,7 +179,7 @@ def synth_gp_emulator(seed=12, suite="mpg", n_train=1320, n_out=5):
     ymean = np.zeros(n_out)
     ymean[: min(5, n_out)] = [-0.55, -3.2, 1.5, -0.6, 0.1][: min(5, n_out)]
     ystd = np.array([0.25, 0.4, 0.3, 0.15, 0.05, 0.02, 0.01][:n_out])
-    return {
+    spec = {
         "kind": "gp",
         "emu_params": list(emu_params),
         "xmin": np.array([EMU_RANGES[p][0] for p in emu_params]),
@@ -188,10 +190,24 @@ def synth_gp_emulator(seed=12, suite="mpg", n_train=1320, n_out=5):
         "alpha": alpha,
         "ymean": ymean,
         "ystd": ystd,
-        "norm_coef": np.array([0.3, -1.1, 0.4]),  # ln norm(mF) = c0 + c1 mF + c2 mF^2
         "kmax_Mpc": 4.0,
         "kp_Mpc": 0.7,
     }
+    if norm == "poly":
+        spec["norm_coef"] = np.array([0.3, -1.1, 0.4])  # ln norm(mF) = c0 + c1 mF + c2 mF^2
+        return spec
+    # a median-P1D-like shape: falls with k, steeper for high mean flux; unevenly spaced nodes in both directions
+    lo, hi = EMU_RANGES["mF"]
+    mF = lo + (hi - lo) * np.sort(np.concatenate([[0.0, 1.0], rng.uniform(0, 1, n_norm_mF - 2)]))
+    kn = np.geomspace(0.03, 4.2, n_norm_k) * (1.0 + 0.02 * rng.uniform(-1, 1, n_norm_k))
+    kn = np.sort(kn)
+    lnn = (0.3 - 1.1 * mF[:, None] + 0.4 * mF[:, None] ** 2) - (0.35 + 0.5 * mF[:, None]) * np.log1p(kn[None, :] / 0.8) \
+        + 0.05 * np.sin(3.0 * np.log(kn[None, :]) + 2.0 * mF[:, None])
+    spec["norm_coef"] = np.zeros(0)
+    spec["norm_mF"] = mF
+    spec["norm_k_Mpc"] = kn
+    spec["norm_table"] = np.exp(lnn)
+    return spec
 
 
 # ---------------------------------------------------------------------------

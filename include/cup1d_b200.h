@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define C1D_ABI_VERSION 6
+#define C1D_ABI_VERSION 7
 #define C1D_MAX_LAYERS 12
 #define C1D_MAX_EMU 8     /* emulator inputs */
 #define C1D_MAX_COEF 8    /* polynomial coefficients the emulator returns */
@@ -76,7 +76,8 @@ typedef enum c1d_column {
   C1D_COL_KT,        /* SiAdd ktot(k)                                  si_add.py:207-217 */
   C1D_COL_Q,         /* 2 R_z^2 k^2                                    resolution_class.py:99-108 */
   C1D_COL_AGN,       /* delta(z, k) of the AGN feedback template       AGN_model.py:99-116 */
-  C1D_COL_SPARE
+  C1D_COL_SPARE      /* GP emulator with a k-table norm: c + t, interval and weight of k_Mpc in the norm's k grid
+                        (np.interp(k_Mpc, input_norm["k_Mpc"], norm_imF(mF)), notebooks/figures_CM26/Fig3a.py:83-85) */
 } c1d_column;
 
 /* constant fields uploaded once with c1d_ctx_upload (float64 unless noted) */
@@ -112,7 +113,9 @@ typedef enum c1d_field {
   C1D_F_GP_ALPHA,      /* [gp_ntrain*nc] K^-1 y */
   C1D_F_GP_YMEAN,      /* [nc] */
   C1D_F_GP_YSTD,       /* [nc] */
-  C1D_F_GP_NORM,       /* [gp_nnorm] polynomial of ln norm(mF) */
+  C1D_F_GP_NORM,       /* [gp_nnorm] polynomial of ln norm(mF): k-independent norm (older form) */
+  C1D_F_GP_NORM_MF,    /* [gp_nm] mean-flux nodes of the norm table, increasing */
+  C1D_F_GP_NORM_TAB,   /* [gp_nm*gp_nkn] norm over (mF node, k node); last k column repeated */
   C1D_F_ZMASK,         /* int32 [nz] 1 = z-bin enters a zmask evaluation */
   C1D_F_COUNT
 } c1d_field;
@@ -137,7 +140,8 @@ typedef struct c1d_config {
   int32_t device;             /* CUDA device ordinal */
   int32_t uniform_k;          /* 1 = the model k grid of every z is evenly spaced (linspace, likelihood.py:90-94) */
   int32_t has_agn;            /* AGN feedback term present (off in the reference: model_contaminants.py:138-154) */
-  int32_t reserved_i[5];
+  int32_t gp_nm, gp_nkn;      /* GP norm table: mean-flux nodes, k nodes + 1 (0, 0 = k-independent norm) */
+  int32_t reserved_i[3];
   double As_fid, ns_fid, nrun_fid;
   double L_emu;               /* ln(kp_emu / ks)   lya_theory.py:299 */
   double L_star;              /* ln(kp_star / ks)  lya_theory.py:565 */

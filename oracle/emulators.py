@@ -95,8 +95,16 @@ class RefGPEmulator(object):
     mean of output o is m_o = sum_i k(u, U_i) alpha[i, o] with an ARD squared
     exponential kernel k = sigma2 exp(-0.5 sum_d ((u_d - U_id)/ell_d)^2);
     y_o = ymean_o + ystd_o m_o are the coefficients of a polynomial in
-    k/kmax, and P1D_Mpc(k) = norm(mF) * exp(sum_o y_o (k/kmax)^o) with
-    ln norm(mF) a polynomial in mF (``norm_imF``).
+    k/kmax, and P1D_Mpc(k) = norm(mF, k) * exp(sum_o y_o (k/kmax)^o).
+
+    The norm follows every use the reference makes of it
+    (notebooks/figures_CM26/Fig3a.py:83-85, Fig4b.py:88, FigB1a.py:84):
+        norm = np.interp(k_Mpc, emulator.input_norm["k_Mpc"], emulator.norm_imF(mF))
+    i.e. ``norm_imF(mF)`` is a table over ``input_norm["k_Mpc"]`` for the given mean flux, interpolated
+    linearly in k.  Here ``norm_imF`` interpolates a stored table ``norm_table[mF node, k node]`` linearly
+    in mF (clamped outside the nodes) [the interpolation LaCE uses along mF is not visible in the
+    reference; an adapter tabulates the real ``norm_imF`` on its own nodes].  Specs written before this
+    form (``norm_coef``: ln norm a polynomial in mF, k-independent) are still evaluated.
     """
 
     def __init__(self, spec, emulator_label="synthetic_gp", suite="mpg"):
@@ -115,15 +123,35 @@ class RefGPEmulator(object):
         self.alpha = np.asarray(spec["alpha"], dtype=np.float64)
         self.ymean = np.asarray(spec["ymean"], dtype=np.float64)
         self.ystd = np.asarray(spec["ystd"], dtype=np.float64)
-        self.norm_coef = np.asarray(spec["norm_coef"], dtype=np.float64)
+        self.norm_coef = np.asarray(spec.get("norm_coef", np.zeros(0)), dtype=np.float64)
         self.imF = self.emu_params.index("mF")
+        self.has_ktable = spec.get("norm_table") is not None
+        if self.has_ktable:
+            self.norm_mF = np.asarray(spec["norm_mF"], dtype=np.float64)
+            self.norm_table = np.asarray(spec["norm_table"], dtype=np.float64)
+            # the attributes the reference reads (Fig3a.py:75-85)
+            self.input_norm = {"k_Mpc": np.asarray(spec["norm_k_Mpc"], dtype=np.float64)}
+
+    def norm_imF(self, mF):
+        """norm over input_norm["k_Mpc"] for one mean flux: linear in mF between the table rows"""
+        m, T = self.norm_mF, self.norm_table
+        j = int(np.clip(np.searchsorted(m, mF, side="right") - 1, 0, len(m) - 2))
+        w = float(np.clip((mF - m[j]) / (m[j + 1] - m[j]), 0.0, 1.0))
+        return T[j] + w * (T[j + 1] - T[j])
+
+    def func_poly(self, x, *coef):
+        """sum_o coef_o x^o (the smooth model of Fig3a.py:86-88)"""
+        acc = np.zeros_like(np.asarray(x, dtype=np.float64))
+        for c in coef[::-1]:
+            acc = acc * x + c
+        return acc
 
     def to_spec(self):
         return self.spec
 
     def coefficients(self, x):
-        """[N, n_in] -> polynomial coefficients [N, n_out], with ln norm(mF)
-        folded into the constant term"""
+        """[N, n_in] -> polynomial coefficients [N, n_out]; a k-independent norm (the older ``norm_coef``
+        form) is folded into the constant term, a k-table norm is applied in emulate_p1d_Mpc"""
         u = (x - self.xmin) / (self.xmax - self.xmin)
         d = (u[:, None, :] - self.X[None, :, :]) / self.ell
         kern = self.sigma2 * np.exp(-0.5 * np.sum(d * d, axis=2))
@@ -148,6 +176,8 @@ class RefGPEmulator(object):
             for j in range(y.shape[1] - 1, -1, -1):
                 acc = acc * t + y[iz, j]
             out[iz][good] = np.exp(acc)
+            if self.has_ktable:
+                out[iz][good] *= np.interp(k_Mpc[iz][good], self.input_norm["k_Mpc"], self.norm_imF(x[iz, self.imF]))
         return out
 
 

@@ -98,6 +98,17 @@ def simulate(cfg, F, x, zmask=None, apply_hull=True):
             for j in range(nc - 1, -1, -1):
                 pl = pl * tab[cc.COL_T, s] + coef[j]
             p_emu = tab[cc.COL_S, s] * (10.0**pl if cfg["emu_kind"] == 0 else np.exp(pl))
+            if cfg["emu_kind"] == 1 and cfg.get("gp_nm", 0) > 0:
+                # k-table norm of the GP emulator: row of this (walker, z) from its mean flux, then the packed
+                # (interval, weight) column of the fine grid
+                nodes, T = F["GP_NORM_MF"], F["GP_NORM_TAB"].reshape(cfg["gp_nm"], cfg["gp_nkn"])
+                j = int(np.clip(np.searchsorted(nodes, mF, side="right") - 1, 0, len(nodes) - 2))
+                wgt = float(np.clip((mF - nodes[j]) / (nodes[j + 1] - nodes[j]), 0.0, 1.0))
+                row = T[j] + wgt * (T[j + 1] - T[j])
+                v = tab[cc.COL_SPARE, s]
+                ci = v.astype(int)
+                tt = v - ci
+                p_emu = p_emu * (row[ci] + tt * (row[np.minimum(ci + 1, cfg["gp_nkn"] - 1)] - row[ci]))
             om = 1 - mF
             if cfg["metal_model"] == 0:
                 a3 = q[4] / om

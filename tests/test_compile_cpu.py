@@ -179,3 +179,40 @@ def test_remove_switches_through_a_derived_spec(golden):
             assert np.max(np.abs(out["p1d"][i] / want - 1)) < 1e-11
             changed |= bool(np.max(np.abs(want / ref["p1d"][i] - 1)) > 1e-6)
         assert changed  # the switch does something
+
+
+@pytest.mark.parametrize("suite", ["mpg", "nyx"])
+def test_gp_ktable_norm_compiles_to_the_oracle(suite):
+    """GP emulator with the norm of the reference's own uses, np.interp(k_Mpc, input_norm["k_Mpc"], norm_imF(mF))
+    (notebooks/figures_CM26/Fig3a.py:83-85): compiled tables (NumPy mirror of the kernels) against the oracle,
+    with mean fluxes and wavenumbers beyond the table's nodes"""
+    from cup1d_b200 import synth
+    from oracle.model import OracleLikelihood
+
+    emu = synth.synth_gp_emulator(seed=5, suite=suite, n_train=60, n_out=5, n_norm_mF=7, n_norm_k=9)
+    # a norm grid narrower than the data: both clamps of np.interp are exercised
+    emu["norm_k_Mpc"] = np.geomspace(0.2, 2.5, 9)
+    emu["norm_mF"] = np.linspace(0.25, 0.7, 7)
+    spec = synth.build_spec(emu, grid="dr1", rebin_k=4, full_cov=False, seed=21, nz=4, nk=18, vary_nrun=(suite == "nyx"))
+    ora = OracleLikelihood(spec)
+    xt = synth.truth_point(spec)
+    synth.attach_mock_data(spec, np.concatenate(ora.get_p1d_kms(values=xt)[0]))
+    ora = OracleLikelihood(spec)
+    cfg, F = compile_spec(spec)
+    assert cfg["gp_nm"] == 7 and cfg["gp_nkn"] == 10 and cfg["gp_nnorm"] == 0
+    x = np.concatenate([synth.walkers_ball(spec, 4, seed=0), synth.walkers_sweep(spec, 12, seed=3, frac_out=0.1)])
+    sim = simulate(cfg, F, x)
+    exp = ora.log_prob_and_blobs_many(x)
+    ok = exp[:, 0] > -1e99
+    assert np.array_equal(sim["lnp"][~ok], exp[~ok, 0])
+    assert np.max(np.abs(sim["lnp"][ok] - exp[ok, 0]) / np.maximum(1.0, np.abs(exp[ok, 0]))) < 1e-11
+    for i in np.where(ok)[0][:6]:
+        po = np.concatenate(ora.get_p1d_kms(values=x[i])[0])
+        assert np.max(np.abs(sim["p1d"][i] / po - 1)) < 1e-12
+    # the table matters: a flat norm gives another model
+    emu2 = dict(emu)
+    emu2["norm_table"] = np.ones_like(emu["norm_table"])
+    spec2 = dict(spec)
+    spec2["emulator"] = emu2
+    cfg2, F2 = compile_spec(spec2)
+    assert np.max(np.abs(simulate(cfg2, F2, x[:1])["p1d"][0] / sim["p1d"][0] - 1)) > 1e-3

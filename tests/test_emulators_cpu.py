@@ -62,3 +62,51 @@ def test_gp_restatement_matches_sklearn():
         want[:, 0] += lnn
         got = emu.coefficients(x)
         np.testing.assert_allclose(got, want, rtol=0, atol=2e-7 * np.max(np.abs(want)))
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("per_output", [False, True])
+def test_sklearn_gp_emulator_adapter(per_output):
+    """emulator_to_spec on an object shaped like LaCE's default GP emulator (tests/fake_lace.py: a fitted scikit-learn
+    GaussianProcessRegressor behind the attributes the reference reads): the extracted spec, evaluated by the oracle
+    restatement, reproduces the object's own emulate_p1d_Mpc, i.e. sklearn.predict"""
+    from fake_lace import FakeLaceGP
+    from cup1d_b200.spec import emulator_to_spec
+    from oracle.emulators import RefGPEmulator
+
+    emu = FakeLaceGP(seed=4, per_output=per_output)
+    spec = emulator_to_spec(emu)
+    assert spec["kind"] == "gp" and spec["norm_table"].shape == (19, 40)
+    ref = RefGPEmulator(spec)
+    rng = np.random.default_rng(1)
+    lims = emu.param_lims
+    for _ in range(5):
+        X = lims[:, 0] + (lims[:, 1] - lims[:, 0]) * rng.uniform(0.1, 0.9, (11, len(lims)))
+        call = {p: X[:, j] for j, p in enumerate(emu.emu_params)}
+        k = np.zeros((11, 40))
+        for iz in range(11):
+            n = 25 + iz
+            k[iz, :n] = np.geomspace(0.015, 5.0, n)  # beyond both ends of the norm's k grid
+        a, b = emu.emulate_p1d_Mpc(call, k), ref.emulate_p1d_Mpc(call, k)
+        good = k > 0
+        assert np.max(np.abs(b[good] / a[good] - 1)) < 1e-9
+
+
+def test_sklearn_gp_adapter_rejects_what_it_cannot_represent():
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import Matern
+
+    from fake_lace import FakeLaceGP
+    from cup1d_b200.spec import emulator_to_spec
+
+    emu = FakeLaceGP(seed=4, optimise=False)
+    U = np.asarray(emu.gp.X_train_)
+    emu.gp = GaussianProcessRegressor(kernel=Matern(length_scale=np.ones(U.shape[1])), optimizer=None).fit(U, np.zeros((len(U), 5)))
+    with pytest.raises(NotImplementedError, match="unsupported GP kernel"):
+        emulator_to_spec(emu)
+    emu = FakeLaceGP(seed=4, optimise=False)
+    emu.func_poly = lambda x, *c: np.exp(np.polyval(c, x))
+    with pytest.raises(NotImplementedError, match="func_poly"):
+        emulator_to_spec(emu)

@@ -512,3 +512,32 @@ def test_non_blocking_stream_first_call(golden):
     np.testing.assert_array_equal(np.nan_to_num(big[: len(x)].cpu().numpy(), nan=-7.0), np.nan_to_num(want, nan=-7.0))
     np.testing.assert_array_equal(np.nan_to_num(again.cpu().numpy(), nan=-7.0), np.nan_to_num(want, nan=-7.0))
     like.close()
+
+
+@pytest.mark.parametrize("name", ["c1_chab_nn", "hcd_const"])
+def test_log_prob_with_log_det_cov(golden, name):
+    """log_prob(..., ignore_log_det_cov=False) (likelihood.py:1026-1034, the term of :950 / :962): scalar and
+    batched calls against the oracle, with and without a z mask; rejected rows stay at min_log_like"""
+    from oracle.model import OracleLikelihood
+
+    spec, ref = golden(name)
+    like = _like(spec)
+    ora = OracleLikelihood(spec)
+    x = ref["x"]
+    zm = [spec["zs"][1], spec["zs"][min(3, len(spec["zs"]) - 1)]]
+    for zmask in (None, zm):
+        exp = np.array([ora.log_prob(v.copy(), ignore_log_det_cov=False, zmask=zmask) for v in x])
+        if not np.all(np.isfinite(exp)):
+            continue  # the reference's det overflowed (dense matrix); the device path stays finite by design
+        got = like.log_prob_batch(x, zmask=zmask, ignore_log_det_cov=False)
+        bad = exp <= -1e99
+        np.testing.assert_array_equal(got[bad], exp[bad])
+        assert np.all(np.abs(got[~bad] - exp[~bad]) <= _tol(exp[~bad]))
+        plain = like.log_prob_batch(x, zmask=zmask)
+        assert np.any(np.abs(plain[~bad] - got[~bad]) > 1e-3)  # the term is there
+        for i in (0, 1, len(x) - 1):
+            s = like.log_prob(x[i].copy(), ignore_log_det_cov=False, zmask=zmask)
+            assert s == pytest.approx(got[i], rel=1e-14)
+            r = like.log_prob_and_blobs(x[i].copy(), ignore_log_det_cov=False, zmask=zmask)
+            assert r[0] == pytest.approx(got[i], rel=1e-14)
+    like.close()

@@ -182,6 +182,26 @@ def _install_stubs(lace_root):
     )
     lace.emulator = mod("lace.emulator")
     lace.emulator.emulator_manager = mod("lace.emulator.emulator_manager")
+
+    # the fitter's imports (fitter.py:3-8): emcee -> this repo's emcee-compatible ensemble sampler, pyDOE2.lhs -> a
+    # plain Latin hypercube (neither package is installed; run_minimizer itself only needs scipy)
+    try:
+        import emcee  # noqa: F401
+    except Exception:  # noqa: BLE001
+        from cup1d_b200 import sampler as _smp
+
+        mod("emcee", EnsembleSampler=_smp.EnsembleSampler)
+    try:
+        import pyDOE2  # noqa: F401
+    except Exception:  # noqa: BLE001
+
+        def lhs(n, samples=None, criterion=None, random_state=None):
+            rng = np.random.default_rng(random_state)
+            samples = samples or n
+            u = (rng.permuted(np.tile(np.arange(samples), (n, 1)), axis=1).T + rng.uniform(size=(samples, n))) / samples
+            return u
+
+        mod("pyDOE2", lhs=lhs)
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     _STATE["stubs"] = True
