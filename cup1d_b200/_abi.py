@@ -27,7 +27,7 @@ FLAG_EMU_I8 = 16
 SYMBOLS = (
     "c1d_abi_version", "c1d_ctx_create", "c1d_ctx_upload", "c1d_ctx_finalize",
     "c1d_loglike_batch", "c1d_p1d_batch", "c1d_emulator_only", "c1d_loglike_batch_host",
-    "c1d_sampler_run", "c1d_philox_u01", "c1d_emulator_paths", "c1d_launch_count", "c1d_set_timing", "c1d_get_timing", "c1d_tc_selftest", "c1d_ctx_destroy", "c1d_last_error",
+    "c1d_sampler_run", "c1d_sampler_run_ens", "c1d_sampler_half_step", "c1d_philox_u01", "c1d_emulator_paths", "c1d_launch_count", "c1d_set_timing", "c1d_get_timing", "c1d_tc_selftest", "c1d_ctx_destroy", "c1d_last_error",
 )
 
 
@@ -85,6 +85,10 @@ def load_library(path=None):
     lib.c1d_loglike_batch_host.argtypes = [vp, dp, i64, dp, u32]
     lib.c1d_sampler_run.argtypes = [vp, dp, dp, dp, i64, i64, i64, C.c_uint64, C.c_double, C.c_int, C.c_int, dp, dp, dp, dp, u32, vp]
     lib.c1d_sampler_run.restype = C.c_int
+    lib.c1d_sampler_run_ens.argtypes = [vp, dp, dp, dp, i64, i64, i64, i64, i64, C.c_uint64, C.c_double, C.c_int, C.c_int, dp, dp, dp, dp, u32, vp]
+    lib.c1d_sampler_run_ens.restype = C.c_int
+    lib.c1d_sampler_half_step.argtypes = [vp, dp, dp, dp, i64, i64, i64, i64, C.c_int, C.c_uint64, C.c_double, i64, i64, dp, u32, vp]
+    lib.c1d_sampler_half_step.restype = C.c_int
     lib.c1d_philox_u01.argtypes = [C.c_uint64, i64, C.c_int, i64, C.c_int, C.POINTER(C.c_double)]
     lib.c1d_philox_u01.restype = C.c_int
     lib.c1d_emulator_paths.argtypes = [vp]
@@ -165,14 +169,21 @@ class Context(object):
         self._check(rc, "c1d_loglike_batch_host")
 
     def sampler_run(self, x_ptr, lnp_ptr, blobs_ptr, W, nsteps, step0, seed, a=2.0, init=True, thin=1,
-                    chain_ptr=None, lnp_chain_ptr=None, blobs_chain_ptr=None, naccept_ptr=None, flags=0, stream=None):
-        rc = self.lib.c1d_sampler_run(self.handle, x_ptr, lnp_ptr, blobs_ptr, W, nsteps, step0, seed, a, int(init), thin,
-                                      chain_ptr, lnp_chain_ptr, blobs_chain_ptr, naccept_ptr, flags, stream)
-        self._check(rc, "c1d_sampler_run")
+                    chain_ptr=None, lnp_chain_ptr=None, blobs_chain_ptr=None, naccept_ptr=None, flags=0, stream=None,
+                    n_ens=1, ens0=0):
+        rc = self.lib.c1d_sampler_run_ens(self.handle, x_ptr, lnp_ptr, blobs_ptr, W, n_ens, ens0, nsteps, step0, seed, a, int(init), thin,
+                                          chain_ptr, lnp_chain_ptr, blobs_chain_ptr, naccept_ptr, flags, stream)
+        self._check(rc, "c1d_sampler_run_ens")
 
     def emulator_paths(self):
         """bit mask: 1 float64, FLAG_EMU_TC 3xTF32, FLAG_EMU_I8 int8 digit slices"""
         return int(self.lib.c1d_emulator_paths(self.handle))
+
+    def sampler_half_step(self, x_ptr, lnp_ptr, blobs_ptr, W, step, half, seed, s0, ns, a=2.0, naccept_ptr=None, flags=0, stream=None,
+                          n_ens=1, ens0=0):
+        rc = self.lib.c1d_sampler_half_step(self.handle, x_ptr, lnp_ptr, blobs_ptr, W, n_ens, ens0, step, half, seed, a, s0, ns,
+                                            naccept_ptr, flags, stream)
+        self._check(rc, "c1d_sampler_half_step")
 
     def launch_count(self):
         return int(self.lib.c1d_launch_count(self.handle))

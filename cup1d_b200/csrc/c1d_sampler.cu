@@ -29,51 +29,60 @@ __host__ __device__ inline double u01(uint32_t a, uint32_t b) {
   return ((double)(v & ((1ull << 53) - 1)) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-// one warp per walker s of the active half: q = c_j - (c_j - x_s) z
+// one warp per walker of the active half of its ensemble: q = c_j - (c_j - x_s) z with c_j drawn from the other
+// half of the SAME ensemble.  The batch holds W / wn independent ensembles of wn walkers (rows e wn .. e wn + wn - 1,
+// first half then second half); s runs over the active halves of all of them, the random numbers are keyed on the
+// global half-index (ens0 + e) nh + sl, so an ensemble draws the same numbers alone, in a batch or on another rank.
 __global__ void __launch_bounds__(256)
-k_stretch_propose(const double* __restrict__ x, int64_t W, int ndim, int half, int64_t step, uint64_t seed,
-                  double a, double* __restrict__ q, double* __restrict__ factors) {
+k_stretch_propose(const double* __restrict__ x, int64_t W, int64_t wn, int64_t ens0, int ndim, int half, int64_t step,
+                  uint64_t seed, double a, int64_t s0, int64_t ns, double* __restrict__ q, double* __restrict__ factors) {
   const int lane = threadIdx.x & 31;
-  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nh = W / 2;
-  if (s >= nh) return;
+  const int64_t sl0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // proposal number within [s0, s0 + ns)
+  const int64_t s = s0 + sl0;
+  const int64_t nh = wn / 2;
+  if (sl0 >= ns) return;
+  const int64_t e = s / nh, sl = s - e * nh, sg = (ens0 + e) * nh + sl;
   uint32_t r[4];
-  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)half << 31), (uint32_t)s, 0u, (uint32_t)seed,
+  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)half << 31), (uint32_t)sg, (uint32_t)(sg >> 32) << 1, (uint32_t)seed,
                 (uint32_t)(seed >> 32), r);
   const double z = (a - 1.0) * u01(r[0], r[1]) + 1.0;
   const double zz = z * z / a;
   int64_t j = (int64_t)(u01(r[2], r[3]) * (double)nh);
   if (j >= nh) j = nh - 1;
-  const double* xs = x + (half * nh + s) * ndim;
-  const double* xc = x + ((1 - half) * nh + j) * ndim;
-  for (int d = lane; d < ndim; d += 32) q[s * ndim + d] = xc[d] - (xc[d] - xs[d]) * zz;
-  if (lane == 0) factors[s] = (ndim - 1.0) * log(zz);
+  const double* xs = x + (e * wn + half * nh + sl) * ndim;
+  const double* xc = x + (e * wn + (1 - half) * nh + j) * ndim;
+  // proposals of this call are stored from row 0
+  for (int d = lane; d < ndim; d += 32) q[sl0 * ndim + d] = xc[d] - (xc[d] - xs[d]) * zz;
+  if (lane == 0) factors[sl0] = (ndim - 1.0) * log(zz);
 }
 
 // accept with probability min(1, z^(n-1) p(q)/p(x)); one warp per walker copies the row
 __global__ void __launch_bounds__(256)
-k_stretch_accept(double* __restrict__ x, double* __restrict__ lnp, double* __restrict__ blobs, int64_t W, int ndim,
-                 int half, int64_t step, uint64_t seed, const double* __restrict__ q,
+k_stretch_accept(double* __restrict__ x, double* __restrict__ lnp, double* __restrict__ blobs, int64_t W, int64_t wn, int64_t ens0,
+                 int ndim, int half, int64_t step, uint64_t seed, int64_t s0, int64_t ns, const double* __restrict__ q,
                  const double* __restrict__ factors, const double* __restrict__ lnp_q,
                  const double* __restrict__ blobs_q, long long* __restrict__ naccept) {
   const int lane = threadIdx.x & 31;
   const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nh = W / 2;
-  if (s >= nh) return;
-  const int64_t w = half * nh + s;
+  const int64_t nh = wn / 2;
+  if (s >= ns) return;
+  const int64_t sq = s;  // row of this proposal in q / factors / lnp_q / blobs_q
+  const int64_t sa = s0 + s;
+  const int64_t e = sa / nh, sl = sa - e * nh, sg = (ens0 + e) * nh + sl;
+  const int64_t w = e * wn + half * nh + sl;
   uint32_t r[4];
-  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)half << 31), (uint32_t)s, 1u, (uint32_t)seed,
+  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)half << 31), (uint32_t)sg, ((uint32_t)(sg >> 32) << 1) | 1u, (uint32_t)seed,
                 (uint32_t)(seed >> 32), r);
   const double lnu = log(u01(r[0], r[1]));
   // lane 0 decides and broadcasts: no lane reads lnp[w] after lane 0 has overwritten it
   int acc_i = 0;
-  if (lane == 0) acc_i = lnu < factors[s] + lnp_q[s] - lnp[w];
+  if (lane == 0) acc_i = lnu < factors[sq] + lnp_q[sq] - lnp[w];
   const bool acc = __shfl_sync(0xffffffffu, acc_i, 0) != 0;
   if (!acc) return;
-  for (int d = lane; d < ndim; d += 32) x[w * ndim + d] = q[s * ndim + d];
-  if (lane < 6) blobs[w * 6 + lane] = blobs_q[s * 6 + lane];
+  for (int d = lane; d < ndim; d += 32) x[w * ndim + d] = q[sq * ndim + d];
+  if (lane < 6) blobs[w * 6 + lane] = blobs_q[sq * 6 + lane];
   if (lane == 0) {
-    lnp[w] = lnp_q[s];
+    lnp[w] = lnp_q[sq];
     if (naccept) naccept[w] += 1;
   }
 }
@@ -84,8 +93,8 @@ k_stretch_accept(double* __restrict__ x, double* __restrict__ lnp, double* __res
 extern "C" int c1d_philox_u01(uint64_t seed, int64_t step, int half, int64_t walker, int which, double* out2) {
   if (!out2) return C1D_ERR_ARG;
   uint32_t r[4];
-  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)half << 31), (uint32_t)walker, (uint32_t)which,
-                (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)half << 31), (uint32_t)walker,
+                ((uint32_t)((uint64_t)walker >> 32) << 1) | (uint32_t)(which & 1), (uint32_t)seed, (uint32_t)(seed >> 32), r);
   out2[0] = u01(r[0], r[1]);
   out2[1] = u01(r[2], r[3]);
   return C1D_OK;
@@ -93,38 +102,65 @@ extern "C" int c1d_philox_u01(uint64_t seed, int64_t step, int half, int64_t wal
 
 int c1d_sampler_reserve(c1d_ctx* ctx, int64_t W);  // c1d_abi.cu
 
-extern "C" int c1d_sampler_run(c1d_ctx* ctx, double* x_dev, double* lnp_dev, double* blobs_dev, int64_t W,
-                               int64_t nsteps, int64_t step0, uint64_t seed, double a, int init, int thin,
-                               double* chain_dev, double* lnp_chain_dev, double* blobs_chain_dev,
-                               long long* naccept_dev, uint32_t flags, void* cuda_stream) {
+// proposals s0 .. s0 + ns - 1 of the active halves: propose, evaluate, accept (everything on stream s)
+static int sampler_half_step(c1d_ctx* ctx, double* x_dev, double* lnp_dev, double* blobs_dev, int64_t W, int64_t wn, int64_t ens0,
+                             int64_t step, int half, uint64_t seed, double a, int64_t s0, int64_t ns, long long* naccept_dev,
+                             uint32_t flags, cudaStream_t s) {
+  if (ns <= 0) return C1D_OK;
+  const int ndim = ctx->cfg.ndim;
+  const unsigned grid = (unsigned)((ns * 32 + 255) / 256);
+  k_stretch_propose<<<grid, 256, 0, s>>>(x_dev, W, wn, ens0, ndim, half, step, seed, a, s0, ns, ctx->ws.xdev, ctx->ws.factors);
+  ctx->launches++;
+  C1D_CUDA(ctx, cudaPeekAtLastError());
+  int rc = c1d_loglike_batch(ctx, ctx->ws.xdev, ns, ctx->ws.lnp, nullptr, ctx->ws.blobs_q, nullptr, flags, (void*)s);
+  if (rc) return rc;
+  k_stretch_accept<<<grid, 256, 0, s>>>(x_dev, lnp_dev, blobs_dev, W, wn, ens0, ndim, half, step, seed, s0, ns, ctx->ws.xdev,
+                                        ctx->ws.factors, ctx->ws.lnp, ctx->ws.blobs_q, naccept_dev);
+  ctx->launches++;
+  C1D_CUDA(ctx, cudaPeekAtLastError());
+  return C1D_OK;
+}
+
+extern "C" int c1d_sampler_half_step(c1d_ctx* ctx, double* x_dev, double* lnp_dev, double* blobs_dev, int64_t W, int64_t n_ens,
+                                     int64_t ens0, int64_t step, int half, uint64_t seed, double a, int64_t s0, int64_t ns,
+                                     long long* naccept_dev, uint32_t flags, void* cuda_stream) {
   if (!ctx) return C1D_ERR_ARG;
-  if (!x_dev || !lnp_dev || !blobs_dev || W < 2 || (W % 2) || nsteps < 0 || thin < 1 || !(a > 1.0)) {
-    snprintf(ctx->err, sizeof(ctx->err), "bad arguments to c1d_sampler_run (W must be even, a > 1)");
+  if (!x_dev || !lnp_dev || !blobs_dev || n_ens < 1 || (W % n_ens) || ((W / n_ens) % 2) || ens0 < 0 || (half != 0 && half != 1) ||
+      s0 < 0 || ns < 0 || s0 + ns > W / 2 || !(a > 1.0)) {
+    snprintf(ctx->err, sizeof(ctx->err), "bad arguments to c1d_sampler_half_step");
+    return C1D_ERR_ARG;
+  }
+  int rc = c1d_sampler_reserve(ctx, ns > 0 ? ns : 1);
+  if (rc) return rc;
+  return sampler_half_step(ctx, x_dev, lnp_dev, blobs_dev, W, W / n_ens, ens0, step, half, seed, a, s0, ns, naccept_dev, flags,
+                           (cudaStream_t)cuda_stream);
+}
+
+extern "C" int c1d_sampler_run_ens(c1d_ctx* ctx, double* x_dev, double* lnp_dev, double* blobs_dev, int64_t W, int64_t n_ens,
+                                   int64_t ens0, int64_t nsteps, int64_t step0, uint64_t seed, double a, int init, int thin,
+                                   double* chain_dev, double* lnp_chain_dev, double* blobs_chain_dev,
+                                   long long* naccept_dev, uint32_t flags, void* cuda_stream) {
+  if (!ctx) return C1D_ERR_ARG;
+  if (!x_dev || !lnp_dev || !blobs_dev || n_ens < 1 || W < 2 * n_ens || (W % n_ens) || ((W / n_ens) % 2) || ens0 < 0 || nsteps < 0 ||
+      thin < 1 || !(a > 1.0)) {
+    snprintf(ctx->err, sizeof(ctx->err), "bad arguments to c1d_sampler_run (an even number of walkers per ensemble, a > 1)");
     return C1D_ERR_ARG;
   }
   const int ndim = ctx->cfg.ndim;
-  const int64_t nh = W / 2;
+  const int64_t wn = W / n_ens, nht = W / 2;  // proposals per half-step: the active halves of all the ensembles
   cudaStream_t s = (cudaStream_t)cuda_stream;
-  int rc = c1d_sampler_reserve(ctx, nh);
+  int rc = c1d_sampler_reserve(ctx, nht);
   if (rc) return rc;
   if (init) {
     rc = c1d_loglike_batch(ctx, x_dev, W, lnp_dev, nullptr, blobs_dev, nullptr, flags, cuda_stream);
     if (rc) return rc;
   }
-  const unsigned grid = (unsigned)((nh * 32 + 255) / 256);
   int64_t stored = 0;
   for (int64_t it = 0; it < nsteps; ++it) {
     const int64_t step = step0 + it;
     for (int half = 0; half < 2; ++half) {
-      k_stretch_propose<<<grid, 256, 0, s>>>(x_dev, W, ndim, half, step, seed, a, ctx->ws.xdev, ctx->ws.factors);
-      ctx->launches++;
-      C1D_CUDA(ctx, cudaPeekAtLastError());
-      rc = c1d_loglike_batch(ctx, ctx->ws.xdev, nh, ctx->ws.lnp, nullptr, ctx->ws.blobs_q, nullptr, flags, cuda_stream);
+      rc = sampler_half_step(ctx, x_dev, lnp_dev, blobs_dev, W, wn, ens0, step, half, seed, a, 0, nht, naccept_dev, flags, s);
       if (rc) return rc;
-      k_stretch_accept<<<grid, 256, 0, s>>>(x_dev, lnp_dev, blobs_dev, W, ndim, half, step, seed, ctx->ws.xdev,
-                                            ctx->ws.factors, ctx->ws.lnp, ctx->ws.blobs_q, naccept_dev);
-      ctx->launches++;
-      C1D_CUDA(ctx, cudaPeekAtLastError());
     }
     if ((it + 1) % thin == 0) {
       if (chain_dev)
@@ -140,4 +176,12 @@ extern "C" int c1d_sampler_run(c1d_ctx* ctx, double* x_dev, double* lnp_dev, dou
     }
   }
   return C1D_OK;
+}
+
+extern "C" int c1d_sampler_run(c1d_ctx* ctx, double* x_dev, double* lnp_dev, double* blobs_dev, int64_t W,
+                               int64_t nsteps, int64_t step0, uint64_t seed, double a, int init, int thin,
+                               double* chain_dev, double* lnp_chain_dev, double* blobs_chain_dev,
+                               long long* naccept_dev, uint32_t flags, void* cuda_stream) {
+  return c1d_sampler_run_ens(ctx, x_dev, lnp_dev, blobs_dev, W, 1, 0, nsteps, step0, seed, a, init, thin, chain_dev, lnp_chain_dev,
+                             blobs_chain_dev, naccept_dev, flags, cuda_stream);
 }

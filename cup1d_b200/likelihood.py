@@ -294,17 +294,21 @@ class B200Likelihood(object):
         return self._out(p, was_numpy)
 
     # ---- on-device ensemble sampler --------------------
-    def run_sampler_device(self, p0, nsteps, nburn=0, thin=1, seed=0, a=2.0, zmask=None, to_numpy=True):
-        """Stretch-move MCMC entirely on the GPU (c1d_sampler_run): ``p0[W, ndim]``
-        initial walkers (W even), ``nburn`` discarded steps, then ``nsteps`` steps of
-        which every ``thin``-th is kept.  Returns the same products as
+    def run_sampler_device(self, p0, nsteps, nburn=0, thin=1, seed=0, a=2.0, zmask=None, to_numpy=True, n_ensembles=1, first_ensemble=0):
+        """Stretch-move MCMC entirely on the GPU (c1d_sampler_run_ens): ``p0[W, ndim]``
+        initial walkers, ``nburn`` discarded steps, then ``nsteps`` steps of
+        which every ``thin``-th is kept.  ``n_ensembles`` independent ensembles of W / n_ensembles walkers (an even
+        number) advance together - the reference's production layout is one ensemble per MPI rank (fitter.py:216-272);
+        rows e*wn .. (e+1)*wn - 1 of ``p0`` are ensemble e and the chain keeps that order (concatenation on the walker
+        axis, fitter.py:262-268).  ``first_ensemble`` is the global number of ensemble 0 (random-number key: an
+        ensemble gives the same chain wherever it runs).  Returns the same products as
         Fitter.run_sampler keeps (fitter.py:238-246): dict(chain[S, W, ndim],
         lnprob[S, W], blobs[S, W] structured, acceptance_fraction[W])."""
         x, _, _ = self._as_device(np.array(p0, dtype=float) if not torch.is_tensor(p0) else p0.clone())
         x = x.clone()
         W = x.shape[0]
-        if W % 2:
-            raise ValueError("the device sampler needs an even number of walkers")
+        if W % n_ensembles or (W // n_ensembles) % 2:
+            raise ValueError("the device sampler needs an even number of walkers per ensemble")
         nkeep = nsteps // thin
         flags = self._flags(zmask, True)
         with torch.cuda.device(self.device):
@@ -318,10 +322,11 @@ class B200Likelihood(object):
             stream = torch.cuda.current_stream(dev).cuda_stream
             if nburn > 0:
                 self.ctx.sampler_run(x.data_ptr(), lnp.data_ptr(), blobs.data_ptr(), W, nburn, 0, seed, a, True, 1,
-                                     None, None, None, None, flags, stream)
+                                     None, None, None, None, flags, stream, n_ens=n_ensembles, ens0=first_ensemble)
             nacc.zero_()
             self.ctx.sampler_run(x.data_ptr(), lnp.data_ptr(), blobs.data_ptr(), W, nsteps, nburn, seed, a, nburn == 0, thin,
-                                 chain.data_ptr(), lchain.data_ptr(), bchain.data_ptr(), nacc.data_ptr(), flags, stream)
+                                 chain.data_ptr(), lchain.data_ptr(), bchain.data_ptr(), nacc.data_ptr(), flags, stream,
+                                 n_ens=n_ensembles, ens0=first_ensemble)
         out = {"chain": chain, "lnprob": lchain, "blobs": bchain, "acceptance_fraction": nacc.double() / max(1, nsteps),
                "last_state": x, "last_lnprob": lnp}
         if to_numpy:

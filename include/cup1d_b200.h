@@ -228,8 +228,27 @@ int c1d_sampler_run(c1d_ctx* ctx, double* x_dev, double* lnp_dev, double* blobs_
                     double* chain_dev, double* lnp_chain_dev, double* blobs_chain_dev,
                     long long* naccept_dev, uint32_t flags, void* cuda_stream);
 
+/* the same for n_ens INDEPENDENT ensembles advanced together (the reference's production layout: one emcee ensemble of
+ * max(nwalkers, 2 ndim + 1) walkers per MPI rank, 128 ranks, fitter.py:69-72, 216-272; launch_data_sampler.sh:69): rows
+ * e*wn .. e*wn + wn - 1 of x_dev (wn = W / n_ens, even) are ensemble e; stretch-move partners come from the other half
+ * of the same ensemble.  The random numbers of ensemble e are keyed on its global number ens0 + e, so that an ensemble
+ * gives the same chain alone, in a batch, or on another rank (ensembles shard over GPUs with no communication;
+ * chains concatenate on the walker axis like fitter.py:262-268). */
+int c1d_sampler_run_ens(c1d_ctx* ctx, double* x_dev, double* lnp_dev, double* blobs_dev, int64_t W, int64_t n_ens,
+                        int64_t ens0, int64_t nsteps, int64_t step0, uint64_t seed, double a, int init, int thin,
+                        double* chain_dev, double* lnp_chain_dev, double* blobs_chain_dev,
+                        long long* naccept_dev, uint32_t flags, void* cuda_stream);
+
+/* one half-step of the same move restricted to proposals s0 .. s0 + ns - 1 of the active halves (propose, batched
+ * likelihood, accept).  With it an ensemble that SPANS several GPUs advances with one all-gather of the updated rows per
+ * half-step (cup1d_b200/dist.py): every rank holds the whole state, updates its share of the active half and the ranks
+ * exchange their shares; the random numbers depend on the walker, not on the rank, so the chain is that of one GPU. */
+int c1d_sampler_half_step(c1d_ctx* ctx, double* x_dev, double* lnp_dev, double* blobs_dev, int64_t W, int64_t n_ens,
+                          int64_t ens0, int64_t step, int half, uint64_t seed, double a, int64_t s0, int64_t ns,
+                          long long* naccept_dev, uint32_t flags, void* cuda_stream);
+
 /* the sampler's random numbers on the host (tests replay a chain with them):
- * out2 = two uniforms in (0,1) of counter (step, half, walker, which) */
+ * out2 = two uniforms in (0,1) of counter (step, half, walker, which); walker = (ens0 + e) * wn / 2 + index in the half */
 int c1d_philox_u01(uint64_t seed, int64_t step, int half, int64_t walker, int which, double* out2);
 
 /* emulator arithmetic available to a finalised context: bit 0 = float64, C1D_FLAG_EMU_TC, C1D_FLAG_EMU_I8

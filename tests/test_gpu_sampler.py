@@ -85,3 +85,65 @@ def test_host_driven_sampler_runs_on_the_batched_likelihood(golden):
     # stored lnprob is consistent with a fresh evaluation
     np.testing.assert_allclose(like.log_prob_batch(res["chain"][-1]), res["lnprob"][-1], rtol=1e-12, atol=1e-9)
     like.close()
+
+
+def test_many_ensembles_in_one_call_equal_the_separate_runs(golden, monkeypatch):
+    """n_ensembles independent ensembles advanced together (the reference's production layout, one ensemble per MPI
+    rank: fitter.py:216-272) give, bit for bit, the chains each ensemble gives alone under its global number - so
+    ensembles can be dealt to GPUs with no communication and concatenated on the walker axis (fitter.py:262-268)"""
+    from cup1d_b200.likelihood import B200Likelihood
+    from cup1d_b200.sampler import get_initial_walkers
+
+    monkeypatch.setenv("C1D_P1D_LAYOUT", "warp")  # one form of stage 3 whatever the batch size (the forms agree to rounding only)
+    spec, ref = golden("sivid_pivot")
+    like = B200Likelihood(spec, device=0)
+    ndim, wn, E, nsteps, seed = like.ndim, 2 * like.ndim + 2, 3, 7, 99
+    x0 = np.clip(ref["x"][0], 0.05, 0.95)
+    p0 = get_initial_walkers(ndim, wn * E, pini=x0, rng=np.random.default_rng(8))
+    joint = like.run_sampler_device(p0, nsteps, nburn=2, thin=1, seed=seed, n_ensembles=E)
+    assert joint["chain"].shape == (nsteps, wn * E, ndim)
+    for e in range(E):
+        alone = like.run_sampler_device(p0[e * wn : (e + 1) * wn], nsteps, nburn=2, thin=1, seed=seed, n_ensembles=1, first_ensemble=e)
+        sl = slice(e * wn, (e + 1) * wn)
+        np.testing.assert_array_equal(joint["chain"][:, sl], alone["chain"])
+        np.testing.assert_array_equal(joint["lnprob"][:, sl], alone["lnprob"])
+        np.testing.assert_array_equal(joint["acceptance_fraction"][sl], alone["acceptance_fraction"])
+    # ensembles do not talk: walkers of ensemble 0 are the same whatever ensemble 1 starts from
+    p1 = p0.copy()
+    p1[wn : 2 * wn] = np.clip(p1[wn : 2 * wn] + 0.01, 0, 1)
+    other = like.run_sampler_device(p1, nsteps, nburn=2, thin=1, seed=seed, n_ensembles=E)
+    np.testing.assert_array_equal(other["chain"][:, :wn], joint["chain"][:, :wn])
+    assert not np.array_equal(other["chain"][:, wn : 2 * wn], joint["chain"][:, wn : 2 * wn])
+    like.close()
+
+
+def test_half_step_in_shares_equals_the_whole_half_step(golden, monkeypatch):
+    """c1d_sampler_half_step over sub-ranges of the active half (what the ranks of a spanning ensemble do, one share
+    each) reproduces the whole half-step bit for bit"""
+    import torch
+
+    from cup1d_b200.likelihood import B200Likelihood
+    from cup1d_b200.sampler import get_initial_walkers
+
+    monkeypatch.setenv("C1D_P1D_LAYOUT", "warp")
+    spec, ref = golden("sivid_pivot")
+    like = B200Likelihood(spec, device=0)
+    ndim, W, seed = like.ndim, 64, 5
+    x0 = np.clip(ref["x"][0], 0.05, 0.95)
+    p0 = get_initial_walkers(ndim, W, pini=x0, rng=np.random.default_rng(3))
+    whole = like.run_sampler_device(p0, 3, seed=seed, to_numpy=False)
+    x = torch.as_tensor(p0, device="cuda:0").clone()
+    rows = like.log_prob_and_blobs_vectorized(x)
+    lnp, blobs = rows[:, 0].contiguous(), rows[:, 1:].contiguous()
+    nacc = torch.zeros(W, dtype=torch.int64, device="cuda:0")
+    nh = W // 2
+    shares = [(0, 5), (5, 16), (21, 11)]
+    for step in range(3):
+        for half in (0, 1):
+            for s0, ns in shares:
+                like.ctx.sampler_half_step(x.data_ptr(), lnp.data_ptr(), blobs.data_ptr(), W, step, half, seed, s0, ns, naccept_ptr=nacc.data_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(x, whole["chain"][step])
+        assert torch.equal(lnp, whole["lnprob"][step])
+    assert sum(n for _, n in shares) == nh
+    like.close()
