@@ -392,14 +392,15 @@ class B200Likelihood(object):
         """likelihood.py:822-972: [log_like, log_like_all[1, Nz](, blob)]"""
         v, tgt, cube_test = self._eval_target(values)
         lnp, blobs, lnl_z, chi2, _ = tgt._evaluate(v[None, :], want_z=True, want_chi2=True, zmask=zmask, cube_test=cube_test)
-        ll, llz = float(-0.5 * chi2[0]), lnl_z[0].cpu().numpy()
+        # NumPy scalars like the reference's (its Fitter calls chi2.copy(), fitter.py:432)
+        ll, llz = np.float64(-0.5 * chi2[0].item()), lnl_z[0].cpu().numpy()
         if not ignore_log_det_cov and np.isfinite(ll):
             # log det C per redshift and of the dense matrix (likelihood.py:950, 962)
             sel = np.ones(self.nz, dtype=bool)
             if zmask is not None:
                 sel = np.array([bool(np.any(np.abs(np.atleast_1d(zmask) - z) < 1e-3)) for z in self.zs])
             llz = llz - 0.5 * self._logdet_z * sel
-            ll = ll - 0.5 * self._logdet_full if (self.has_full and zmask is None) else float(np.sum(llz))
+            ll = np.float64(ll - 0.5 * self._logdet_full) if (self.has_full and zmask is None) else np.float64(np.sum(llz))
         if not np.isfinite(ll):
             out = [-np.inf, -np.inf]
             if return_blob:

@@ -141,7 +141,8 @@ def test_half_step_in_shares_equals_the_whole_half_step(golden, monkeypatch):
     for step in range(3):
         for half in (0, 1):
             for s0, ns in shares:
-                like.ctx.sampler_half_step(x.data_ptr(), lnp.data_ptr(), blobs.data_ptr(), W, step, half, seed, s0, ns, naccept_ptr=nacc.data_ptr())
+                like.ctx.sampler_half_step(x.data_ptr(), lnp.data_ptr(), blobs.data_ptr(), W, step, half, seed, s0, ns, naccept_ptr=nacc.data_ptr(),
+                                           flags=like._flags(None, True))
         torch.cuda.synchronize()
         assert torch.equal(x, whole["chain"][step])
         assert torch.equal(lnp, whole["lnprob"][step])

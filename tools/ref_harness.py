@@ -143,6 +143,11 @@ def _install_stubs(lace_root):
     if "cup1d" in sys.modules and _STATE.get("stubs"):
         return
 
+    try:
+        import torch  # noqa: F401 - before the stand-ins below: torch's own optional imports must not see them
+    except Exception:  # noqa: BLE001
+        pass
+
     def mod(name, **attrs):
         m = types.ModuleType(name)
         for k, v in attrs.items():
