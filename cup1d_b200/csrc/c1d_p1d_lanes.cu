@@ -29,6 +29,7 @@
 
 #include "c1d_internal.h"
 #include "c1d_devmath.cuh"
+#include "c1d_tc_common.cuh"
 
 namespace {
 
@@ -57,6 +58,8 @@ struct P1dwState {
   double* d_wb;    // [nf] weight into bin ja + 1
   int* d_seg[PL_NPART];  // [nseg][PL_SEGW]
   int nseg[PL_NPART];
+  double* d_wsw;   // [nf][2] (+-wa, wb) for the warp-specialised kernel: the sign of wa says "this point opens the next bin"
+  int ws_ok;       // weights non-negative and the bin index advances by at most one per fine point
 };
 
 template <int NC, int KIND, int METAL, bool UNI, int U>
@@ -291,6 +294,350 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ seg, int nseg, const int* __
   }
 }
 
+
+// ------------------------------------------------------------------------------------
+// Warp-specialised walker-per-lane form (k_p1d_split).  The single-role kernel above is bound by
+// instruction issue and by the latency of its dependent fp64 chain at 4 warps per sub-partition
+// (128 registers per thread): ncu issue slots 60 %, fp64 pipe 56 %, dominant stall "wait".
+// Here a (z, 32 walkers) item is evaluated by a PAIR of warps.  The PRODUCER warp forms, per fine point,
+//     A = HCD(k) P_emu(k),   P_emu = S 10^poly(t)   (or e^poly for the GP emulators)
+// from the NC polynomial coefficients and the five HCD amplitudes of its lane's walker; the CONSUMER
+// warp forms the metal terms (exp recurrences, G = 2 - 2/(1+E)), the SiAdd term,
+// P = (A mult + add) (1 + R Q), the rebinning and the residual.  Each role keeps only its own
+// amplitudes in registers (`setmaxnreg` moves what the producers do not need to the consumers), so 24
+// warps (6 per sub-partition) are resident instead of 16, each with a shorter dependent chain and ~35 %
+// fewer instructions per point (constant-bank polynomial coefficients, no conversion instructions in
+// 10^x, one flag bit instead of a bin-index table for the rebinning).  A producer hands its consumer
+// chunks of WS_CH points x 32 lanes through a double buffer in shared memory and one named-barrier
+// rendezvous per chunk.  Every value is formed by the same operations whatever the k-segment cut
+// (anchors sit on multiples of PL_ANCHOR points of the redshift bin), so the results stay bit-identical
+// for any number of segments.
+// ------------------------------------------------------------------------------------
+constexpr int WS_PAIRS = 12, WS_THREADS = 64 * WS_PAIRS;
+constexpr int WS_CH = 16, WS_NBUF = 2;  // points per chunk, chunks in the ring (double buffer)
+constexpr int WS_UNROLL = 4;
+constexpr int WS_WAVES = 3;
+constexpr int WS_PROW = 6, WS_CROW = 12;     // doubles per producer / consumer table row
+constexpr int WS_PREG = 64, WS_CREG = 96;    // registers per thread after setmaxnreg (launch: 80)
+// producer row: (t, S) (D1, D2) (D3, D4);  consumer row: (k, T1) (T2A, T2BC) (T3A, T3BC) (KT, Q) (+-wa, wb) (AGN, -)
+__device__ __constant__ int c_ws_psrc[6] = {C1D_COL_T, C1D_COL_S, C1D_COL_D1, C1D_COL_D2, C1D_COL_D3, C1D_COL_D4};
+__device__ __constant__ int c_ws_csrc[8] = {C1D_COL_K, C1D_COL_T1, C1D_COL_T2A, C1D_COL_T2BC, C1D_COL_T3A, C1D_COL_T3BC, C1D_COL_KT, C1D_COL_Q};
+// (ln 2 / 32)^k / k!, k = 0 .. 6
+__device__ __constant__ double c_ws_e2[7] = {1.0, 0.02166084939249829, 0.0002345961982022468, 1.693850972437182e-06,
+                                             9.172562701824643e-09, 3.973709984549416e-11, 1.4345655584131934e-13};
+
+__device__ __noinline__ double ws_exp_slow(double x, int kind) { return kind == 0 ? exp10(x) : exp(x); }
+// the exact re-evaluations at the recurrence anchors (one point in PL_ANCHOR): out of line, the loop body stays small
+__device__ __noinline__ double ws_exp_anchor(double x) { return exp_poly(x); }
+
+// 10^x (KIND 0) or e^x (KIND 1) = 2^e 2^(j/32) 2^(r/32): n = rint(32 x log2 b) = 32 e + j from the low word of
+// x L + 1.5 2^52 (no conversion instructions), degree-6 Horner polynomial with constant-bank coefficients,
+// the power of two added into the exponent field of the table value.  |x| < 280 (700): the caller checks.
+template <int KIND>
+__device__ __forceinline__ double ws_exp_fast(double x, const double* __restrict__ tab) {
+  const double L_HI = KIND == 0 ? 106.30169903639559 : 46.16624130844683;
+  const double L_LO = KIND == 0 ? 5.3171760543154944e-15 : 6.513687597097931e-16;
+  const double MAGIC = 6755399441055744.0;
+  const double tq = fma(x, L_HI, MAGIC);
+  const int ni = __double2loint(tq);
+  const double n = tq - MAGIC;
+  double r = fma(x, L_HI, -n);
+  r = fma(x, L_LO, r);
+  const double tv = tab[ni & 31];
+  const double sc = __hiloint2double(__double2hiint(tv) + ((ni >> 5) << 20), __double2loint(tv));
+  // Estrin: (1 + c1 r) + r^2 (c2 + c3 r) + r^4 ((c4 + c5 r) + c6 r^2)
+  const double r2 = r * r;
+  const double a0 = fma(c_ws_e2[1], r, 1.0), a1 = fma(c_ws_e2[3], r, c_ws_e2[2]), a2 = fma(c_ws_e2[5], r, c_ws_e2[4]);
+  const double r4 = r2 * r2;
+  const double b0 = fma(a1, r2, a0), b1 = fma(c_ws_e2[6], r2, a2);
+  return fma(b1, r4, b0) * sc;
+}
+
+// rendezvous of a producer / consumer pair once per chunk on the pair's own named barrier (ids 2 .. 13): the
+// producer arrives after filling chunk q, the consumer before reading it, so the consumer reads chunk q while the
+// producer fills chunk q + 1 in the other slot; no polling, the waiting warp sleeps in the barrier unit
+// emulator polynomial sum_j c_j t^j in Estrin form: dependent depth 3 instead of NC - 1 (the producer's chain is
+// what bounds it: ptxas does not interleave the points of a chunk)
+template <int NC>
+__device__ __forceinline__ double ws_poly(const double* cf, double t) {
+  const double t2 = t * t;
+  const double a0 = fma(cf[1], t, cf[0]), a1 = fma(cf[3], t, cf[2]);
+  const double a2 = NC >= 6 ? fma(cf[5], t, cf[4]) : cf[4];
+  if (NC <= 6) {
+    const double t4 = t2 * t2;
+    return fma(a2, t4, fma(a1, t2, a0));
+  } else {
+    const double a3 = cf[6], t4 = t2 * t2;
+    return fma(fma(a3, t2, a2), t4, fma(a1, t2, a0));
+  }
+}
+
+// rendezvous of a producer / consumer pair once per chunk on the pair's own named barrier (ids 2 .. 13): the
+// producer arrives after filling chunk q, the consumer before reading it, so the consumer reads chunk q while the
+// producer fills chunk q + 1 in the other slot; no polling, the waiting warp sleeps in the barrier unit
+// the same for two arguments at once, statement by statement: two independent chains for the scheduler
+template <int KIND>
+__device__ __forceinline__ void ws_exp_fast2(double xa, double xb, const double* __restrict__ tab, double& ya, double& yb) {
+  const double L_HI = KIND == 0 ? 106.30169903639559 : 46.16624130844683;
+  const double L_LO = KIND == 0 ? 5.3171760543154944e-15 : 6.513687597097931e-16;
+  const double MAGIC = 6755399441055744.0;
+  const double ta = fma(xa, L_HI, MAGIC), tb = fma(xb, L_HI, MAGIC);
+  const int na = __double2loint(ta), nb = __double2loint(tb);
+  const double tva = tab[na & 31], tvb = tab[nb & 31];
+  const double fa = ta - MAGIC, fb = tb - MAGIC;
+  double ra = fma(xa, L_HI, -fa), rb = fma(xb, L_HI, -fb);
+  ra = fma(xa, L_LO, ra);
+  rb = fma(xb, L_LO, rb);
+  double pa = fma(c_ws_e2[6], ra, c_ws_e2[5]), pb = fma(c_ws_e2[6], rb, c_ws_e2[5]);
+#pragma unroll
+  for (int k = 4; k >= 1; --k) {
+    pa = fma(pa, ra, c_ws_e2[k]);
+    pb = fma(pb, rb, c_ws_e2[k]);
+  }
+  pa = fma(pa, ra, 1.0);
+  pb = fma(pb, rb, 1.0);
+  ya = pa * __hiloint2double(__double2hiint(tva) + ((na >> 5) << 20), __double2loint(tva));
+  yb = pb * __hiloint2double(__double2hiint(tvb) + ((nb >> 5) << 20), __double2loint(tvb));
+}
+
+__device__ __forceinline__ void ws_bar_pair(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 2) : "memory"); }
+__device__ __forceinline__ void ws_bar_all() { asm volatile("bar.sync 1, %0;" ::"n"(WS_THREADS) : "memory"); }
+
+struct WsRange {  // the CTA's share of a segment
+  int z, i_lo, np, j_lo, j_hi;
+  int c_lo, c_hi;
+};
+
+template <int NC, int KIND, int METAL, bool AGN>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+k_p1d_split(DevCtx c, const int* __restrict__ seg, int nseg, const int* __restrict__ rja_g, const double2* __restrict__ wsw_g, int64_t W,
+            const int* __restrict__ status, const double* __restrict__ amp, double* __restrict__ dvec, double* __restrict__ p_out,
+            double* __restrict__ dvz, int tzw, int nfp_max, int ndz_max) {
+  using namespace c1d_tc;
+  extern __shared__ __align__(16) double sm[];
+  double* crow = sm;                                       // [nfp_max][WS_CROW] consumer table rows
+  double* prow = crow + (size_t)nfp_max * WS_CROW;         // [nfp_max][WS_PROW] producer table rows
+  double* ring = prow + (size_t)nfp_max * WS_PROW;         // [WS_PAIRS][WS_NBUF][WS_CH][32] A
+  double* dat = ring + (size_t)WS_PAIRS * WS_NBUF * WS_CH * 32;  // [ndz_max]
+  double* etab = dat + ndz_max;                            // [32]
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 32) etab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+  const int nitems = (int)((W + 31) / 32);
+  int64_t total = 0;
+  for (int sg = 0; sg < nseg; ++sg) total += nitems * (int64_t)(seg[sg * PL_SEGW + 2] - seg[sg * PL_SEGW + 1]);
+  const int64_t t0 = total * blockIdx.x / gridDim.x, t1 = total * (blockIdx.x + 1) / gridDim.x;
+
+  // both roles walk the segments the same way: range of items, table staging by all threads, two CTA barriers
+  auto seg_range = [&](int sg, int64_t& cum, WsRange& r) {
+    r.z = seg[sg * PL_SEGW];
+    r.i_lo = seg[sg * PL_SEGW + 1];
+    r.np = seg[sg * PL_SEGW + 2] - r.i_lo;
+    r.j_lo = seg[sg * PL_SEGW + 3];
+    r.j_hi = seg[sg * PL_SEGW + 4];
+    const int64_t cost = r.np, zend = cum + nitems * cost;
+    // boundaries on multiples of WS_PAIRS items (the same formula on both sides of a boundary): every pair of a CTA
+    // gets the same number of items of a segment, the CTAs differ by at most one round
+    auto cut = [&](int64_t t) {
+      const int64_t it = ((t - cum + cost - 1) / cost + WS_PAIRS - 1) / WS_PAIRS * WS_PAIRS;
+      return (int)(it < nitems ? it : nitems);
+    };
+    r.c_lo = (t0 > cum) ? cut(t0) : 0;
+    r.c_hi = (t1 < zend) ? ((t1 > cum) ? cut(t1) : 0) : nitems;
+    cum = zend;
+    return r.c_lo < r.c_hi;
+  };
+  auto stage = [&](const WsRange& r, int nfp) {
+    ws_bar_all();  // previous segment fully processed before its tables are overwritten
+    const int f0 = c.zoff_f[r.z], d0 = c.zoff_d[r.z], ndz = c.zoff_d[r.z + 1] - d0;
+    const int g0 = f0 + r.i_lo;
+    for (int t = threadIdx.x; t < 14 * nfp; t += WS_THREADS) {
+      const int col = t / nfp, i = t - col * nfp;
+      const int is = g0 + (i < r.np ? i : r.np - 1);  // the padding repeats the last point (it carries no weight)
+      if (col < 8)
+        crow[i * WS_CROW + col] = c.tab[(size_t)c_ws_csrc[col] * c.nf + is];
+      else
+        prow[i * WS_PROW + col - 8] = c.tab[(size_t)c_ws_psrc[col - 8] * c.nf + is];
+    }
+    for (int t = threadIdx.x; t < nfp; t += WS_THREADS) {
+      const int is = g0 + (t < r.np ? t : r.np - 1);
+      const double2 w2 = t < r.np ? wsw_g[is] : make_double2(0.0, 0.0);  // padding points carry no weight and open no bin
+      crow[t * WS_CROW + 8] = w2.x;
+      crow[t * WS_CROW + 9] = w2.y;
+      crow[t * WS_CROW + 10] = AGN ? c.tab[(size_t)C1D_COL_AGN * c.nf + is] : 0.0;
+      crow[t * WS_CROW + 11] = 0.0;
+    }
+    for (int t = threadIdx.x; t < ndz; t += WS_THREADS) dat[t] = c.data[d0 + t];
+    ws_bar_all();
+  };
+
+  if (warp < WS_PAIRS) {
+    // ---------------- producers: A = HCD P_emu (1 + R Q) ----------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_PREG));
+    double* const myring = ring + (size_t)warp * WS_NBUF * WS_CH * 32 + lane;
+    uint32_t q = 0;  // chunks handed over so far
+    int64_t cum = 0;
+    for (int sg = 0; sg < nseg; ++sg) {
+      WsRange r;
+      if (!seg_range(sg, cum, r)) continue;
+      const int nfp = (r.np + WS_CH - 1) / WS_CH * WS_CH;
+      stage(r, nfp);
+      for (int item = r.c_lo + warp; item < r.c_hi; item += WS_PAIRS) {
+        const int64_t w = (int64_t)item * 32 + lane;
+        const int64_t wv = w < W ? w : W - 1;
+        if (!__any_sync(0xffffffffu, w < W && status[wv] == ST_OK)) continue;  // the consumer skips the item too
+        const double2* a2p = reinterpret_cast<const double2*>(amp + ((int64_t)r.z * W + wv) * C1D_NAMP);
+        double cf[NC + 1];
+#pragma unroll
+        for (int j = 0; j < (NC + 1) / 2; ++j) {
+          const double2 v = __ldg(a2p + A_COEF0 / 2 + j);
+          cf[2 * j] = v.x;
+          cf[2 * j + 1] = v.y;
+        }
+        const double2 h01 = __ldg(a2p + A_H0 / 2), h23 = __ldg(a2p + A_H0 / 2 + 1), h4x = __ldg(a2p + A_H0 / 2 + 2);  // (h0, hA) (hB, hC) (hD, aa)
+        const double2* tp = reinterpret_cast<const double2*>(prow);
+        for (int i0 = 0; i0 < nfp; i0 += WS_CH, tp += WS_CH * (WS_PROW / 2)) {
+          double* dst = myring + (q & (WS_NBUF - 1)) * (WS_CH * 32);
+          bool bad = false;  // arguments outside the fast range (or NaN): redone below with the library function
+#pragma unroll WS_UNROLL
+          for (int u = 0; u < WS_CH; ++u) {
+            const double2 ts = tp[u * (WS_PROW / 2)], d12 = tp[u * (WS_PROW / 2) + 1], d34 = tp[u * (WS_PROW / 2) + 2];
+            const double pl = ws_poly<NC>(cf, ts.x);
+            bad |= !(fabs(pl) < (KIND == 0 ? 280.0 : 700.0));
+            // what does not depend on the exponential first: B = S HCD
+            const double hcd = (h01.x + h01.y * d12.x) + (h23.x * d12.y + (h23.y * d34.x + h4x.x * d34.y));  // hcd_model_rogers_class.py:115-135
+            dst[u * 32] = ws_exp_fast<KIND>(pl, etab) * (ts.y * hcd);                                       // lya_theory.py:690-701
+          }
+          if (__any_sync(0xffffffffu, bad)) {
+#pragma unroll 1
+            for (int u = 0; u < WS_CH; ++u) {
+              const double2 ts = tp[u * (WS_PROW / 2)], d12 = tp[u * (WS_PROW / 2) + 1], d34 = tp[u * (WS_PROW / 2) + 2];
+              const double pl = ws_poly<NC>(cf, ts.x);
+              if (!(fabs(pl) < (KIND == 0 ? 280.0 : 700.0))) {
+                const double hcd = (h01.x + h01.y * d12.x) + (h23.x * d12.y + (h23.y * d34.x + h4x.x * d34.y));
+                dst[u * 32] = ws_exp_slow(pl, KIND) * (ts.y * hcd);
+              }
+            }
+          }
+          ws_bar_pair(warp);  // chunk q is complete; the consumer has finished chunk q - 1, whose slot is filled next
+          ++q;
+        }
+      }
+    }
+  } else {
+    // ---------------- consumers: metals, SiAdd, rebinning, residual ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_CREG));
+    const int cw = warp - WS_PAIRS;
+    const double* const myring = ring + (size_t)cw * WS_NBUF * WS_CH * 32 + lane;
+    uint32_t q = 0;
+    int64_t cum = 0;
+    for (int sg = 0; sg < nseg; ++sg) {
+      WsRange r;
+      if (!seg_range(sg, cum, r)) continue;
+      const int nfp = (r.np + WS_CH - 1) / WS_CH * WS_CH;
+      stage(r, nfp);
+      const int z = r.z, j_lo = r.j_lo, j_hi = r.j_hi;
+      const int f0 = c.zoff_f[z], nfz = c.zoff_f[z + 1] - f0, d0 = c.zoff_d[z];
+      const double* kcol = c.tab + (size_t)C1D_COL_K * c.nf + f0;
+      const double dk = (kcol[nfz - 1] - kcol[0]) / (double)(nfz - 1);
+      // bin the first point of the segment feeds; a set flag on that point belongs to the previous segment
+      const int jc0 = (r.i_lo == 0) ? 0 : rja_g[f0 + r.i_lo] - (__double2hiint(crow[8]) < 0 ? 1 : 0);
+
+      for (int item = r.c_lo + cw; item < r.c_hi; item += WS_PAIRS) {
+        const int64_t w = (int64_t)item * 32 + lane;
+        const bool live = w < W;
+        const int64_t wv = live ? w : W - 1;
+        const bool ok = live && status[wv] == ST_OK;
+        if (!__any_sync(0xffffffffu, ok)) {
+          // rejected walkers carry no model (the reference returns None)
+          if (live)
+            for (int j = j_lo; j < j_hi; ++j) {
+              if (dvec) dvec[wv * c.ldd + d0 + j] = 0.0;
+              if (dvz) dvz[wv * ((int64_t)c.nz * tzw) + (int64_t)z * tzw + j] = 0.0;
+              if (p_out) p_out[wv * c.nd + d0 + j] = qnan;
+            }
+          continue;
+        }
+        const double2* a2p = reinterpret_cast<const double2*>(amp + ((int64_t)z * W + wv) * C1D_NAMP);
+        const double2 s32 = __ldg(a2p + A_S3 / 2), mc1 = __ldg(a2p + A_M0 / 2), c2ab = __ldg(a2p + A_C2A / 2), c3ab = __ldg(a2p + A_C3A / 2);
+        const double2 hdaa = __ldg(a2p + A_AA / 2), sar = __ldg(a2p + A_SA2 / 2), agn2 = __ldg(a2p + A_AGN / 2);  // (hD, aa) (sa2, res) (fagn, -)
+        const double s3 = s32.x, s2 = s32.y, m0 = mc1.x, c1 = mc1.y, c2a = c2ab.x, c2b = c2ab.y, c3a = c3ab.x, c3b = c3ab.y;
+        const double aa = hdaa.y, sa2 = sar.x, res = sar.y, fagn = agn2.x;
+        const double sg3 = (METAL == 0) ? -s3 : s3;  // SiVid grows with k (si_vid_final.py:208)
+        // exp(-s k) and exp(-s^2 k^2) on an evenly spaced grid advance by constant ratios; the products
+        // are re-anchored with an exact evaluation every PL_ANCHOR points
+        const double R3 = ws_exp_anchor(sg3 * dk), R2 = ws_exp_anchor(-s2 * dk), gq = ws_exp_anchor(-2.0 * sa2 * (dk * dk));
+        double E3 = 0.0, E2 = 0.0, gg = 0.0, grho = 0.0;
+        int jc = jc0;
+        double acc0 = 0.0, acc1 = 0.0;
+        auto flush = [&](int j, double m) {
+          const double dj = dat[j] - m;
+          if (live && j >= j_lo) {
+            if (dvec) dvec[wv * c.ldd + d0 + j] = ok ? dj : 0.0;
+            if (dvz) dvz[wv * ((int64_t)c.nz * tzw) + (int64_t)z * tzw + j] = ok ? dj : 0.0;
+            if (p_out) p_out[wv * c.nd + d0 + j] = ok ? m : qnan;
+          }
+        };
+        const double2* rp = reinterpret_cast<const double2*>(crow);
+        for (int i0 = 0; i0 < nfp; i0 += WS_CH, rp += WS_CH * (WS_CROW / 2)) {
+          if ((i0 & (PL_ANCHOR - 1)) == 0) {
+            const double k = rp[0].x;
+            E3 = ws_exp_anchor(sg3 * k);
+            E2 = ws_exp_anchor(-s2 * k);
+            gg = aa * ws_exp_anchor(-1.0 * sa2 * (k * k));  // the SiAdd amplitude rides on the recurrence
+            grho = ws_exp_anchor(-1.0 * sa2 * (2.0 * k * dk + dk * dk));
+          }
+          ws_bar_pair(cw);  // chunk q has been produced
+          const double* src = myring + (q & (WS_NBUF - 1)) * (WS_CH * 32);
+#pragma unroll WS_UNROLL
+          for (int u = 0; u < WS_CH; ++u) {
+            const double2* tp = rp + u * (WS_CROW / 2);
+            const double A = src[u * 32];
+            const double e3 = E3, e2 = E2, g = gg;
+            E3 *= R3;
+            E2 *= R2;
+            gg *= grho;
+            grho *= gq;
+            const double T1 = tp[0].y;
+            double mult;
+            if (METAL == 0) {
+              // si_mult.py:212-218, 267-341:  G = 2 - 2/(1 + E)
+              const double2 v2 = tp[1], v3 = tp[2];
+              const double G3 = fma(-2.0, rcp_fast1(1.0 + e3), 2.0);
+              const double G2 = fma(-2.0, rcp_fast1(1.0 + e2), 2.0);
+              mult = m0 + (c1 * G3 * T1 + G2 * (c2a * v2.x + c2b * v2.y)) + (c3a * v3.x + c3b * v3.y);
+            } else {
+              mult = 1.0 + c1 * e3 + c2a * T1 * e2;  // si_vid_final.py:205-219
+            }
+            if (AGN) mult *= fma(fagn, tp[5].x, 1.0);  // AGN_model.py:116-120
+            const double2 kq = tp[3], rw = tp[4];
+            // si_add.py:168-219 (g = aa exp(-sa2 k^2)), resolution_class.py:99-108, lya_theory.py:778-784
+            const double P = fma(A, mult, kq.x * g) * fma(res, kq.y, 1.0);
+            // rebinning (likelihood.py:147-161): a negative sign on wa opens the next bin
+            if (__double2hiint(rw.x) < 0) {
+              flush(jc, acc0);
+              acc0 = acc1;
+              acc1 = 0.0;
+              ++jc;
+            }
+            acc0 = fma(fabs(rw.x), P, acc0);
+            acc1 = fma(rw.y, P, acc1);
+          }
+          ++q;
+        }
+        while (jc < j_hi) {
+          flush(jc, acc0);
+          acc0 = acc1;
+          acc1 = 0.0;
+          ++jc;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------
@@ -302,6 +649,7 @@ void c1d_p1dw_destroy(c1d_ctx* ctx) {
   cudaFree(st->d_ja);
   cudaFree(st->d_wa);
   cudaFree(st->d_wb);
+  cudaFree(st->d_wsw);
   for (int q = 0; q < PL_NPART; ++q) cudaFree(st->d_seg[q]);
   delete st;
   ctx->p1dw_state = nullptr;
@@ -394,6 +742,26 @@ int c1d_p1dw_prepare(c1d_ctx* ctx) {
   C1D_CUDA(ctx, cudaMemcpy(s->d_ja, ja.data(), c.nf * sizeof(int), cudaMemcpyHostToDevice));
   C1D_CUDA(ctx, cudaMemcpy(s->d_wa, wa.data(), c.nf * sizeof(double), cudaMemcpyHostToDevice));
   C1D_CUDA(ctx, cudaMemcpy(s->d_wb, wb.data(), c.nf * sizeof(double), cudaMemcpyHostToDevice));
+  // warp-specialised kernel: (+-wa, wb) pairs, the sign of wa set on the points that open the next bin
+  {
+    std::vector<double> wsw((size_t)c.nf * 2);
+    int ok = 1;
+    for (int z = 0; z < c.nz && ok; ++z) {
+      const int f0 = zf[z], nfz = zf[z + 1] - f0;
+      for (int i = 0; i < nfz; ++i) {
+        const int step = ja[f0 + i] - (i ? ja[f0 + i - 1] : 0);
+        if (step < 0 || step > 1 || wa[f0 + i] < 0.0 || wb[f0 + i] < 0.0) {
+          ok = 0;
+          break;
+        }
+        wsw[2 * (size_t)(f0 + i)] = step ? -wa[f0 + i] : wa[f0 + i];  // -0.0 keeps the flag on a zero weight
+        wsw[2 * (size_t)(f0 + i) + 1] = wb[f0 + i];
+      }
+    }
+    s->ws_ok = ok;
+    C1D_CUDA(ctx, cudaMalloc(&s->d_wsw, wsw.size() * sizeof(double)));
+    C1D_CUDA(ctx, cudaMemcpy(s->d_wsw, wsw.data(), wsw.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   for (int q = 0; q < PL_NPART; ++q) {
     s->nseg[q] = (int)(segs[q].size() / PL_SEGW);
     C1D_CUDA(ctx, cudaMalloc(&s->d_seg[q], segs[q].size() * sizeof(int)));
@@ -408,7 +776,10 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int w
   P1dwState* st = (P1dwState*)ctx->p1dw_state;
   // C1D_P1D_LAYOUT=warp | lanes overrides the choice by batch size (tests run both forms on the same inputs)
   const char* layout = getenv("C1D_P1D_LAYOUT");
-  const bool force_warp = layout && !strcmp(layout, "warp"), force_lanes = layout && !strcmp(layout, "lanes");
+  // ("lanes" = the single-role walker-per-lane kernel, "split" = the warp-specialised one, both whatever the batch size)
+  const bool force_warp = layout && !strcmp(layout, "warp"), force_split = layout && !strcmp(layout, "split");
+  const bool force_lanes = (layout && !strcmp(layout, "lanes")) || force_split;
+  const bool no_split = layout && !strcmp(layout, "lanes");
   if (!st || force_warp) return 0;
   const c1d_config& cfg = ctx->cfg;
   const int nfz_max = ctx->nfz_max, ndz_max = ctx->ndz_max;
@@ -440,21 +811,53 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int w
 #undef PL_CASE
 #undef PL_PICK
   if (!kern) return 0;
-  C1D_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int threads = pl_threads(U), warps = threads / 32;
+  // the warp-specialised kernel where it applies: evenly spaced k, a compile-time polynomial degree, no GP norm table,
+  // a rebinning operator whose bin index moves by at most one per fine point
+  typedef void (*kern_ws_t)(DevCtx, const int*, int, const int*, const double2*, int64_t, const int*, const double*, double*, double*, double*, int,
+                            int, int);
+  kern_ws_t kws = nullptr;
+  const int nfp_ws = (nfz_max + WS_CH - 1) / WS_CH * WS_CH;
+  const size_t smem_ws = ((size_t)nfp_ws * (WS_CROW + WS_PROW) + (size_t)WS_PAIRS * WS_NBUF * WS_CH * 32 + ndz_max + 32) * sizeof(double) + 16;
+  if (st->ws_ok && !no_split && cfg.uniform_k && nc && !(cfg.emu_kind == 1 && cfg.gp_nm > 0) && smem_ws <= 227 * 1024) {
+    const int wsel = ((nc - 5) << 3) | (cfg.emu_kind << 2) | (cfg.metal_model << 1) | (cfg.has_agn ? 1 : 0);
+#define WS_CASE(NCV)                                                         \
+  case (((NCV) - 5) << 3) | 0: kws = k_p1d_split<NCV, 0, 0, false>; break;   \
+  case (((NCV) - 5) << 3) | 1: kws = k_p1d_split<NCV, 0, 0, true>; break;    \
+  case (((NCV) - 5) << 3) | 2: kws = k_p1d_split<NCV, 0, 1, false>; break;   \
+  case (((NCV) - 5) << 3) | 3: kws = k_p1d_split<NCV, 0, 1, true>; break;    \
+  case (((NCV) - 5) << 3) | 4: kws = k_p1d_split<NCV, 1, 0, false>; break;   \
+  case (((NCV) - 5) << 3) | 5: kws = k_p1d_split<NCV, 1, 0, true>; break;    \
+  case (((NCV) - 5) << 3) | 6: kws = k_p1d_split<NCV, 1, 1, false>; break;   \
+  case (((NCV) - 5) << 3) | 7: kws = k_p1d_split<NCV, 1, 1, true>; break;
+    switch (wsel) {
+      WS_CASE(5)
+      WS_CASE(6)
+      WS_CASE(7)
+    }
+#undef WS_CASE
+  }
+  if (kws)
+    C1D_CUDA(ctx, cudaFuncSetAttribute(kws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+  else
+    C1D_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = kws ? WS_THREADS : pl_threads(U), warps = kws ? WS_PAIRS : pl_threads(U) / 32;
   const int64_t zitems = ((W + 31) / 32) * cfg.nz;
   // a warp-item is 32 walkers long; batches below PL_WAVES waves of (z, 32 walkers) items cut the redshift
   // bins into 2, 4 or 8 segments (bit-identical results, finer items), and below PL_MIN_WAVES2 / 2 waves of
   // the finest items the warp-per-walker kernel takes over (C1D_P1D_PARTS=1|2|4|8 forces the cut)
   const int64_t wave = (int64_t)ctx->num_sms * warps;
   int q = 0;
-  while (q + 1 < PL_NPART && (zitems << q) < PL_WAVES * wave) ++q;
+  // (the pair kernel pays more per segment - staging behind two CTA barriers, per-item set-up in both roles: measured
+  // optimum at ~3 waves of pair items against 10-20 for the single-role kernel)
+  while (q + 1 < PL_NPART && (zitems << q) < (kws ? WS_WAVES : PL_WAVES) * wave) ++q;
   if (const char* e = getenv("C1D_P1D_PARTS")) {
     const int v = atoi(e);
     q = v >= 8 ? 3 : (v >= 4 ? 2 : (v >= 2 ? 1 : 0));
   }
   const int64_t items = ((W + 31) / 32) * st->nseg[q];
-  if (2 * items < PL_MIN_WAVES2 * wave && !force_lanes) return 0;
+  // (pair kernel: only when even the finest cut leaves fewer than 3.5 waves; measured C4: 2048 walkers 0.125 ms warp-per-walker
+  // against 0.139, 4096 walkers 0.223 against 0.19)
+  if (2 * items < PL_MIN_WAVES2 * wave && (!kws || q == PL_NPART - 1) && !force_lanes) return 0;
   int64_t grid = (int64_t)ctx->num_sms;
   if (grid > (items + warps - 1) / warps) grid = (items + warps - 1) / warps;
   if (grid < 1) grid = 1;
@@ -470,8 +873,12 @@ int c1d_p1dw_launch(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int w
     dvz = ctx->ws.dvz;
   }
   ctx->d.gp_emu_in = ctx->ws.emu_in;
-  kern<<<(unsigned)grid, threads, smem, s>>>(ctx->d, st->d_seg[q], st->nseg[q], st->d_ja, st->d_wa, st->d_wb, W, ctx->ws.status, ctx->ws.amp, dvec, p_out,
-                                                dvz, ctx->tzw, nfp_max, ndz_max);
+  if (kws)
+    kws<<<(unsigned)grid, threads, smem_ws, s>>>(ctx->d, st->d_seg[q], st->nseg[q], st->d_ja, reinterpret_cast<const double2*>(st->d_wsw), W,
+                                                    ctx->ws.status, ctx->ws.amp, dvec, p_out, dvz, ctx->tzw, nfp_ws, ndz_max);
+  else
+    kern<<<(unsigned)grid, threads, smem, s>>>(ctx->d, st->d_seg[q], st->nseg[q], st->d_ja, st->d_wa, st->d_wb, W, ctx->ws.status, ctx->ws.amp, dvec, p_out,
+                                                  dvz, ctx->tzw, nfp_max, ndz_max);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return 1;

@@ -114,7 +114,8 @@ def main():
             bad = exp[:, 0] <= -1e99
             okrows = np.where(~bad)[0][:12]
             pref = np.stack([np.concatenate(ora.get_p1d_kms(values=x[i].copy())[0]) for i in okrows]) if len(okrows) else None
-            for env in ({"C1D_P1D_LAYOUT": "warp"}, {"C1D_P1D_LAYOUT": "lanes", "C1D_P1D_PARTS": "1"}, {"C1D_P1D_LAYOUT": "lanes", "C1D_P1D_PARTS": "8"}, {}):
+            for env in ({"C1D_P1D_LAYOUT": "warp"}, {"C1D_P1D_LAYOUT": "lanes", "C1D_P1D_PARTS": "1"}, {"C1D_P1D_LAYOUT": "lanes", "C1D_P1D_PARTS": "8"},
+                        {"C1D_P1D_LAYOUT": "split", "C1D_P1D_PARTS": "1"}, {"C1D_P1D_LAYOUT": "split", "C1D_P1D_PARTS": "4"}, {}):
                 for k in ("C1D_P1D_LAYOUT", "C1D_P1D_PARTS"):
                     os.environ.pop(k, None)
                 os.environ.update(env)

@@ -212,7 +212,7 @@ def test_full_size_properties():
     #     (production picks the form by batch size: the two agree to rounding, not bit for bit)
     import os
 
-    for layout in ("lanes", "warp"):
+    for layout in ("lanes", "split", "warp"):
         os.environ["C1D_P1D_LAYOUT"] = layout
         try:
             lnp_all = like.log_prob_batch(xd)
@@ -304,7 +304,7 @@ def test_edge_batches(golden):
     import os
 
     bad = np.full((37, n), 1.5)
-    for layout in ("lanes", "warp"):
+    for layout in ("lanes", "split", "warp"):
         os.environ["C1D_P1D_LAYOUT"] = layout
         try:
             lnp, blobs = like.log_prob_and_blobs_batch(bad)
@@ -321,7 +321,7 @@ def test_edge_batches(golden):
     reps = 131072 // len(x) + 2
     big = torch.as_tensor(np.tile(x, (reps, 1)), device="cuda:0")
     assert big.shape[0] > 131072
-    for layout in ("lanes", "warp"):
+    for layout in ("lanes", "split", "warp"):
         os.environ["C1D_P1D_LAYOUT"] = layout
         try:
             out = like.log_prob_batch(big)
@@ -395,8 +395,9 @@ def test_every_gp_kernel_on_goldens(golden, monkeypatch, name, kernel):
     like.close()
 
 
+@pytest.mark.parametrize("layout", ["lanes", "split"])
 @pytest.mark.parametrize("name", ["c1", "c3", "c4"])
-def test_stage3_segments_are_bit_identical(monkeypatch, name):
+def test_stage3_segments_are_bit_identical(monkeypatch, name, layout):
     """medium batches cut every redshift bin of the walker-per-lane stage 3 into 2, 4 or 8 k-segments
     (C1D_P1D_PARTS forces the cut): log-posteriors, per-z log-likelihoods and the model P1D must not
     change by a single bit, rejected and ragged rows included"""
@@ -409,7 +410,7 @@ def test_stage3_segments_are_bit_identical(monkeypatch, name):
     x = np.concatenate([synth.walkers_sweep(spec, 1500, seed=21, frac_out=0.02), synth.walkers_ball(spec, 77, seed=3)])
     x[40:72] = 1.5  # one whole 32-walker item outside the cube
     xd = torch.as_tensor(x, device="cuda:0")
-    monkeypatch.setenv("C1D_P1D_LAYOUT", "lanes")
+    monkeypatch.setenv("C1D_P1D_LAYOUT", layout)
     ref = None
     for parts in (1, 2, 4, 8):
         monkeypatch.setenv("C1D_P1D_PARTS", str(parts))
@@ -426,7 +427,7 @@ def test_stage3_segments_are_bit_identical(monkeypatch, name):
     like.close()
 
 
-@pytest.mark.parametrize("layout", ["lanes", "warp"])
+@pytest.mark.parametrize("layout", ["lanes", "split", "warp"])
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
 def test_both_stage3_forms_on_goldens(golden, monkeypatch, name, layout):
     """the walker-per-lane and the warp-per-walker stage 3 (chosen by batch size in production) are both
@@ -488,10 +489,12 @@ def test_gp_large_batch_kernel():
     like.close()
 
 
-def test_non_blocking_stream_first_call(golden):
+def test_non_blocking_stream_first_call(golden, monkeypatch):
     """the first evaluation of a fresh context (workspace allocation and its memsets, the finalisation copies) and a
     set_icov re-upload, issued on a non-blocking side stream: same rows as on the default stream"""
     import torch
+
+    monkeypatch.setenv("C1D_P1D_LAYOUT", "warp")  # one form of stage 3 whatever the batch size: rows comparable bit for bit
 
     spec, ref = golden("dr1_full_nn")
     x = np.tile(ref["x"], (40, 1))
