@@ -15,7 +15,7 @@ from . import compile as _cmp
 
 ABI_VERSION = 7
 LIB_NAME = "libcup1d_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+LIB_PATH = os.environ.get("C1D_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)  # C1D_LIB: a variant build (kernel tuning experiments)
 
 FLAG_ZMASK = 1
 FLAG_NO_HULL = 2

@@ -313,12 +313,18 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ seg, int nseg, const int* __
 // (anchors sit on multiples of PL_ANCHOR points of the redshift bin), so the results stay bit-identical
 // for any number of segments.
 // ------------------------------------------------------------------------------------
+#ifndef WS_CH_
+#define WS_CH_ 16
+#define WS_UNROLL_ 4
+#define WS_PREG_ 64
+#define WS_CREG_ 96
+#endif
 constexpr int WS_PAIRS = 12, WS_THREADS = 64 * WS_PAIRS;
-constexpr int WS_CH = 16, WS_NBUF = 2;  // points per chunk, chunks in the ring (double buffer)
-constexpr int WS_UNROLL = 4;
+constexpr int WS_CH = WS_CH_, WS_NBUF = 2;  // points per chunk, chunks in the ring (double buffer)
+constexpr int WS_UNROLL = WS_UNROLL_;
 constexpr int WS_WAVES = 3;
 constexpr int WS_PROW = 6, WS_CROW = 12;     // doubles per producer / consumer table row
-constexpr int WS_PREG = 64, WS_CREG = 96;    // registers per thread after setmaxnreg (launch: 80)
+constexpr int WS_PREG = WS_PREG_, WS_CREG = WS_CREG_;   // registers per thread after setmaxnreg (launch: 80)
 // producer row: (t, S) (D1, D2) (D3, D4);  consumer row: (k, T1) (T2A, T2BC) (T3A, T3BC) (KT, Q) (+-wa, wb) (AGN, -)
 __device__ __constant__ int c_ws_psrc[6] = {C1D_COL_T, C1D_COL_S, C1D_COL_D1, C1D_COL_D2, C1D_COL_D3, C1D_COL_D4};
 __device__ __constant__ int c_ws_csrc[8] = {C1D_COL_K, C1D_COL_T1, C1D_COL_T2A, C1D_COL_T2BC, C1D_COL_T3A, C1D_COL_T3BC, C1D_COL_KT, C1D_COL_Q};
