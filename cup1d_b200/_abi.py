@@ -48,7 +48,8 @@ class Config(C.Structure):
         ("uniform_k", C.c_int32),
         ("has_agn", C.c_int32),
         ("gp_nm", C.c_int32), ("gp_nkn", C.c_int32),
-        ("reserved_i", C.c_int32 * 3),
+        ("hcd_gate", C.c_int32),
+        ("reserved_i", C.c_int32 * 2),
         ("As_fid", C.c_double), ("ns_fid", C.c_double), ("nrun_fid", C.c_double),
         ("L_emu", C.c_double), ("L_star", C.c_double),
         ("blob_fid", C.c_double * 6), ("star_lo", C.c_double * 3), ("star_hi", C.c_double * 3),

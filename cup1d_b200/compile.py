@@ -128,6 +128,18 @@ def compile_z_functions(spec):
             fam = dict(src)
             fam.update(ztype="pivot", znodes=np.zeros(0), coeffs=np.asarray(src["coeffs"], dtype=float)[-1:],
                        param_idx=np.asarray(src["param_idx"])[-1:], zmax=np.nan, otype="exp")
+        elif q == "HCD_damp1" and spec["cont"]["hcd_model"] == "mcdonald":
+            # HCD_Model_McDonald2005 nulls on the constant coefficient, not on the value (hcd_model_McDonald2005.py:75-76)
+            fam = dict(fams[q])
+            fam["null"] = np.nan
+        elif q == "HCD_damp2" and spec["cont"]["hcd_model"] == "mcdonald":
+            # the gate: exp(constant coefficient), 0 when that coefficient is <= the null value
+            src = fams["HCD_damp1"]
+            fam = dict(src)
+            fam.update(ztype="pivot", znodes=np.zeros(0), coeffs=np.asarray(src["coeffs"], dtype=float)[-1:],
+                       param_idx=np.asarray(src["param_idx"])[-1:], zmax=np.nan, otype="exp")
+        elif q in ("HCD_damp3", "HCD_damp4") and spec["cont"]["hcd_model"] == "mcdonald":
+            fam = _neutral_family(0.0, "const")
         elif q == "R_coeff" and not spec["cont"]["apply_resolution"]:
             # the resolution term is applied only if some R_coeff is free (lya_theory.py:712-722)
             fam = _neutral_family(0.0, "const")
@@ -232,6 +244,8 @@ def compile_tables(spec):
                 tab[COL_D1 + it, s] = 1 / (a_z * np.exp(k * b_z) - 1) ** 2
         elif cont["hcd_model"] == "boss":
             tab[COL_D1, s] = 1 / (1 - (1 / (15000 * k - 8.9)))  # hcd_boss.py:5-7
+        elif cont["hcd_model"] == "mcdonald":
+            tab[COL_D1, s] = 0.018 + 1 / (15000 * k - 8.9)  # hcd_model_McDonald2005.py:91
         else:
             raise NotImplementedError("hcd model " + str(cont["hcd_model"]))
         # si_add.py:172-217
@@ -393,6 +407,7 @@ def compile_spec(spec):
     cfg = {
         "uniform_k": int(uniform),
         "has_agn": int(cont.get("agn") is not None and "ln_AGN" in spec["families"]),
+        "hcd_gate": int(cont["hcd_model"] == "mcdonald"),
         "nz": nz, "ndim": ndim, "n_emu": n_emu, "nd": nd, "nf": nf,
         "ell_width": int(ell), "rebin_width": int(rwidth),
         "n_layers": 0, "layer_dims": [0] * (MAX_LAYERS + 1),

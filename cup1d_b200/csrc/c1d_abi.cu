@@ -231,7 +231,7 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
   d.gp_ntrain = c.gp_ntrain; d.gp_nnorm = c.gp_nnorm; d.gp_imf = c.gp_imf;
   d.gp_nm = c.emu_kind == 1 ? c.gp_nm : 0; d.gp_nkn = c.emu_kind == 1 ? c.gp_nkn : 0;
   d.metal_model = c.metal_model; d.apply_resolution = c.apply_resolution; d.has_full = c.has_full;
-  d.has_gauss = c.has_gauss; d.n_hull_facets = c.n_hull_facets; d.uniform_k = c.uniform_k; d.has_agn = c.has_agn;
+  d.has_gauss = c.has_gauss; d.n_hull_facets = c.n_hull_facets; d.uniform_k = c.uniform_k; d.has_agn = c.has_agn; d.hcd_gate = c.hcd_gate;
   d.idx_As = c.idx_As; d.idx_ns = c.idx_ns; d.idx_nrun = c.idx_nrun;
   for (int j = 0; j < C1D_MAX_EMU; ++j) d.emu_code[j] = c.emu_code[j];
   d.As_fid = c.As_fid; d.ns_fid = c.ns_fid; d.nrun_fid = c.nrun_fid; d.L_emu = c.L_emu; d.L_star = c.L_star;

@@ -37,7 +37,7 @@ struct DevCtx {
   int ldd;  // row stride of the residual buffer = nd rounded up to a multiple of 64 (zero padded)
   int layer_dims[C1D_MAX_LAYERS + 1];
   int gp_ntrain, gp_nnorm, gp_imf, gp_nm, gp_nkn;
-  int metal_model, apply_resolution, has_full, has_gauss, n_hull_facets, uniform_k, has_agn;
+  int metal_model, apply_resolution, has_full, has_gauss, n_hull_facets, uniform_k, has_agn, hcd_gate;
   int idx_As, idx_ns, idx_nrun;
   int emu_code[C1D_MAX_EMU];
   double As_fid, ns_fid, nrun_fid, L_emu, L_star;

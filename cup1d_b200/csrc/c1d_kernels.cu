@@ -189,8 +189,9 @@ k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ st
       a[A_C2B] = 0.0; a[A_C3A] = 0.0; a[A_C3B] = 0.0;
     }
     a[A_H0] = 1.0 + q[C1D_Q_HCD_CONST];  // hcd_model_rogers_class.py:116
-    a[A_HCD1 + 0] = q[C1D_Q_HCD1];
-    a[A_HCD1 + 1] = q[C1D_Q_HCD2];
+    // HCD_Model_McDonald2005 (hcd_model_McDonald2005.py:71-92): A_damp(z) unless the constant coefficient is nulled
+    a[A_HCD1 + 0] = (!c.hcd_gate || q[C1D_Q_HCD2] > 0.0) ? q[C1D_Q_HCD1] : 0.0;
+    a[A_HCD1 + 1] = c.hcd_gate ? 0.0 : q[C1D_Q_HCD2];
     a[A_HCD1 + 2] = q[C1D_Q_HCD3];
     a[A_HCD1 + 3] = q[C1D_Q_HCD4];
     a[A_AA] = q[C1D_Q_F_SIADD] * q[C1D_Q_F_SIADD];  // si_add.py:219
@@ -846,26 +847,34 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
+template <int NST>  // cp.async stages: 2 for batches that fill the machine (3 CTAs per SM), 4 for small ones (latency of the K loop)
 __global__ void __launch_bounds__(256)
-k_chi2_dmma(int64_t W, int ndp, const double* __restrict__ dvec, const double* __restrict__ Cp,
+k_chi2_dmma(int64_t W, int ndp, int grp, const double* __restrict__ dvec, const double* __restrict__ Cp,
             double* __restrict__ partial) {
   extern __shared__ __align__(16) double qsm[];
   double (*As)[Q_TW][Q_ASTR] = reinterpret_cast<double (*)[Q_TW][Q_ASTR]>(qsm);
-  double (*Bs)[Q_KC][Q_BSTR] = reinterpret_cast<double (*)[Q_KC][Q_BSTR]>(qsm + 2 * Q_TW * Q_ASTR);
-  double (*red)[Q_TW] = reinterpret_cast<double (*)[Q_TW]>(qsm + 2 * Q_TW * Q_ASTR + 2 * Q_KC * Q_BSTR);
+  double (*Bs)[Q_KC][Q_BSTR] = reinterpret_cast<double (*)[Q_KC][Q_BSTR]>(qsm + NST * Q_TW * Q_ASTR);
+  double (*red)[Q_TW] = reinterpret_cast<double (*)[Q_TW]>(qsm + NST * Q_TW * Q_ASTR + NST * Q_KC * Q_BSTR);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;
-  // walker tiles are the fast grid index: all CTAs in flight stream the same column tile of C^-1.
-  // (Measured alternative, column-tile pairs fastest: the residuals are then read from HBM once, 371 MB
-  // instead of 1.94 GB per launch, but the kernel takes 1.28 ms instead of 1.10 ms — it is DMMA-bound,
-  // the extra reads are hidden — so the faster order stays.)
-  const int64_t w0 = (int64_t)blockIdx.x * Q_TW;
+  // Grid order: groups of `grp` walker tiles; inside a group the column tiles from the costliest down, the walker
+  // tiles of the group fastest.  The CTAs in flight stream the same column tile of C^-1, and the residual rows of a
+  // group (grp x 128 walkers x ndp doubles, 46 MB at grp = 64) stay in L2 while its column tiles re-read them, so they
+  // come from HBM about once instead of once per column tile (2.16 GB -> see DESIGN.md; with one group = the whole
+  // batch, the former order, every column-tile pass streams the residuals again).  The other extreme, column tiles
+  // fastest, also reads them once but measured 16 % slower (1.28 ms against 1.10 ms).
   const int ntj = ndp / Q_TJ;
+  const int nrb = (int)((W + Q_TW - 1) / Q_TW);
+  const int per = grp * ntj;
+  const int g = (int)blockIdx.x / per, rem = (int)blockIdx.x - g * per;
+  const int gl = min(grp, nrb - g * grp);  // walker tiles in this group (the last one may be short)
+  const int by = rem / gl;
+  const int64_t w0 = (int64_t)(g * grp + rem - by * gl) * Q_TW;
   // one column tile per CTA, the costliest (last) tiles first.  (Measured against pairing tiles
   // (y, ntj-1-y) for equal work per CTA: the smaller units balance medium batches over the SMs, 0.135 ->
   // 0.088 ms at 4096 walkers and 0.199 -> 0.164 ms at 8192 on C4, and tie at 65 536.)
   {
-    const int jt = ntj - 1 - (int)blockIdx.y;
+    const int jt = ntj - 1 - by;
     const int j0 = jt * Q_TJ;
     const int nk = (jt + 1) * (Q_TJ / Q_KC);
     const int kdiag = jt * (Q_TJ / Q_KC);
@@ -894,15 +903,21 @@ k_chi2_dmma(int64_t W, int ndp, const double* __restrict__ dvec, const double* _
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    load_chunk(0, 0);
+    // NST - 1 chunks in flight; one (possibly empty) commit group per trip keeps the group count uniform
+#pragma unroll
+    for (int p = 0; p < NST - 1; ++p) {
+      if (p < nk)
+        load_chunk(p, p);
+      else
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int kc = 0; kc < nk; ++kc) {
-      const int buf = kc & 1;
-      if (kc + 1 < nk) {
-        load_chunk(kc + 1, buf ^ 1);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
+      const int buf = kc % NST;
+      if (kc + NST - 1 < nk)
+        load_chunk(kc + NST - 1, (kc + NST - 1) % NST);
+      else
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(NST - 1) : "memory");
       __syncthreads();
       if (kc == kdiag) {
         // everything accumulated so far is strictly below the diagonal block: count it twice
@@ -1066,11 +1081,23 @@ int c1d_launch_chi2z(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
 int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
   const int ndp = ctx->d.ldd;
   const int ntj = ndp / Q_TJ;
-  dim3 grid((unsigned)((W + Q_TW - 1) / Q_TW), (unsigned)ntj);
-  const size_t smem = (size_t)(2 * Q_TW * Q_ASTR + 2 * Q_KC * Q_BSTR + 2 * Q_TW) * sizeof(double);
+  const int nrb = (int)((W + Q_TW - 1) / Q_TW);
+  int grp = 64;  // 8192 walkers: 46 MB of residuals at ndp = 704, well inside the 126 MB L2
+  if (const char* e = getenv("C1D_CHI2_GROUP")) grp = atoi(e) > 0 ? atoi(e) : grp;
+  if (grp > nrb) grp = nrb;
+  // batches of at most one CTA per SM are bound by the latency of the K loop (up to 44 dependent cp.async round trips
+  // with two stages): four stages there (C4, 1024 walkers: see DESIGN.md), the same arithmetic in the same order
+  int nst = (nrb * ntj <= ctx->num_sms) ? 4 : 2;
+  if (const char* e = getenv("C1D_CHI2_STAGES")) nst = atoi(e) == 4 ? 4 : 2;
+  const size_t smem = (size_t)(nst * Q_TW * Q_ASTR + nst * Q_KC * Q_BSTR + 2 * Q_TW) * sizeof(double);
   // per launch, not once per process: the attribute is per device and a process may own several contexts
-  C1D_CUDA(ctx, cudaFuncSetAttribute(k_chi2_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_chi2_dmma<<<grid, 256, smem, s>>>(W, ndp, ctx->ws.dvec, ctx->icov_pad, ctx->ws.chi2p);
+  if (nst == 4) {
+    C1D_CUDA(ctx, cudaFuncSetAttribute(k_chi2_dmma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chi2_dmma<4><<<(unsigned)(nrb * ntj), 256, smem, s>>>(W, ndp, grp, ctx->ws.dvec, ctx->icov_pad, ctx->ws.chi2p);
+  } else {
+    C1D_CUDA(ctx, cudaFuncSetAttribute(k_chi2_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chi2_dmma<2><<<(unsigned)(nrb * ntj), 256, smem, s>>>(W, ndp, grp, ctx->ws.dvec, ctx->icov_pad, ctx->ws.chi2p);
+  }
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return C1D_OK;

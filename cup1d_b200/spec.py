@@ -505,9 +505,28 @@ def spec_from_likelihood(like):
         hcd_model = "rogers"
     elif hname == "HCD_BOSS":
         hcd_model = "boss"
+    elif hname == "HCD_Model_McDonald2005":
+        hcd_model = "mcdonald"
     else:
         raise NotImplementedError("HCD model " + hname)
-    for model in (si_mult, si_add, hcd, res):
+    if hcd_model == "mcdonald":
+        # not a Contaminant: pivot polynomial in ln_A_damp_i with parameter i feeding coefficient [n-1-i]
+        # (hcd_model_McDonald2005.py:41-63, 94-131), A_damp = exp(poly(ln((1+z)/(1+z_0)))), nulled on the constant coefficient
+        coeffs = np.array(hcd.ln_A_damp_coeff, dtype=float)
+        n = len(coeffs)
+        pidx = np.full(n, -1, dtype=np.int64)
+        matched = [p for p in free_names if "ln_A_damp" in p]
+        if matched and len(matched) != n:
+            raise ValueError("number of params mismatch in get_A_damp_coeffs")  # hcd_model_McDonald2005.py:117-121
+        for i in range(n):
+            nm = "ln_A_damp_" + str(i)
+            if nm in free_names:
+                pidx[n - 1 - i] = free_names.index(nm)
+        families["HCD_damp1"] = {
+            "ztype": "pivot", "otype": "exp", "znodes": np.zeros(0), "coeffs": coeffs, "param_idx": pidx,
+            "z0": float(hcd.z_0), "null": float(hcd.null_value), "zmax": np.nan,
+        }
+    for model in (si_mult, si_add, res) + (() if hcd_model == "mcdonald" else (hcd,)):
         for name in model.list_coeffs:
             if model.prop_coeffs[name + "_ztype"].endswith("_smspl"):
                 raise NotImplementedError("interp_smspl not supported: " + name)

@@ -469,6 +469,27 @@ def build_spec(
     return spec
 
 
+def use_mcdonald_hcd(spec, n_hcd=2):
+    """Switch a built spec to HCD_Model_McDonald2005 (hcd_model_McDonald2005.py): the two HCD_damp1 parameters
+    become ln_A_damp_0 (constant coefficient, prior [-7, 2.5] so that walkers cross the null value -6) and, with
+    ``n_hcd=2``, ln_A_damp_1 (slope in ln((1+z)/(1+z_0)), held fixed otherwise); the other Rogers amplitudes stay in the
+    parameter vector without effect."""
+    fam = spec["families"]
+    old = fam["HCD_damp1"]
+    i0, i1 = int(old["param_idx"][0]), int(old["param_idx"][1])
+    p = spec["params"]
+    p["min"][i0], p["max"][i0], p["value"][i0] = -7.0, 2.5, -1.2
+    p["min"][i1], p["max"][i1], p["value"][i1] = -3.0, 3.0, 0.7
+    fam["HCD_damp1"] = {
+        "ztype": "pivot", "otype": "exp", "znodes": np.zeros(0),
+        "coeffs": np.array([0.7, -1.2]) if n_hcd == 2 else np.array([-1.2]),
+        "param_idx": np.array([i1, i0], dtype=np.int64) if n_hcd == 2 else np.array([i0], dtype=np.int64),
+        "z0": 3.0, "null": -6.0, "zmax": np.nan,
+    }
+    spec["cont"]["hcd_model"] = "mcdonald"
+    return spec
+
+
 def truth_point(spec):
     """cube coordinates of the fiducial parameter values"""
     p = spec["params"]

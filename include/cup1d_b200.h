@@ -141,7 +141,10 @@ typedef struct c1d_config {
   int32_t uniform_k;          /* 1 = the model k grid of every z is evenly spaced (linspace, likelihood.py:90-94) */
   int32_t has_agn;            /* AGN feedback term present (off in the reference: model_contaminants.py:138-154) */
   int32_t gp_nm, gp_nkn;      /* GP norm table: mean-flux nodes, k nodes + 1 (0, 0 = k-independent norm) */
-  int32_t reserved_i[3];
+  int32_t hcd_gate;           /* 1 = HCD_Model_McDonald2005 (hcd_model_McDonald2005.py:71-92): the amplitude quantity HCD_damp1 = A_damp(z)
+                                 counts only while the gate quantity HCD_damp2 (the constant coefficient against the null value) is > 0;
+                                 column D1 holds 0.018 + 1/(15000 k - 8.9).  0 = Rogers / BOSS (was reserved: zero-filled by older callers) */
+  int32_t reserved_i[2];
   double As_fid, ns_fid, nrun_fid;
   double L_emu;               /* ln(kp_emu / ks)   lya_theory.py:299 */
   double L_star;              /* ln(kp_star / ks)  lya_theory.py:565 */

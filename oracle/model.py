@@ -242,6 +242,23 @@ def hcd_rogers_contamination(rg, vals, zs, k_kms):
     return out
 
 
+def hcd_mcdonald_contamination(fam, zs, k_kms, pvalues):
+    """hcd_model_McDonald2005.py:71-92: 1 + A_damp(z) (0.018 + 1/(15000 k - 8.9)), A_damp = exp(poly(ln((1+z)/(1+z_0)))),
+    the whole term 1 when the constant coefficient is <= the null value (:75-76).  The reference's own multi-redshift
+    call only runs in that nulled state (``if A_damp == 0`` on an array raises otherwise); the formula is applied
+    per redshift bin here, as its single-redshift form reads."""
+    coeff = family_coeffs(fam, pvalues)
+    out = []
+    for iz in range(len(k_kms)):
+        if coeff[-1] <= fam["null"]:
+            out.append(np.ones_like(k_kms[iz]))
+            continue
+        xz = np.log((1 + zs[iz]) / (1 + fam["z0"]))
+        a_damp = np.exp(np.polyval(coeff, xz))
+        out.append(1 + a_damp * (0.018 + 1 / (15000 * k_kms[iz] - 8.9)))
+    return out
+
+
 def hcd_boss_contamination(vals, k_kms):
     """hcd_boss.py:5-7, 66-91"""
     out = []
@@ -455,6 +472,8 @@ class OracleTheory(object):
             names = ["HCD_damp1", "HCD_damp2", "HCD_damp3", "HCD_damp4", "HCD_const"]
             vals = {n: nulled_value(fam[n], z, pvalues) for n in names}
             hcd = hcd_rogers_contamination(cont["rogers"], vals, z, k_kms)
+        elif cont["hcd_model"] == "mcdonald":
+            hcd = hcd_mcdonald_contamination(fam["HCD_damp1"], z, k_kms, pvalues)
         else:
             vals = {"HCD_damp1": nulled_value(fam["HCD_damp1"], z, pvalues)}
             hcd = hcd_boss_contamination(vals, k_kms)

@@ -124,6 +124,10 @@ def simulate(cfg, F, x, zmask=None, apply_hull=True):
                 mult = 1 + q[4] / om * np.exp(q[5] * k) + q[6] / om * tab[cc.COL_T1, s] * np.exp(-q[7] * k)
             if cfg.get("has_agn"):
                 mult = mult * (1 + (q[18] if q[19] > 0 else 0.0) * tab[cc.COL_AGN, s])
+            if cfg.get("hcd_gate"):
+                q = q.copy()
+                q[12] = q[12] if q[13] > 0 else 0.0
+                q[13] = 0.0
             hcd = (1 + q[16]) + q[12] * tab[cc.COL_D1, s] + q[13] * tab[cc.COL_D2, s] + q[14] * tab[cc.COL_D3, s] + q[15] * tab[cc.COL_D4, s]
             add = q[10] ** 2 * tab[cc.COL_KT, s] * np.exp(-q[11] ** 2 * k * k)
             res = 1 + (q[17] if cfg["apply_resolution"] else 0.0) * tab[cc.COL_Q, s]

@@ -75,3 +75,50 @@ def test_agn_template_against_reference_model():
                "param_idx": np.full(n, -1), "z0": float(ref["z0"]), "null": float(ref["null"]), "zmax": np.nan}
         got = om.agn_contamination(agn, fam, np.array([z]), [k], None)[0]
         assert np.max(np.abs(got - exp)) <= 1e-15
+
+
+def test_hcd_mcdonald2005_against_reference_model():
+    """the reference's own HCD_Model_McDonald2005.get_contamination (tools/make_golden.py mcdonald_kat): nulled and
+    live amplitudes, one and two coefficients, coefficients from like_params"""
+    ref = np.load(os.path.join(GOLDEN_DIR, "mcdonald_kat.npz"))
+    k = ref["k"]
+    n_null = 0
+    for case, exp in zip(ref["cases"], ref["out"]):
+        z, n = case[0], int(case[1])
+        fam = {"ztype": "pivot", "otype": "exp", "znodes": np.zeros(0), "coeffs": case[2 : 2 + n],
+               "param_idx": np.full(n, -1), "z0": float(ref["z0"]), "null": float(ref["null"]), "zmax": np.nan}
+        got = om.hcd_mcdonald_contamination(fam, np.array([z]), [k], None)[0]
+        assert np.max(np.abs(got - exp)) <= 4e-16 * np.max(np.abs(exp))
+        n_null += int(np.all(exp == 1.0))
+    assert 0 < n_null < len(ref["cases"])
+
+
+def test_hcd_mcdonald2005_compiled_tables():
+    """a synthetic configuration switched to HCD_Model_McDonald2005: the compiled tables (through the NumPy mirror of
+    the kernels) against the oracle, walkers on both sides of the null value"""
+    from cup1d_b200 import compile as cc
+    from cup1d_b200 import synth
+    from oracle.model import OracleLikelihood
+    import devsim
+
+    emu = synth.synth_nn_emulator(seed=5, nhidden=2, max_neurons=16, head=8)
+    for n_hcd in (1, 2):
+        spec = synth.build_spec(emu, grid="chab", rebin_k=2, full_cov=False, nz=4, nz_igm=2, seed=9)
+        synth.use_mcdonald_hcd(spec, n_hcd=n_hcd)
+        ora = OracleLikelihood(spec)
+        p_truth = np.concatenate(ora.get_p1d_kms(values=synth.truth_point(spec))[0])
+        synth.attach_mock_data(spec, p_truth)
+        ora = OracleLikelihood(spec)
+        x = synth.walkers_ball(spec, 12, seed=3)
+        i0 = spec["params"]["names"].index("HCD_damp1_0")
+        x[:4, i0] = 0.05  # ln_A_damp_0 = -6.5: below the null value, HCD term = 1
+        exp = ora.log_prob_and_blobs_many(x)
+        cfg, F = cc.compile_spec(spec)
+        got = devsim.simulate(cfg, F, x)
+        ok = exp[:, 0] > -1e99
+        assert ok.sum() >= 8
+        np.testing.assert_allclose(got["lnp"][ok], exp[ok, 0], rtol=1e-10, atol=1e-8)
+        # the nulled walkers differ from the live ones: the term is in the model
+        x2 = x[:1].copy()
+        x2[0, i0] = 0.8
+        assert abs(ora.log_prob_and_blobs_many(x2)[0, 0] - exp[0, 0]) > 1e-3

@@ -278,6 +278,33 @@ def make_agn_kat():
     print("agn_kat          %d cases" % len(cases))
 
 
+def make_mcdonald_kat():
+    """HCD_Model_McDonald2005.get_contamination of the reference (hcd_model_McDonald2005.py:83-92) on a few
+    (z, coefficients), one redshift per call (its multi-redshift call only runs nulled), free parameters through
+    like_params as well as constructor coefficients"""
+    rh.setup()
+    from cup1d.contaminants.hcd_model_McDonald2005 import HCD_Model_McDonald2005
+    from cup1d.likelihood.likelihood_parameter import LikelihoodParameter
+
+    k = np.linspace(1e-3, 0.04, 200)
+    cases, outs = [], []
+    for z in (2.0, 2.2, 3.0, 3.7, 4.4):
+        for coeff in ([0.0, -1.2], [0.7, -0.3], [-2.0], [0.0, -6.0], [0.3, -6.5], [1.5, 2.0]):
+            m = HCD_Model_McDonald2005(ln_A_damp_coeff=list(coeff))
+            c = m.get_contamination(z, k)
+            cases.append([z, len(coeff)] + list(coeff) + [0.0] * (2 - len(coeff)))
+            outs.append(np.ones_like(k) * c)
+    # through like_params: parameter i feeds coefficient [n-1-i]
+    m = HCD_Model_McDonald2005(free_param_names=["ln_A_damp_0", "ln_A_damp_1"])
+    lp = [LikelihoodParameter(name="ln_A_damp_0", value=-0.8, min_value=-7, max_value=2.5),
+          LikelihoodParameter(name="ln_A_damp_1", value=1.1, min_value=-10, max_value=10)]
+    cases.append([3.4, 2, 1.1, -0.8])
+    outs.append(np.ones_like(k) * m.get_contamination(3.4, k, like_params=lp))
+    np.savez_compressed(os.path.join(OUT, "mcdonald_kat.npz"), k=k, cases=np.array(cases), out=np.array(outs),
+                        null=m.null_value, z0=m.z_0)
+    print("mcdonald_kat     %d cases" % len(cases))
+
+
 def make_theory_kat(name, emu, grid, nz, rebin_k, seed, **kw):
     """Theory.get_p1d_kms (lya_theory.py:610-814) and Likelihood.get_p1d_kms (likelihood.py:722-785) of the
     reference off the likelihood's own grid: a redshift subset, a custom k grid, full / partial / empty
@@ -349,6 +376,7 @@ CONFIGS["theory_kat_nyx"] = lambda: make_theory_kat(
     "theory_kat_nyx", RefGPEmulator(small_gp(52, "nyx"), "synthetic_nyx_gp", "nyx"), "dr1c", 5, 4, 1200,
     use_hull=True, vary_alphas=True, use_star_priors={"Delta2_star": [0.2, 0.6]}, use_ic=False)
 CONFIGS["agn_kat"] = make_agn_kat
+CONFIGS["mcdonald_kat"] = make_mcdonald_kat
 
 if __name__ == "__main__":
     assert rh.available(), "needs /root/reference"
