@@ -2,6 +2,8 @@
 // stage kernels on the caller's stream.  See include/cup1d_b200.h for the contract.
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 #include "c1d_internal.h"
 
 static const char* k_no_ctx = "null context";
@@ -360,6 +362,12 @@ static int timing_drain(c1d_ctx* ctx) {
     if (ctx->timing) C1D_CUDA(ctx, cudaEventRecord(ctx->evr[ctx->ev_pending][i], s));    \
   } while (0)
 
+// NVTX range around the launches of one stage (tracing): visible in nsys / ncu --nvtx timelines
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 extern "C" int c1d_loglike_batch(c1d_ctx* ctx, const double* x_dev, int64_t W, double* lnp_dev,
                                  double* lnl_z_dev, double* blobs_dev, double* chi2_dev,
                                  uint32_t flags, void* cuda_stream) {
@@ -382,18 +390,34 @@ extern "C" int c1d_loglike_batch(c1d_ctx* ctx, const double* x_dev, int64_t W, d
     int64_t n = (W - w0 < chunk) ? (W - w0) : chunk;
     double* blobs = blobs_dev ? blobs_dev + w0 * 6 : ctx->ws.blobs;
     if (ctx->timing && ctx->ev_pending == C1D_TRING && (rc = timing_drain(ctx))) return rc;
+    NvtxRange chunk_range("c1d_loglike_batch chunk");
     TICK(0);
-    if ((rc = c1d_launch_stage1(ctx, x_dev + w0 * c.ndim, n, blobs, flags, s))) return rc;
+    {
+      NvtxRange r("c1d stage 1: parameters, priors, emulator inputs");
+      if ((rc = c1d_launch_stage1(ctx, x_dev + w0 * c.ndim, n, blobs, flags, s))) return rc;
+    }
     TICK(1);
-    if ((rc = c1d_launch_emulator(ctx, ctx->ws.emu_in, n * c.nz, ctx->ws.amp, C1D_NAMP, flags, s))) return rc;
+    {
+      NvtxRange r("c1d stage 2: emulator");
+      if ((rc = c1d_launch_emulator(ctx, ctx->ws.emu_in, n * c.nz, ctx->ws.amp, C1D_NAMP, flags, s))) return rc;
+    }
     TICK(2);
-    if ((rc = c1d_launch_stage3(ctx, n, nullptr, use_full, want_chi2z, s))) return rc;
+    {
+      NvtxRange r("c1d stage 3: contaminants, rebinning, residual");
+      if ((rc = c1d_launch_stage3(ctx, n, nullptr, use_full, want_chi2z, s))) return rc;
+    }
     TICK(3);
-    if (use_full && (rc = c1d_launch_chi2(ctx, n, s))) return rc;
+    {
+      NvtxRange r("c1d stage 4: dense chi2");
+      if (use_full && (rc = c1d_launch_chi2(ctx, n, s))) return rc;
+    }
     TICK(4);
-    if ((rc = c1d_launch_finalize(ctx, n, lnp_dev + w0, lnl_z_dev ? lnl_z_dev + w0 * c.nz : nullptr, blobs,
-                                  chi2_dev ? chi2_dev + w0 : nullptr, flags, s)))
-      return rc;
+    {
+      NvtxRange r("c1d stage 5: finalize");
+      if ((rc = c1d_launch_finalize(ctx, n, lnp_dev + w0, lnl_z_dev ? lnl_z_dev + w0 * c.nz : nullptr, blobs,
+                                    chi2_dev ? chi2_dev + w0 : nullptr, flags, s)))
+        return rc;
+    }
     TICK(5);
     if (ctx->timing) ctx->ev_pending++;
   }
