@@ -37,7 +37,7 @@ def main():
         if W < 1:
             continue
         x = torch.as_tensor(synth.walkers_sweep(spec, W, seed=16 + rank), device=dev)
-        for prec in ("fp64", "3xtf32"):
+        for prec in ("i8", "fp64"):  # the default arithmetic of NN emulators and the all-float64 path
             like.set_emulator_precision(prec)
             steps = 5 if lg >= 16 else 20
             for _ in range(3):
