@@ -69,6 +69,7 @@ constexpr size_t I8_SMEM = I8_OFF_BAR + 128;
 static_assert(I8_SMEM <= 232448, "shared memory budget");
 constexpr int I8_MAX_UNITS = 96;
 constexpr int I8_MAX_BLOCKS = 2 * C1D_MAX_LAYERS;
+constexpr int I8_MAX_COLS = 1024;  // padded output columns of all layers together (the per-column constants ride in the kernel parameters)
 constexpr double I8_FULL = 127.0 * 16777216.0;        // largest |q|: the top balanced digit stays within +-127
 
 struct I8Unit {        // one weight unit = 32 k of one (layer, n-block, K-group): 16 bytes, ready-made descriptor fields
@@ -103,6 +104,10 @@ struct I8Blk {         // one (layer, n-block) as the epilogue sees it
 struct I8Params {
   const uint8_t* wimg;
   const double2* sb;        // per layer, padded, concatenated: (2^24 * weight-row scale, bias)
+  // the same in the kernel parameters (constant bank, 16 KB of the 32 KB a launch may carry): the epilogue reads the
+  // 16 pairs of a batch through the uniform datapath instead of 16 LDG.128 into 64 vector registers whose latency sat
+  // between the accumulator loads and their first use (dominant stall of the kernel: long scoreboard)
+  double2 sbc[I8_MAX_COLS];
   const double *emu_lo, *emu_rng_inv;
   int n_units, n_blocks, n_in, last_out;
   int col_off[C1D_MAX_LAYERS];  // offset of the layer in sw / bias
@@ -121,6 +126,11 @@ struct I8State {
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(I8_EPI_THREADS) : "memory"); }
 
+// int32 -> float64 without the conversion unit (I2F.F64 runs at 16 per clock per SM; the epilogue converts two or
+// three integers per element): the integer is placed in the mantissa of 2^52 + 2^31 + x and the offset subtracted,
+// one logic operation and one DADD.  Exact.
+__device__ __forceinline__ double i2d_fast(int x) { return __hiloint2double(0x43300000, x ^ (int)0x80000000) - 4503601774854144.0; }
+
 // recombined integer sum of 16 columns: T = ((acc0 * 256 + acc1) * 256 + acc2) * 256 + acc3, exact in float64.
 // SAFE32: acc2 * 256 + acc3 fits 32 bits (two conversions and one DFMA per value instead of three and two).
 template <bool SAFE32>
@@ -136,10 +146,10 @@ __device__ __forceinline__ void load_T16(uint32_t taddr, uint32_t ls, double* T)
   tc_wait_ld();
   if (SAFE32) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) T[i] = fma((double)(int)r0[i], 65536.0, (double)((int)r2[i] * 256 + (int)r1[i]));
+    for (int i = 0; i < 16; ++i) T[i] = fma(i2d_fast((int)r0[i]), 65536.0, i2d_fast((int)r2[i] * 256 + (int)r1[i]));
   } else {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) T[i] = fma((double)(int)r0[i], 65536.0, fma((double)(int)r2[i], 256.0, (double)(int)r1[i]));
+    for (int i = 0; i < 16; ++i) T[i] = fma(i2d_fast((int)r0[i]), 65536.0, fma(i2d_fast((int)r2[i]), 256.0, i2d_fast((int)r1[i])));
   }
 }
 
@@ -255,7 +265,7 @@ k_mlp_i8(I8Params p, const double* __restrict__ emu_in, int64_t nrows, double* _
         d_phase ^= 1;
         tc_fence_after();
         if (dbg) p.dbg[8 * b + 1] = clock64();
-        const double2* sbp = p.sb + p.col_off[B.layer] + B.n0;
+        const double2* sbp = p.sbc + p.col_off[B.layer] + B.n0;
         const uint32_t nb = B.nb, ls = B.lstride;
         if (B.last) {
           // ---- output layer: coefficients = T * scale + bias ----
@@ -264,14 +274,14 @@ k_mlp_i8(I8Params p, const double* __restrict__ emu_in, int64_t nrows, double* _
             load_T16<false>(lane_addr + B.dcol, ls, T);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const double2 cb = __ldg(sbp + i);
+              const double2 cb = sbp[i];
               T[i] = fma(T[i], sa0 * cb.x, cb.y);
             }
             if (B.gin == 2) {
               double U[16];
               load_T16<false>(lane_addr + B.dcol + B.gstride, ls, U);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) T[i] = fma(U[i], sa1 * __ldg(sbp + i).x, T[i]);
+              for (int i = 0; i < 16; ++i) T[i] = fma(U[i], sa1 * sbp[i].x, T[i]);
             }
             if (grow < nrows) {
 #pragma unroll
@@ -290,7 +300,7 @@ k_mlp_i8(I8Params p, const double* __restrict__ emu_in, int64_t nrows, double* _
           else load_T16<false>(lane_addr + B.dcol + c, ls, T);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const double2 cb = __ldg(sbp + c + i);
+            const double2 cb = sbp[c + i];
             T[i] = fma(T[i], sa0 * cb.x, cb.y);
           }
           if (B.gin == 2) {
@@ -298,7 +308,7 @@ k_mlp_i8(I8Params p, const double* __restrict__ emu_in, int64_t nrows, double* _
             if (B.safe32) load_T16<true>(lane_addr + B.dcol + B.gstride + c, ls, U);
             else load_T16<false>(lane_addr + B.dcol + B.gstride + c, ls, U);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) T[i] = fma(U[i], sa1 * __ldg(sbp + c + i).x, T[i]);
+            for (int i = 0; i < 16; ++i) T[i] = fma(U[i], sa1 * sbp[c + i].x, T[i]);
           }
           uint32_t lo[16], hi[16];
 #pragma unroll
@@ -342,7 +352,8 @@ k_mlp_i8(I8Params p, const double* __restrict__ emu_in, int64_t nrows, double* _
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const double h = __hiloint2double((int)hi[i], (int)lo[i]);
-                const uint32_t q = (uint32_t)__double2int_rn(h * inv_s);
+                // round to nearest through the low word of h / s + 1.5 2^52 (|q| < 2^31): no conversion instruction
+                const uint32_t q = (uint32_t)__double2loint(fma(h, inv_s, 6755399441055744.0));
                 v[i] = (q + 0x80808080u) ^ 0x80808080u;
               }
               const uint32_t k = (uint32_t)Q.kbase + c;
@@ -616,6 +627,8 @@ int c1d_i8_prepare(c1d_ctx* ctx) {
 #undef UP
   p.wimg = (const uint8_t*)st->d_wimg;
   p.sb = (const double2*)st->d_sb;
+  if (sb.size() > (size_t)I8_MAX_COLS) return C1D_OK;  // unsupported shape: the caller keeps the float64 kernel
+  memcpy(p.sbc, sb.data(), sb.size() * sizeof(double2));
   p.dbg = nullptr;
   p.exp = getenv("C1D_I8_EXP") ? atoi(getenv("C1D_I8_EXP")) : 0;
   if (getenv("C1D_I8_DEBUG")) {
