@@ -13,7 +13,7 @@ import numpy as np
 
 from . import compile as _cmp
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 LIB_NAME = "libcup1d_b200.so"
 LIB_PATH = os.environ.get("C1D_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)  # C1D_LIB: a variant build (kernel tuning experiments)
 
@@ -22,6 +22,7 @@ FLAG_NO_HULL = 2
 FLAG_EMU_TC = 4
 FLAG_NO_CUBE = 8
 FLAG_EMU_I8 = 16
+FLAG_CHI2_I8 = 32
 
 # every symbol include/cup1d_b200.h declares
 SYMBOLS = (
@@ -177,7 +178,7 @@ class Context(object):
         self._check(rc, "c1d_sampler_run_ens")
 
     def emulator_paths(self):
-        """bit mask: 1 float64, FLAG_EMU_TC 3xTF32, FLAG_EMU_I8 int8 digit slices"""
+        """bit mask: 1 float64, FLAG_EMU_TC 3xTF32, FLAG_EMU_I8 int8 digit slices, FLAG_CHI2_I8 dense chi2 as int8 digit slices"""
         return int(self.lib.c1d_emulator_paths(self.handle))
 
     def sampler_half_step(self, x_ptr, lnp_ptr, blobs_ptr, W, step, half, seed, s0, ns, a=2.0, naccept_ptr=None, flags=0, stream=None,

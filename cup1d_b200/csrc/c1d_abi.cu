@@ -108,6 +108,7 @@ static int refresh_icov_pad(c1d_ctx* ctx) {
   const c1d_config& c = ctx->cfg;
   if (!c.has_full) {
     if (ctx->icov_pad) { cudaFree(ctx->icov_pad); ctx->icov_pad = nullptr; }
+    c1d_chi2i8_destroy(ctx);
     return C1D_OK;
   }
   const size_t ldd = ctx->d.ldd;
@@ -117,7 +118,7 @@ static int refresh_icov_pad(c1d_ctx* ctx) {
   }
   C1D_CUDA(ctx, cudaMemcpy2D(ctx->icov_pad, ldd * sizeof(double), ctx->dev[C1D_F_ICOV_FULL], (size_t)c.nd * sizeof(double),
                              (size_t)c.nd * sizeof(double), c.nd, cudaMemcpyDeviceToDevice));
-  return C1D_OK;
+  return c1d_chi2i8_prepare(ctx);  // digit planes of the folded matrix for the tcgen05 chi2
 }
 
 static int refresh_icovz_pad(c1d_ctx* ctx, const int32_t* zd) {
@@ -409,7 +410,7 @@ extern "C" int c1d_loglike_batch(c1d_ctx* ctx, const double* x_dev, int64_t W, d
     TICK(3);
     {
       NvtxRange r("c1d stage 4: dense chi2");
-      if (use_full && (rc = c1d_launch_chi2(ctx, n, s))) return rc;
+      if (use_full && (rc = c1d_launch_chi2(ctx, n, flags, s))) return rc;
     }
     TICK(4);
     {
@@ -519,6 +520,7 @@ extern "C" int c1d_emulator_paths(const c1d_ctx* ctx) {
   } else {
     m |= 1;
   }
+  if (c1d_chi2i8_available(ctx)) m |= (int)C1D_FLAG_CHI2_I8;
   return m;
 }
 
@@ -550,6 +552,7 @@ extern "C" int c1d_ctx_destroy(c1d_ctx* ctx) {
   cudaDeviceSynchronize();
   c1d_tc_destroy(ctx);
   c1d_i8_destroy(ctx);
+  c1d_chi2i8_destroy(ctx);
   c1d_mlp64_destroy(ctx);
   c1d_p1dw_destroy(ctx);
   ws_free(ctx);

@@ -105,6 +105,8 @@ struct c1d_ctx {
   void* tc_state;
   // int8 digit-slice tensor-core emulator path (c1d_mlp_i8.cu)
   void* i8_state;
+  // int8 digit-slice tensor-core dense chi2 (c1d_chi2_i8.cu)
+  void* chi2i8_state;
   // fp64 tensor-core emulator path (c1d_mlp_f64.cu)
   void* mlp64_state;
   // walker-per-lane stage 3 (c1d_p1d_lanes.cu): per-fine-point rebinning maps, null when not applicable
@@ -129,7 +131,7 @@ int c1d_launch_emulator(c1d_ctx* ctx, const double* emu_in, int64_t nrows, doubl
                         int out_stride, uint32_t flags, cudaStream_t s);
 int c1d_launch_stage3(c1d_ctx* ctx, int64_t W, double* p_out, int want_dvec, int want_chi2z,
                       cudaStream_t s);
-int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, cudaStream_t s);
+int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, uint32_t flags, cudaStream_t s);
 int c1d_launch_finalize(c1d_ctx* ctx, int64_t W, double* lnp, double* lnl_z, double* blobs,
                         double* chi2, uint32_t flags, cudaStream_t s);
 
@@ -160,3 +162,10 @@ int c1d_i8_available(const c1d_ctx* ctx);
 int c1d_i8_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out, int out_stride,
                   cudaStream_t s);
 void c1d_i8_destroy(c1d_ctx* ctx);
+
+// int8 digit-slice tensor-core dense chi2 (c1d_chi2_i8.cu): prepare digit-slices the folded inverse covariance (called
+// whenever C1D_F_ICOV_FULL changes) and leaves the path unavailable beyond 704 data points; launch fills ws.chi2p
+int c1d_chi2i8_prepare(c1d_ctx* ctx);
+int c1d_chi2i8_available(const c1d_ctx* ctx);
+int c1d_chi2i8_launch(c1d_ctx* ctx, int64_t W, int ntj, cudaStream_t s);
+void c1d_chi2i8_destroy(c1d_ctx* ctx);

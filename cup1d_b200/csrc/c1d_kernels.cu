@@ -1078,9 +1078,10 @@ int c1d_launch_chi2z(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
   return C1D_OK;
 }
 
-int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, cudaStream_t s) {
+int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, uint32_t flags, cudaStream_t s) {
   const int ndp = ctx->d.ldd;
   const int ntj = ndp / Q_TJ;
+  if (flags & C1D_FLAG_CHI2_I8) return c1d_chi2i8_launch(ctx, W, ntj, s);  // tcgen05 digit slices (c1d_chi2_i8.cu)
   const int nrb = (int)((W + Q_TW - 1) / Q_TW);
   int grp = 64;  // 8192 walkers: 46 MB of residuals at ndp = 704, well inside the 126 MB L2
   if (const char* e = getenv("C1D_CHI2_GROUP")) grp = atoi(e) > 0 ? atoi(e) : grp;

@@ -112,6 +112,7 @@ struct I8Params {
   int n_units, n_blocks, n_in, last_out;
   int col_off[C1D_MAX_LAYERS];  // offset of the layer in sw / bias
   double slope;
+  int merge;  // 1: two digit pairs per tcgen05.mma (level accumulators nb columns apart); C1D_I8_MERGE=0 keeps ten instructions per unit
   int exp;  // C1D_I8_EXP (measurements only, results are wrong): 1 = no weight copies, 2 = epilogues without arithmetic
   long long* dbg;  // C1D_I8_DEBUG=1: CTA 0 records the clock of its second tile per (layer, n-block), 8 slots each
   I8Blk blk[I8_MAX_BLOCKS];
@@ -399,7 +400,22 @@ k_mlp_i8(I8Params p, const double* __restrict__ emu_in, int64_t nrows, double* _
         const uint64_t bd0 = desc_sw32_0 | (uint64_t)(ring16 + slot * (I8_SLOT >> 4)), bstep = (idesc >> 17) << 4;  // nb rows x 32 B per plane, / 16
         const uint32_t d0 = tmem_base + p.units[u].dcol, ls = p.units[u].lstride;
         const uint32_t keep = (uflags & 1u) ? 0u : 1u;
-        if (leader) {
+        if (leader && p.merge) {
+          // Digit planes j, j + 1 of the weights are consecutive row groups of one operand and the level accumulators
+          // consecutive column groups (lstride = nb), so one instruction of N = 2 nb serves two pairs: six instructions
+          // instead of ten, 64 KB instead of 80 KB of operand reads per unit (the SS form is shared-memory bound at
+          // N <= 128: tools/i8_probe.cu)
+          const uint32_t idesc2 = idesc + (idesc & (63u << 17));  // N -> 2 N
+          mma_i8_ss(d0, ad0, bd0, idesc2, keep);                                  // (0,0) (0,1) -> levels 0, 1
+          mma_i8_ss(d0 + 2 * ls, ad0, bd0 + 2 * bstep, idesc2, keep);             // (0,2) (0,3) -> levels 2, 3
+          mma_i8_ss(d0 + ls, ad0 + astep, bd0, idesc2, 1u);                       // (1,0) (1,1) -> levels 1, 2
+          mma_i8_ss(d0 + 3 * ls, ad0 + astep, bd0 + 2 * bstep, idesc, 1u);        // (1,2)       -> level 3
+          mma_i8_ss(d0 + 2 * ls, ad0 + 2 * astep, bd0, idesc2, 1u);               // (2,0) (2,1) -> levels 2, 3
+          mma_i8_ss(d0 + 3 * ls, ad0 + 3 * astep, bd0, idesc, 1u);                // (3,0)       -> level 3
+          tc_commit(bar_bempty + 8 * slot);
+          if (uflags & 2u) tc_commit(bar_dfull);
+          if (dbg && (uflags & 2u)) p.dbg[8 * bidx + 6] = clock64();
+        } else if (leader) {
           // the pairs (0, j) are the first writers of the level accumulators
           mma_i8_ss(d0, ad0, bd0, idesc, keep);
           mma_i8_ss(d0 + ls, ad0, bd0 + bstep, idesc, keep);
@@ -505,6 +521,7 @@ int c1d_i8_prepare(c1d_ctx* ctx) {
   p.n_in = c.layer_dims[0];
   p.last_out = c.layer_dims[L];
   p.slope = c.nn_slope;
+  p.merge = getenv("C1D_I8_MERGE") ? atoi(getenv("C1D_I8_MERGE")) : 1;
   std::vector<I8Unit> units;
   std::vector<I8Blk> blks;
   std::vector<uint8_t> img;
@@ -562,6 +579,7 @@ int c1d_i8_prepare(c1d_ctx* ctx) {
       if (gin[l] == 2) { B.dcol = 0; B.lstride = 64; B.gstride = 256; }
       else if (b == 1 && mode[l] == 0) { B.dcol = 256; B.lstride = 64; B.gstride = 0; }
       else { B.dcol = 0; B.lstride = 128; B.gstride = 0; }
+      if (p.merge) B.lstride = (uint16_t)nb;  // consecutive level accumulators: one MMA covers two of them
       B.hlo = B.dcol;
       B.hhi = (uint16_t)(B.dcol + B.lstride);
       if (out_groups) {

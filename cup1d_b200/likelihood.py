@@ -20,6 +20,8 @@ no CPU implementation behind this class.
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -89,6 +91,23 @@ class B200Likelihood(object):
                              "must be followed by one of at most 64); use 'fp64'")
         self.emulator_precision = mode
         self._base_flags = {"fp64": 0, "3xtf32": _abi.FLAG_EMU_TC, "i8": _abi.FLAG_EMU_I8}[mode]
+        # the dense chi2 follows the emulator: with the digit-slice emulator (log-likelihood within 1e-4) the quadratic
+        # form runs on tcgen05 too (five digit planes: 5e-11 relative), with "fp64" everything stays on the fp64 pipe
+        self.set_chi2_precision("i8" if mode == "i8" and (paths & _abi.FLAG_CHI2_I8) else "fp64")
+
+    def set_chi2_precision(self, mode):
+        """arithmetic of the dense chi2: "i8" (tcgen05 digit slices, up to 704 data points) or "fp64" (DMMA);
+        C1D_CHI2=fp64|i8 in the environment overrides the choice that follows the emulator precision"""
+        mode = os.environ.get("C1D_CHI2", mode)
+        if mode not in ("i8", "fp64"):
+            raise ValueError("chi2 precision must be 'i8' or 'fp64'")
+        if mode == "i8" and not (self.ctx.emulator_paths() & _abi.FLAG_CHI2_I8):
+            if "C1D_CHI2" in os.environ:
+                mode = "fp64"  # no dense covariance (or more than 704 points): nothing to switch
+            else:
+                raise ValueError("the int8 digit-slice chi2 needs a dense inverse covariance of at most 704 data points")
+        self.chi2_precision = mode
+        self._base_flags = (self._base_flags & ~_abi.FLAG_CHI2_I8) | (_abi.FLAG_CHI2_I8 if mode == "i8" else 0)
 
     def set_data(self, full_Pk_kms):
         """Replace the data vector (mock generation)"""

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define C1D_ABI_VERSION 7
+#define C1D_ABI_VERSION 8
 #define C1D_MAX_LAYERS 12
 #define C1D_MAX_EMU 8     /* emulator inputs */
 #define C1D_MAX_COEF 8    /* polynomial coefficients the emulator returns */
@@ -170,6 +170,10 @@ typedef struct c1d_ctx c1d_ctx;
 #define C1D_FLAG_EMU_TC 4u    /* emulator layers on tcgen05 tensor cores in 3xTF32 (float32-class accuracy: misses the 1e-4 log-likelihood tolerance) */
 #define C1D_FLAG_EMU_I8 16u   /* emulator layers on tcgen05 tensor cores as int8 digit slices with exact int32 accumulation and float64
                                  recombination (float64-class accuracy); without either flag the layers run on the fp64 tensor cores (DMMA) */
+#define C1D_FLAG_CHI2_I8 32u  /* dense chi2 = d^T C^-1 d (likelihood.py:956-960) on tcgen05 tensor cores as five int8 digit planes per operand,
+                                 exact int32 accumulation, float64 recombination (chi2 within 5e-11 relative of the float64 evaluation);
+                                 without it the quadratic form runs on the fp64 tensor cores (DMMA).  Available up to 704 data points:
+                                 see c1d_emulator_paths */
 
 int c1d_abi_version(void);
 
@@ -254,8 +258,9 @@ int c1d_sampler_half_step(c1d_ctx* ctx, double* x_dev, double* lnp_dev, double* 
  * out2 = two uniforms in (0,1) of counter (step, half, walker, which); walker = (ens0 + e) * wn / 2 + index in the half */
 int c1d_philox_u01(uint64_t seed, int64_t step, int half, int64_t walker, int which, double* out2);
 
-/* emulator arithmetic available to a finalised context: bit 0 = float64, C1D_FLAG_EMU_TC, C1D_FLAG_EMU_I8
- * (the int8 digit-slice kernel needs an MLP whose layers wider than 192 are followed by one of at most 64) */
+/* arithmetic available to a finalised context: bit 0 = float64, C1D_FLAG_EMU_TC, C1D_FLAG_EMU_I8
+ * (the int8 digit-slice kernel needs an MLP whose layers wider than 192 are followed by one of at most 64),
+ * C1D_FLAG_CHI2_I8 (dense inverse covariance of at most 704 data points) */
 int c1d_emulator_paths(const c1d_ctx* ctx);
 
 /* number of kernels launched by this context since creation */
