@@ -28,7 +28,7 @@ FLAG_CHI2_I8 = 32
 SYMBOLS = (
     "c1d_abi_version", "c1d_ctx_create", "c1d_ctx_upload", "c1d_ctx_finalize",
     "c1d_loglike_batch", "c1d_p1d_batch", "c1d_emulator_only", "c1d_loglike_batch_host",
-    "c1d_sampler_run", "c1d_sampler_run_ens", "c1d_sampler_half_step", "c1d_philox_u01", "c1d_emulator_paths", "c1d_launch_count", "c1d_set_timing", "c1d_get_timing", "c1d_tc_selftest", "c1d_ctx_destroy", "c1d_last_error",
+    "c1d_sampler_run", "c1d_sampler_run_ens", "c1d_sampler_half_step", "c1d_philox_u01", "c1d_emulator_paths", "c1d_launch_count", "c1d_graph_replays", "c1d_set_timing", "c1d_get_timing", "c1d_tc_selftest", "c1d_ctx_destroy", "c1d_last_error",
 )
 
 
@@ -97,6 +97,8 @@ def load_library(path=None):
     lib.c1d_emulator_paths.restype = C.c_int
     lib.c1d_launch_count.argtypes = [vp]
     lib.c1d_launch_count.restype = i64
+    lib.c1d_graph_replays.argtypes = [vp]
+    lib.c1d_graph_replays.restype = i64
     lib.c1d_set_timing.argtypes = [vp, C.c_int]
     lib.c1d_get_timing.argtypes = [vp, C.POINTER(C.c_double)]
     lib.c1d_tc_selftest.argtypes = [C.c_int, vp, vp, vp, C.c_int, C.c_int]
@@ -189,6 +191,9 @@ class Context(object):
 
     def launch_count(self):
         return int(self.lib.c1d_launch_count(self.handle))
+
+    def graph_replays(self):
+        return int(self.lib.c1d_graph_replays(self.handle))
 
     def set_timing(self, on):
         self._check(self.lib.c1d_set_timing(self.handle, int(bool(on))), "c1d_set_timing")

@@ -14,6 +14,7 @@ extern "C" int c1d_abi_version(void) { return C1D_ABI_VERSION; }
 extern "C" const char* c1d_last_error(const c1d_ctx* ctx) { return ctx ? ctx->err : k_no_ctx; }
 
 extern "C" int64_t c1d_launch_count(const c1d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t c1d_graph_replays(const c1d_ctx* ctx) { return ctx ? ctx->graph_replays : 0; }
 
 static size_t field_elem_size(int f) {
   switch (f) {
@@ -95,6 +96,7 @@ extern "C" int c1d_ctx_create(const c1d_config* cfg, c1d_ctx** out) {
   for (int r = 0; r < C1D_TRING; ++r)
     for (int i = 0; i < 6; ++i) C1D_CUDA(ctx, cudaEventCreate(&ctx->evr[r][i]));
   C1D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  C1D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->graph_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
     C1D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming));
     C1D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
@@ -157,6 +159,7 @@ extern "C" int c1d_ctx_upload(c1d_ctx* ctx, int field_id, const void* host_ptr, 
   if (!ctx->dev[field_id]) C1D_CUDA(ctx, cudaMalloc(&ctx->dev[field_id], bytes));
   // re-uploads (new data vector, zmask) must not race with work in flight
   C1D_CUDA(ctx, cudaDeviceSynchronize());
+  c1d_graphs_clear(ctx);  // the field may move, and derived tables are rebuilt
   C1D_CUDA(ctx, cudaMemcpy(ctx->dev[field_id], host_ptr, bytes, cudaMemcpyHostToDevice));
   ctx->bytes[field_id] = bytes;
   if (!ctx->finalized) return C1D_OK;
@@ -184,6 +187,7 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
   if (!ctx) return C1D_ERR_ARG;
   c1d_config& c = ctx->cfg;
   C1D_CUDA(ctx, cudaSetDevice(c.device));
+  c1d_graphs_clear(ctx);
   // z offsets are needed on the host to size the per-z blocks
   int32_t zf[1024], zd[1024];
   if (c.nz + 1 > 1024) { snprintf(ctx->err, sizeof(ctx->err), "too many z bins"); return C1D_ERR_ARG; }
@@ -291,6 +295,7 @@ static int ws_reserve(c1d_ctx* ctx, int64_t W) {
   if (W <= w.cap) return C1D_OK;
   const c1d_config& c = ctx->cfg;
   C1D_CUDA(ctx, cudaDeviceSynchronize());
+  c1d_graphs_clear(ctx);  // captured launches point into the old workspace
   ws_free(ctx);
   int64_t cap = W;
   C1D_CUDA(ctx, cudaMalloc(&w.status, cap * sizeof(int)));
@@ -369,6 +374,77 @@ struct NvtxRange {
   ~NvtxRange() { nvtxRangePop(); }
 };
 
+// the five stages of one chunk on stream s (timed per stage when timing is on)
+static int run_chain(c1d_ctx* ctx, const double* x, int64_t n, double* lnp, double* lnl_z, double* blobs_out, double* chi2,
+                     uint32_t flags, cudaStream_t s, bool timed) {
+  const c1d_config& c = ctx->cfg;
+  const int use_full = c.has_full && !(flags & C1D_FLAG_ZMASK);
+  const int want_chi2z = !use_full || lnl_z != nullptr;
+  double* blobs = blobs_out ? blobs_out : ctx->ws.blobs;
+  int rc;
+#define TICK_T(i) do { if (timed) TICK(i); } while (0)
+  NvtxRange chunk_range("c1d_loglike_batch chunk");
+  TICK_T(0);
+  {
+    NvtxRange r("c1d stage 1: parameters, priors, emulator inputs");
+    if ((rc = c1d_launch_stage1(ctx, x, n, blobs, flags, s))) return rc;
+  }
+  TICK_T(1);
+  {
+    NvtxRange r("c1d stage 2: emulator");
+    if ((rc = c1d_launch_emulator(ctx, ctx->ws.emu_in, n * c.nz, ctx->ws.amp, C1D_NAMP, flags, s))) return rc;
+  }
+  TICK_T(2);
+  {
+    NvtxRange r("c1d stage 3: contaminants, rebinning, residual");
+    if ((rc = c1d_launch_stage3(ctx, n, nullptr, use_full, want_chi2z, s))) return rc;
+  }
+  TICK_T(3);
+  {
+    NvtxRange r("c1d stage 4: dense chi2");
+    if (use_full && (rc = c1d_launch_chi2(ctx, n, flags, s))) return rc;
+  }
+  TICK_T(4);
+  {
+    NvtxRange r("c1d stage 5: finalize");
+    if ((rc = c1d_launch_finalize(ctx, n, lnp, lnl_z, blobs, chi2, flags, s))) return rc;
+  }
+  TICK_T(5);
+#undef TICK_T
+  return C1D_OK;
+}
+
+// ---- CUDA graphs for small batches -------------------------------------------------------------------------------
+// Below a few thousand walkers the five dependent launches and the gaps between them are a large part of a call
+// (C1, 64 walkers: kernels ~40 us of a ~100 us call).  A call that repeats an earlier one's shape, flags
+// and buffers - the sampler's half-steps, the minimiser's simplex evaluations, an emcee loop over torch's caching
+// allocator - is captured once (on an internal stream: the caller's may be the legacy default stream, which cannot be
+// captured) and replayed with one cudaGraphLaunch.  The first occurrence of a key runs normally, so every lazy
+// allocation and function attribute of that configuration exists before the capture.  Anything that changes what the
+// kernel parameters point to (workspace growth, uploads, re-finalisation) drops the cache.  C1D_GRAPH=0 disables it.
+void c1d_graphs_clear(c1d_ctx* ctx) {
+  for (int i = 0; i < C1D_NGRAPH; ++i) {
+    if (ctx->graphs[i].exec) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graphs[i].exec);
+    memset(&ctx->graphs[i], 0, sizeof(ctx->graphs[i]));
+  }
+  memset(ctx->graph_seen, 0, sizeof(ctx->graph_seen));
+}
+
+static bool graph_key_eq(const c1d_graph_entry& a, const c1d_graph_entry& b) {
+  return a.W == b.W && a.flags == b.flags && a.x == b.x && a.lnp == b.lnp && a.lnl_z == b.lnl_z && a.blobs == b.blobs &&
+         a.chi2 == b.chi2;
+}
+
+static int64_t graph_max_walkers() {
+  static int64_t v = -1;
+  if (v < 0) {
+    const char* e = getenv("C1D_GRAPH");
+    v = e ? atoll(e) : 1;
+    if (v == 1) v = 8192;  // default: batches of at most 8192 walkers
+  }
+  return v;
+}
+
 extern "C" int c1d_loglike_batch(c1d_ctx* ctx, const double* x_dev, int64_t W, double* lnp_dev,
                                  double* lnl_z_dev, double* blobs_dev, double* chi2_dev,
                                  uint32_t flags, void* cuda_stream) {
@@ -385,41 +461,64 @@ extern "C" int c1d_loglike_batch(c1d_ctx* ctx, const double* x_dev, int64_t W, d
   int64_t chunk = W < CHUNK_MAX ? W : CHUNK_MAX;
   rc = ws_reserve(ctx, chunk);
   if (rc) return rc;
-  const int use_full = c.has_full && !(flags & C1D_FLAG_ZMASK);
-  const int want_chi2z = !use_full || lnl_z_dev != nullptr;
+  if (W <= graph_max_walkers() && !ctx->timing) {
+    c1d_graph_entry key;
+    memset(&key, 0, sizeof(key));
+    key.W = W; key.flags = flags; key.x = x_dev; key.lnp = lnp_dev; key.lnl_z = lnl_z_dev; key.blobs = blobs_dev; key.chi2 = chi2_dev;
+    for (int i = 0; i < C1D_NGRAPH; ++i)
+      if (ctx->graphs[i].exec && graph_key_eq(ctx->graphs[i], key)) {
+        C1D_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)ctx->graphs[i].exec, s));
+        ctx->graphs[i].stamp = ++ctx->graph_clock;
+        ctx->launches += ctx->graphs[i].nlaunch;
+        ctx->graph_replays++;
+        return C1D_OK;
+      }
+    int seen = -1;
+    for (int i = 0; i < C1D_NGRAPH; ++i)
+      if (ctx->graph_seen[i].stamp && graph_key_eq(ctx->graph_seen[i], key)) seen = i;
+    if (seen >= 0) {
+      // second call with this key (callers that alternate between two output buffers repeat every other call): capture it
+      memset(&ctx->graph_seen[seen], 0, sizeof(ctx->graph_seen[seen]));
+      int slot = 0;
+      for (int i = 1; i < C1D_NGRAPH; ++i)
+        if (ctx->graphs[i].stamp < ctx->graphs[slot].stamp) slot = i;
+      if (ctx->graphs[slot].exec) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graphs[slot].exec);
+      memset(&ctx->graphs[slot], 0, sizeof(ctx->graphs[slot]));
+      cudaGraph_t graph = nullptr;
+      const int64_t l0 = ctx->launches;
+      C1D_CUDA(ctx, cudaStreamBeginCapture(ctx->graph_stream, cudaStreamCaptureModeThreadLocal));
+      rc = run_chain(ctx, x_dev, W, lnp_dev, lnl_z_dev, blobs_dev, chi2_dev, flags, ctx->graph_stream, false);
+      cudaError_t ce = cudaStreamEndCapture(ctx->graph_stream, &graph);
+      const int64_t nl = ctx->launches - l0;
+      ctx->launches = l0;
+      cudaGraphExec_t exec = nullptr;
+      if (rc == C1D_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+        key.exec = exec; key.nlaunch = nl; key.stamp = ++ctx->graph_clock;
+        ctx->graphs[slot] = key;
+        C1D_CUDA(ctx, cudaGraphLaunch(exec, s));
+        ctx->launches += nl;
+        ctx->graph_replays++;
+        return C1D_OK;
+      }
+      // capture not possible (a launcher that allocates or synchronises): clear the error state and run normally
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (rc) return rc;
+    } else {
+      int slot = 0;  // remember the key: the oldest remembered one makes room
+      for (int i = 1; i < C1D_NGRAPH; ++i)
+        if (ctx->graph_seen[i].stamp < ctx->graph_seen[slot].stamp) slot = i;
+      ctx->graph_seen[slot] = key;
+      ctx->graph_seen[slot].stamp = ++ctx->graph_clock;
+    }
+  }
   for (int64_t w0 = 0; w0 < W; w0 += chunk) {
     int64_t n = (W - w0 < chunk) ? (W - w0) : chunk;
-    double* blobs = blobs_dev ? blobs_dev + w0 * 6 : ctx->ws.blobs;
     if (ctx->timing && ctx->ev_pending == C1D_TRING && (rc = timing_drain(ctx))) return rc;
-    NvtxRange chunk_range("c1d_loglike_batch chunk");
-    TICK(0);
-    {
-      NvtxRange r("c1d stage 1: parameters, priors, emulator inputs");
-      if ((rc = c1d_launch_stage1(ctx, x_dev + w0 * c.ndim, n, blobs, flags, s))) return rc;
-    }
-    TICK(1);
-    {
-      NvtxRange r("c1d stage 2: emulator");
-      if ((rc = c1d_launch_emulator(ctx, ctx->ws.emu_in, n * c.nz, ctx->ws.amp, C1D_NAMP, flags, s))) return rc;
-    }
-    TICK(2);
-    {
-      NvtxRange r("c1d stage 3: contaminants, rebinning, residual");
-      if ((rc = c1d_launch_stage3(ctx, n, nullptr, use_full, want_chi2z, s))) return rc;
-    }
-    TICK(3);
-    {
-      NvtxRange r("c1d stage 4: dense chi2");
-      if (use_full && (rc = c1d_launch_chi2(ctx, n, flags, s))) return rc;
-    }
-    TICK(4);
-    {
-      NvtxRange r("c1d stage 5: finalize");
-      if ((rc = c1d_launch_finalize(ctx, n, lnp_dev + w0, lnl_z_dev ? lnl_z_dev + w0 * c.nz : nullptr, blobs,
-                                    chi2_dev ? chi2_dev + w0 : nullptr, flags, s)))
-        return rc;
-    }
-    TICK(5);
+    if ((rc = run_chain(ctx, x_dev + w0 * c.ndim, n, lnp_dev + w0, lnl_z_dev ? lnl_z_dev + w0 * c.nz : nullptr,
+                        blobs_dev ? blobs_dev + w0 * 6 : nullptr, chi2_dev ? chi2_dev + w0 : nullptr, flags, s, ctx->timing != 0)))
+      return rc;
     if (ctx->timing) ctx->ev_pending++;
   }
   return C1D_OK;
@@ -555,6 +654,7 @@ extern "C" int c1d_ctx_destroy(c1d_ctx* ctx) {
   c1d_chi2i8_destroy(ctx);
   c1d_mlp64_destroy(ctx);
   c1d_p1dw_destroy(ctx);
+  c1d_graphs_clear(ctx);
   ws_free(ctx);
   if (ctx->icov_pad) cudaFree(ctx->icov_pad);
   if (ctx->icovz_pad) cudaFree(ctx->icovz_pad);
@@ -568,6 +668,7 @@ extern "C" int c1d_ctx_destroy(c1d_ctx* ctx) {
     if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->graph_stream) cudaStreamDestroy(ctx->graph_stream);
   delete ctx;
   return C1D_OK;
 }

@@ -60,12 +60,13 @@ struct CQParams {
   int tile_r0[CQ_MAX_TILES];      // first row of the tile
   int tile_rows[CQ_MAX_TILES];    // rows of the tile (<= 128)
   int tile_units[CQ_MAX_TILES];   // k units of the tile (k < end of the tile)
-  uint32_t off_ring, off_sd, off_red, off_bar;  // shared-memory offsets (the residual operand starts at 0)
+  uint32_t off_ring, off_sd, off_bar;  // shared-memory offsets (the residual operand starts at 0)
+  long long* dbg;  // C1D_CHI2_DEBUG=1: clocks of CTA 0's second group (phases of warp 0 and of the MMA warp)
 };
 
 struct CQState {
   CQParams p;
-  void *d_img, *d_rscale;
+  void *d_img, *d_rscale, *d_dbg;
   size_t smem;
   bool ready;
 };
@@ -82,11 +83,11 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
   const uint32_t ring = base + p.off_ring;
   const uint32_t bar0 = base + p.off_bar;
   const uint32_t bar_bfull = bar0, bar_bempty = bar0 + 8 * CQ_NSLOT;
-  const uint32_t bar_dfull = bar0 + 16 * CQ_NSLOT, bar_dfree = bar_dfull + 16, bar_bready = bar_dfree + 16;
-  const uint32_t tmem_slot = bar_bready + 8;
-  volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(smem_raw + p.off_bar + 16 * CQ_NSLOT + 40);
-  double* sd_s = reinterpret_cast<double*>(smem_raw + p.off_sd);    // [NW] scale of the walker's digits (NaN: bad row)
-  double* red_s = reinterpret_cast<double*>(smem_raw + p.off_red);  // [4 quadrants][NW]
+  const uint32_t bar_dfull = bar0 + 16 * CQ_NSLOT, bar_dfree = bar_dfull + 16, bar_tready = bar_dfree + 16;
+  const uint32_t tmem_slot = bar_tready + 8 * CQ_MAX_TILES;
+  volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(smem_raw + p.off_bar + 16 * CQ_NSLOT + 32 + 8 * CQ_MAX_TILES);
+  double* sd_s = reinterpret_cast<double*>(smem_raw + p.off_sd);    // [2][NW] scale of the walker's digits (NaN: bad row), this group / the next
+  double* red_s = reinterpret_cast<double*>(smem_raw);              // [4 quadrants][NW]: on the operand region, free once the group's MMAs are complete
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = tid & 31;
   if (tid == 0) {
@@ -102,7 +103,7 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
       mbar_init(bar_dfull + 8 * b, 1);
       mbar_init(bar_dfree + 8 * b, CQ_EPI_THREADS);
     }
-    mbar_init(bar_bready, CQ_EPI_THREADS);
+    for (int t = 0; t < CQ_MAX_TILES; ++t) mbar_init(bar_tready + 8 * t, CQ_EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == CQ_EPI_WARPS) tmem_alloc(tmem_slot, 512u);
@@ -119,72 +120,110 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
     // ======================= quantiser / epilogue warps =======================
     const uint32_t quad = (uint32_t)warp & 3u, sub = (uint32_t)warp >> 2;
     const uint32_t lane_addr = tmem_base + ((quad * 32u) << 16);
-    const int ngk = ldd >> 4;  // 16-k groups of a residual row
     uint32_t tcount = 0;       // tiles seen so far (accumulator set = tcount & 1)
-    for (int64_t it = 0; it < groups_per_cta; ++it) {
-      const int64_t w0 = (it * gridDim.x + blockIdx.x) * CQ_NW;
-      // ---- row maxima -> scales (the MMAs of the previous group are complete: its last dfull was waited for) ----
-      for (int n = warp; n < CQ_NW; n += CQ_EPI_WARPS) {
-        const int64_t w = w0 + n;
-        uint32_t mhi = 0;  // |x| orders like its high word; NaN / Inf carry the largest
-        if (w < W) {
-          const double* row = dvec + w * ldd;
-          for (int k = lane; k < ldd; k += 32) mhi = max(mhi, (uint32_t)__double2hiint(row[k]) & 0x7fffffffu);
-        }
+
+    // A warp owns four walkers of the group (rows 4 warp .. 4 warp + 3 of the N-side operand): it finds their maxima
+    // (lanes along k, coalesced), and later converts them 64 k at a time with lane = (row, 8 k): a 256-bit load touches
+    // 16 lines instead of the 32 of a lane-per-row mapping (the L1 tag stage serves a line per cycle), and the four rows
+    // land on the four 32-byte bank windows of the swizzled operand, so the 8-byte stores are conflict-free.
+    auto row_scales = [&](int64_t w0, int sel) {
+#pragma unroll 1
+      for (int h = 0; h < 4; ++h) {  // one row at a time, all its loads in flight (44 registers; the rows come from L2)
+        const int nn = 4 * warp + h;
+        const int64_t w = w0 + nn;
+        const double2* row = reinterpret_cast<const double2*>(dvec + (w < W ? w : W - 1) * ldd) + lane;
+        double2 v[11];
+#pragma unroll
+        for (int i = 0; i < 11; ++i) v[i] = (64 * i < ldd) ? row[32 * i] : make_double2(0.0, 0.0);
+        uint32_t mhi = 0u;  // |x| orders like its high word; NaN / Inf carry the largest
+#pragma unroll
+        for (int i = 0; i < 11; ++i)
+          mhi = max(mhi, max((uint32_t)__double2hiint(v[i].x) & 0x7fffffffu, (uint32_t)__double2hiint(v[i].y) & 0x7fffffffu));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
         if (lane == 0) {
           // upper bound of max|d|: the next value of the high word (2^-20 above at most)
-          double s = 0.0;
-          if (mhi >= 0x7ff00000u) s = __longlong_as_double(0x7ff8000000000000LL);
-          else if (mhi != 0u) s = __hiloint2double((int)(mhi + 1u), 0) * (1.0 / CQ_FULL);
-          sd_s[n] = s;
+          double sc = 0.0;
+          if (w >= W) sc = 0.0;
+          else if (mhi >= 0x7ff00000u) sc = __longlong_as_double(0x7ff8000000000000LL);
+          else if (mhi != 0u) sc = __hiloint2double((int)(mhi + 1u), 0) * (1.0 / CQ_FULL);
+          sd_s[sel * CQ_NW + nn] = sc;
         }
       }
-      cq_epi_bar();
-      // ---- residuals -> five digit planes of the N-side operand ----
-      for (int item = tid; item < CQ_NW * ngk; item += CQ_EPI_THREADS) {
-        const int n = item / ngk, gk = item - n * ngk;
-        const int64_t w = w0 + n;
-        const double s = sd_s[n];
+      __syncwarp();
+    };
+    const int qn = 4 * warp + (lane >> 3);       // the row this lane converts
+    const int qk = 8 * (lane & 7);               // its 8 k inside a 64-k step
+    auto load8 = [&](const double* src, double (&x)[8]) {
+      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(src));
+      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[4]), "=d"(x[5]), "=d"(x[6]), "=d"(x[7]) : "l"(src + 4));
+    };
+    const int tpre = p.ntile > 3 ? p.ntile - 3 : 0;  // the next group's scales are found under the long tiles of this one
+
+    for (int64_t it = 0; it < groups_per_cta; ++it) {
+      const int64_t w0 = (it * gridDim.x + blockIdx.x) * CQ_NW;
+      const int sel = (int)(it & 1);
+      const double* sdc = sd_s + sel * CQ_NW;
+      const bool dbg = p.dbg && blockIdx.x == 0 && tid == 0 && it == 1;
+      if (dbg) p.dbg[0] = clock64();
+      if (it == 0) {
+        row_scales(w0, 0);
+        cq_epi_bar();
+      }
+      // ---- residuals -> five digit planes of the N-side operand (the MMAs of the previous group are complete: its
+      //      last dfull was waited for); the loads of the next step are in flight while one is converted; a row tile's
+      //      MMAs start as soon as the k units it needs are in place (bar_tready) ----
+      {
+        const double s = sdc[qn];
         const double inv_s = (s > 0.0) ? 1.0 / s : 0.0;  // zero rows, bad rows (NaN scale) and padding walkers: digits 0
-        uint32_t vlo[16], vhi[16];
-        const double2* src = reinterpret_cast<const double2*>(dvec + (w < W ? w : W - 1) * ldd + 16 * gk);
+        const int64_t wq = w0 + qn;
+        const double* src = dvec + (wq < W ? wq : W - 1) * ldd + qk;
+        const int nho = ldd >> 6;
+        double xa[8], xb[8], xc[8];  // two steps of loads in flight (L2 latency exceeds one step of conversions)
+        load8(src, xa);
+        if (nho > 1) load8(src + 64, xb);
+        int tnext = 0;  // next row tile to release
+        for (int ho = 0; ho < nho; ++ho) {
+          if (ho + 2 < nho) load8(src + 64 * (ho + 2), xc);
+          uint32_t pw[CQ_ND][2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const double2 x = src[i];
+          for (int g = 0; g < 2; ++g) {
+            uint32_t vlo[4], vhi[4];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            // round to nearest through the mantissa of x / s + 1.5 2^52 (|q| < 2^40): no conversion instruction
-            const double r = fma(h ? x.y : x.x, (w < W) ? inv_s : 0.0, 6755399441055744.0);
-            unsigned long long q = ((unsigned long long)(uint32_t)__double2hiint(r) << 32) | (uint32_t)__double2loint(r);
-            q = (q + 0x8080808080ull) ^ 0x8080808080ull;  // two's complement -> balanced digit bytes
-            vlo[2 * i + h] = (uint32_t)q;
-            vhi[2 * i + h] = (uint32_t)(q >> 32);
+            for (int e = 0; e < 4; ++e) {
+              // round to nearest through the mantissa of x / s + 1.5 2^52 (|q| < 2^40): no conversion instruction
+              const double r = fma(xa[4 * g + e], inv_s, 6755399441055744.0);
+              unsigned long long q = ((unsigned long long)(uint32_t)__double2hiint(r) << 32) | (uint32_t)__double2loint(r);
+              q = (q + 0x8080808080ull) ^ 0x8080808080ull;  // two's complement -> balanced digit bytes
+              vlo[e] = (uint32_t)q;
+              vhi[e] = (uint32_t)(q >> 32);
+            }
+            const uint32_t a = __byte_perm(vlo[0], vlo[1], 0x5140), b = __byte_perm(vlo[0], vlo[1], 0x7362);
+            const uint32_t c = __byte_perm(vlo[2], vlo[3], 0x5140), d = __byte_perm(vlo[2], vlo[3], 0x7362);
+            pw[4][g] = __byte_perm(a, c, 0x5410);  // bytes 0: least significant digit = plane 4
+            pw[3][g] = __byte_perm(a, c, 0x7632);
+            pw[2][g] = __byte_perm(b, d, 0x5410);
+            pw[1][g] = __byte_perm(b, d, 0x7632);
+            const uint32_t e4 = __byte_perm(vhi[0], vhi[1], 0x0040), f4 = __byte_perm(vhi[2], vhi[3], 0x0040);
+            pw[0][g] = __byte_perm(e4, f4, 0x5410);  // most significant digit = plane 0
+          }
+          const int k0 = 64 * ho + qk;
+          const uint32_t dst = base + (uint32_t)(k0 >> 5) * CQ_BUNIT + sw32_off((uint32_t)qn, (uint32_t)(k0 >> 4) & 1u) + ((uint32_t)k0 & 8u);
+#pragma unroll
+          for (int pl = 0; pl < CQ_ND; ++pl)
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + (uint32_t)pl * CQ_BPLANE), "r"(pw[pl][0]), "r"(pw[pl][1]) : "memory");
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { xa[i] = xb[i]; xb[i] = xc[i]; }
+          // units [0, 2 ho + 2) are written by this thread: release the row tiles they complete
+          while (tnext < p.ntile && p.tile_units[tnext] <= 2 * ho + 2) {
+            fence_async_smem();
+            mbar_arrive(bar_tready + 8 * tnext);
+            ++tnext;
           }
         }
-        const uint32_t dst = base + (uint32_t)(gk >> 1) * CQ_BUNIT + sw32_off((uint32_t)n, (uint32_t)gk & 1u);
-        uint32_t pw[CQ_ND][4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t a = __byte_perm(vlo[4 * g], vlo[4 * g + 1], 0x5140), b = __byte_perm(vlo[4 * g], vlo[4 * g + 1], 0x7362);
-          const uint32_t c = __byte_perm(vlo[4 * g + 2], vlo[4 * g + 3], 0x5140), d = __byte_perm(vlo[4 * g + 2], vlo[4 * g + 3], 0x7362);
-          pw[4][g] = __byte_perm(a, c, 0x5410);  // bytes 0: least significant digit = plane 4
-          pw[3][g] = __byte_perm(a, c, 0x7632);
-          pw[2][g] = __byte_perm(b, d, 0x5410);
-          pw[1][g] = __byte_perm(b, d, 0x7632);
-          const uint32_t e = __byte_perm(vhi[4 * g], vhi[4 * g + 1], 0x0040), f = __byte_perm(vhi[4 * g + 2], vhi[4 * g + 3], 0x0040);
-          pw[0][g] = __byte_perm(e, f, 0x5410);  // most significant digit = plane 0
-        }
-#pragma unroll
-        for (int pl = 0; pl < CQ_ND; ++pl)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)pl * CQ_BPLANE), "r"(pw[pl][0]),
-                       "r"(pw[pl][1]), "r"(pw[pl][2]), "r"(pw[pl][3])
-                       : "memory");
       }
-      fence_async_smem();
-      mbar_arrive(bar_bready);
 
+      if (dbg) p.dbg[1] = clock64();
       // ---- epilogues: partial sums over the rows this thread holds, 16 walkers ----
       double acc[16];
 #pragma unroll
@@ -195,31 +234,50 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
         const bool rvalid = r < p.tile_rows[t] && p.tile_r0[t] + r < p.nd;
         const int j = rvalid ? p.tile_r0[t] + r : 0;
         const double cs = __ldg(p.rscale + t * 128 + r);    // 0 for padding rows
-        double dj[16];
+        double cd[16];  // (row scale) x (residual of this row) per walker: the products wait for the accumulators
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const int64_t w = w0 + 16 * sub + c;
-          dj[c] = __ldg(dvec + (w < W ? w : W - 1) * ldd + j);
+          cd[c] = cs * __ldg(dvec + (w < W ? w : W - 1) * ldd + j);
         }
+        if (dbg) p.dbg[8 + 4 * t] = clock64();
         mbar_wait(bar_dfull + 8 * buf, (tcount >> 1) & 1u);
         tc_fence_after();
+        if (dbg) p.dbg[9 + 4 * t] = clock64();
+        // level by level, eight walkers at a time: eight independent float64 chains per thread, the next level's
+        // tcgen05.ld in flight under the arithmetic of this one, few registers (no spills at the 128 cap)
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
-          uint32_t rl[CQ_ND][8];
           const uint32_t ta = lane_addr + buf * CQ_ACC_COLS + 16u * sub + 8u * hb;
-#pragma unroll
-          for (int l = 0; l < CQ_ND; ++l) tmem_ld8(ta + (uint32_t)l * CQ_NW, rl[l]);
+          uint32_t ra[8], rb[8];
+          double T[8];
+          tmem_ld8(ta, ra);
           tc_wait_ld();
+          tmem_ld8(ta + CQ_NW, rb);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            double T = cq_i2d(rl[0][c]);
+          for (int c = 0; c < 8; ++c) T[c] = cq_i2d(ra[c]);
 #pragma unroll
-            for (int l = 1; l < CQ_ND; ++l) T = fma(T, 256.0, cq_i2d(rl[l][c]));
-            acc[8 * hb + c] = fma(T * cs, dj[8 * hb + c], acc[8 * hb + c]);
+          for (int l = 1; l < CQ_ND; ++l) {
+            tc_wait_ld();
+            if (l & 1) {
+              if (l + 1 < CQ_ND) tmem_ld8(ta + (uint32_t)(l + 1) * CQ_NW, ra);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) T[c] = fma(T[c], 256.0, cq_i2d(rb[c]));
+            } else {
+              if (l + 1 < CQ_ND) tmem_ld8(ta + (uint32_t)(l + 1) * CQ_NW, rb);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) T[c] = fma(T[c], 256.0, cq_i2d(ra[c]));
+            }
           }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[8 * hb + c] = fma(T[c], cd[8 * hb + c], acc[8 * hb + c]);
         }
         tc_fence_before();
         mbar_arrive(bar_dfree + 8 * buf);
+        if (dbg) p.dbg[10 + 4 * t] = clock64();
+        // the next group's scales under this group's long tiles (the loads also bring its residuals into L2)
+        if (t == tpre && it + 1 < groups_per_cta) row_scales(((it + 1) * gridDim.x + blockIdx.x) * CQ_NW, sel ^ 1);
+        if (dbg) p.dbg[11 + 4 * t] = clock64();
       }
       // ---- sum over the lanes (rows) in a fixed order, then over the four quadrants ----
 #pragma unroll
@@ -235,12 +293,13 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
       }
       cq_epi_bar();
       if (tid < CQ_NW && w0 + tid < W) {
-        const double v = ((red_s[tid] + red_s[CQ_NW + tid]) + (red_s[2 * CQ_NW + tid] + red_s[3 * CQ_NW + tid])) * sd_s[tid];
+        const double v = ((red_s[tid] + red_s[CQ_NW + tid]) + (red_s[2 * CQ_NW + tid] + red_s[3 * CQ_NW + tid])) * sdc[tid];
         double* o = chi2p + (w0 + tid) * ntj;
         o[0] = v;  // k_finalize adds the ntj partial sums of the walker: the rest are zero
         for (int q = 1; q < ntj; ++q) o[q] = 0.0;
       }
-      cq_epi_bar();  // sd_s / red_s are rewritten by the next group
+      if (dbg) p.dbg[2] = clock64();
+      cq_epi_bar();  // red_s lies in the operand region the next group's digits overwrite; the scale buffers alternate
     }
   } else if (warp == CQ_EPI_WARPS) {
     // ================================ MMA issuer ================================
@@ -249,14 +308,18 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
     const uint32_t base16 = base >> 4, ring16 = ring >> 4;
     uint32_t g = 0, tcount = 0;
     for (int64_t it = 0; it < groups_per_cta; ++it) {
-      mbar_wait(bar_bready, (uint32_t)it & 1u);
-      tc_fence_after();
+      const bool dbg = p.dbg && blockIdx.x == 0 && leader && it == 1;
       for (int t = 0; t < p.ntile; ++t, ++tcount) {
         const uint32_t buf = tcount & 1u;
+        if (dbg) p.dbg[48 + 4 * t] = clock64();
+        mbar_wait(bar_tready + 8 * t, (uint32_t)it & 1u);  // the k units of this tile are in shared memory
+        tc_fence_after();
+        if (dbg) p.dbg[49 + 4 * t] = clock64();
         if (tcount >= 2u) {
           mbar_wait(bar_dfree + 8 * buf, ((tcount >> 1) - 1u) & 1u);
           tc_fence_after();
         }
+        if (dbg) p.dbg[50 + 4 * t] = clock64();
         const uint32_t d0 = tmem_base + buf * CQ_ACC_COLS;
         const int nu = p.tile_units[t];
         for (int u = 0; u < nu; ++u, ++g) {
@@ -278,6 +341,7 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
           }
           __syncwarp();
         }
+        if (dbg) p.dbg[51 + 4 * t] = clock64();
       }
     }
   } else {
@@ -321,16 +385,15 @@ int c1d_chi2i8_prepare(c1d_ctx* ctx) {
   const int nunits_b = ldd / 32;
   const size_t off_ring = ((size_t)nunits_b * CQ_BUNIT + 1023) & ~(size_t)1023;
   const size_t off_sd = off_ring + (size_t)CQ_NSLOT * CQ_AUNIT;
-  const size_t off_red = off_sd + CQ_NW * sizeof(double);
-  const size_t off_bar = off_red + 4 * CQ_NW * sizeof(double);
-  const size_t smem = off_bar + 128;
+  const size_t off_bar = off_sd + 2 * CQ_NW * sizeof(double);
+  const size_t smem = off_bar + 192;
   if (smem > CQ_SMEM_MAX) return C1D_OK;  // more than 704 data points: unavailable
   CQState* st = new CQState();
   memset(st, 0, sizeof(*st));
   ctx->chi2i8_state = st;
   CQParams& p = st->p;
   p.ntile = ntile; p.nunits_b = nunits_b; p.ldd = ldd; p.nd = nd;
-  p.off_ring = (uint32_t)off_ring; p.off_sd = (uint32_t)off_sd; p.off_red = (uint32_t)off_red; p.off_bar = (uint32_t)off_bar;
+  p.off_ring = (uint32_t)off_ring; p.off_sd = (uint32_t)off_sd; p.off_bar = (uint32_t)off_bar;
   st->smem = smem;
   const int h0 = ldd - 128 * (ntile - 1);  // the short tile first
   int total_units = 0;
@@ -384,6 +447,12 @@ int c1d_chi2i8_prepare(c1d_ctx* ctx) {
   p.img = (const uint8_t*)st->d_img;
   p.rscale = (const double*)st->d_rscale;
   C1D_CUDA(ctx, cudaFuncSetAttribute(k_chi2_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p.dbg = nullptr;
+  if (getenv("C1D_CHI2_DEBUG")) {
+    C1D_CUDA(ctx, cudaMalloc(&st->d_dbg, 96 * sizeof(long long)));
+    C1D_CUDA(ctx, cudaMemset(st->d_dbg, 0, 96 * sizeof(long long)));
+    p.dbg = (long long*)st->d_dbg;
+  }
   st->ready = true;
   return C1D_OK;
 }
@@ -404,13 +473,25 @@ int c1d_chi2i8_launch(c1d_ctx* ctx, int64_t W, int ntj, cudaStream_t s) {
   k_chi2_i8<<<grid, CQ_THREADS, st->smem, s>>>(st->p, ctx->ws.dvec, W, ctx->ws.chi2p, ntj);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
+  if (st->p.dbg && ngroups > 2 * grid) {
+    // diagnostic: the second group of CTA 0, cycles relative to its start; synchronises
+    long long h[96];
+    C1D_CUDA(ctx, cudaStreamSynchronize(s));
+    C1D_CUDA(ctx, cudaMemcpy(h, st->d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    const long long t0 = h[0];
+    fprintf(stderr, "chi2 i8 group: digits done %lld  epilogues done %lld\n", h[1] - t0, h[2] - t0);
+    for (int t = 0; t < st->p.ntile; ++t)
+      fprintf(stderr, "  tile %d (%2d units): epilogue warp waits from %6lld to %6lld, loads done %6lld, after scales %6lld | MMA warp: at %6lld, digits ready %6lld, accumulators free %6lld, issued %6lld\n",
+              t, st->p.tile_units[t], h[8 + 4 * t] - t0, h[9 + 4 * t] - t0, h[10 + 4 * t] - t0, h[11 + 4 * t] - t0, h[48 + 4 * t] - t0,
+              h[49 + 4 * t] - t0, h[50 + 4 * t] - t0, h[51 + 4 * t] - t0);
+  }
   return C1D_OK;
 }
 
 void c1d_chi2i8_destroy(c1d_ctx* ctx) {
   CQState* st = (CQState*)ctx->chi2i8_state;
   if (!st) return;
-  cudaFree(st->d_img); cudaFree(st->d_rscale);
+  cudaFree(st->d_img); cudaFree(st->d_rscale); cudaFree(st->d_dbg);
   delete st;
   ctx->chi2i8_state = nullptr;
 }

@@ -79,6 +79,18 @@ struct Workspace {
   double* blobs_q; // [cap*6] blobs of the proposals
 };
 
+// one captured evaluation (c1d_loglike_batch on a small batch): the key is everything the kernel parameters depend on
+#define C1D_NGRAPH 8
+struct c1d_graph_entry {
+  int64_t W;
+  uint32_t flags;
+  const double* x;
+  double *lnp, *lnl_z, *blobs, *chi2;
+  void* exec;        // cudaGraphExec_t
+  int64_t nlaunch;   // kernels in the graph
+  uint64_t stamp;    // last use (least recently used entry is replaced)
+};
+
 struct c1d_ctx {
   c1d_config cfg;
   void* dev[C1D_F_COUNT];
@@ -97,6 +109,11 @@ struct c1d_ctx {
   // host-buffer entry point: copy stream and events that order its uploads / downloads against the kernels
   cudaStream_t copy_stream;
   cudaEvent_t ev_up[2], ev_done[2];
+  // CUDA graphs of small-batch evaluations (c1d_abi.cu)
+  cudaStream_t graph_stream;
+  c1d_graph_entry graphs[C1D_NGRAPH], graph_seen[C1D_NGRAPH];  // captured; keys met once (captured on their second call)
+  uint64_t graph_clock;
+  int64_t graph_replays;
   double last_ms[8];
   double* icov_pad;  // [ldd*ldd] zero-padded copy of the dense inverse covariance
   double* icovz_pad; // [nz][tzw*tzw] zero-padded per-z inverse covariance blocks, tzw = ndz_max rounded up to 64
@@ -135,6 +152,7 @@ int c1d_launch_chi2(c1d_ctx* ctx, int64_t W, uint32_t flags, cudaStream_t s);
 int c1d_launch_finalize(c1d_ctx* ctx, int64_t W, double* lnp, double* lnl_z, double* blobs,
                         double* chi2, uint32_t flags, cudaStream_t s);
 
+void c1d_graphs_clear(c1d_ctx* ctx);  // drop the captured small-batch evaluations (their parameters went stale)
 int c1d_launch_pack7(c1d_ctx* ctx, int64_t w0, int64_t W, cudaStream_t s);  // rows [w0, w0 + W) of ws.lnp / ws.blobs -> ws.out7
 
 // fp64 (DMMA) MLP: padded weight image + slab plan, built at finalize

@@ -266,6 +266,11 @@ int c1d_emulator_paths(const c1d_ctx* ctx);
 /* number of kernels launched by this context since creation */
 int64_t c1d_launch_count(const c1d_ctx* ctx);
 
+/* number of c1d_loglike_batch calls served by replaying a captured CUDA graph: batches of at most 8192 walkers
+ * (C1D_GRAPH=<walkers> in the environment, 0 = off) whose shape, flags and buffers repeat the previous call's are
+ * captured once and replayed; their kernels count in c1d_launch_count as if launched one by one */
+int64_t c1d_graph_replays(const c1d_ctx* ctx);
+
 /* per-stage device time [ms], measured with CUDA events on the caller's stream when enabled
  * (0 = off, default).  The events are read back lazily, so the evaluation calls stay
  * asynchronous: c1d_get_timing waits for the evaluations recorded so far, returns the times
