@@ -26,7 +26,7 @@ os.makedirs(OUT, exist_ok=True)
 PROF = os.path.join(OUT, "profiles")
 os.makedirs(PROF, exist_ok=True)
 CMD = [sys.executable, "bench.py", "--steps", "2", "--warmup", "3", "--no-cpu-baseline", "--no-alt", "--no-sampler", "--no-verify"]
-KERNELS = "k_mlp_i8|k_fused_p1d_lanes|k_chi2_dmma|k_stage1"
+KERNELS = "k_mlp_i8|k_fused_p1d_lanes|k_p1d_split|k_chi2_i8|k_chi2_dmma|k_stage1"
 
 
 def run(cmd, **kw):
