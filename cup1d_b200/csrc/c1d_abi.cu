@@ -286,7 +286,7 @@ extern "C" int c1d_ctx_finalize(c1d_ctx* ctx) {
 static void ws_free(c1d_ctx* ctx) {
   Workspace& w = ctx->ws;
   cudaFree(w.status); cudaFree(w.lnprior); cudaFree(w.blobs); cudaFree(w.emu_in); cudaFree(w.amp);
-  cudaFree(w.dvec); cudaFree(w.dvz); cudaFree(w.chi2z); cudaFree(w.chi2p); cudaFree(w.lnp); cudaFree(w.xdev); cudaFree(w.out7); cudaFree(w.factors); cudaFree(w.blobs_q);
+  cudaFree(w.dvec); cudaFree(w.dvz); cudaFree(w.chi2z); cudaFree(w.chi2p); cudaFree(w.lnp); cudaFree(w.xdev); cudaFree(w.xt); cudaFree(w.out7); cudaFree(w.factors); cudaFree(w.blobs_q);
   memset(&w, 0, sizeof(w));
 }
 
@@ -309,6 +309,7 @@ static int ws_reserve(c1d_ctx* ctx, int64_t W) {
   C1D_CUDA(ctx, cudaMalloc(&w.chi2p, (size_t)cap * (ctx->d.ldd / 64) * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.lnp, cap * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.xdev, (size_t)cap * c.ndim * sizeof(double)));
+  C1D_CUDA(ctx, cudaMalloc(&w.xt, (size_t)cap * c.ndim * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.out7, (size_t)cap * 7 * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.factors, cap * sizeof(double)));
   C1D_CUDA(ctx, cudaMalloc(&w.blobs_q, (size_t)cap * 6 * sizeof(double)));
@@ -432,7 +433,21 @@ void c1d_graphs_clear(c1d_ctx* ctx) {
 
 static bool graph_key_eq(const c1d_graph_entry& a, const c1d_graph_entry& b) {
   return a.W == b.W && a.flags == b.flags && a.x == b.x && a.lnp == b.lnp && a.lnl_z == b.lnl_z && a.blobs == b.blobs &&
-         a.chi2 == b.chi2;
+         a.chi2 == b.chi2 && a.envh == b.envh;
+}
+
+// the launchers read diagnostic switches from the environment at every launch (kernel form, tile counts): a graph
+// captured under one setting must not serve a call made under another (the tests flip them between calls)
+static uint64_t graph_env_hash() {
+  static const char* names[] = {"C1D_P1D_LAYOUT", "C1D_P1D_PARTS", "C1D_GP_KERNEL", "C1D_CHI2_GROUP", "C1D_CHI2_STAGES",
+                                "C1D_MLP64_G", "C1D_TC_CLUSTER"};
+  uint64_t h = 1469598103934665603ull;  // FNV-1a
+  for (const char* n : names) {
+    const char* v = getenv(n);
+    for (const char* q = v ? v : ""; *q; ++q) h = (h ^ (uint8_t)*q) * 1099511628211ull;
+    h = (h ^ 0xffu) * 1099511628211ull;
+  }
+  return h;
 }
 
 static int64_t graph_max_walkers() {
@@ -464,7 +479,7 @@ extern "C" int c1d_loglike_batch(c1d_ctx* ctx, const double* x_dev, int64_t W, d
   if (W <= graph_max_walkers() && !ctx->timing) {
     c1d_graph_entry key;
     memset(&key, 0, sizeof(key));
-    key.W = W; key.flags = flags; key.x = x_dev; key.lnp = lnp_dev; key.lnl_z = lnl_z_dev; key.blobs = blobs_dev; key.chi2 = chi2_dev;
+    key.W = W; key.flags = flags; key.x = x_dev; key.lnp = lnp_dev; key.lnl_z = lnl_z_dev; key.blobs = blobs_dev; key.chi2 = chi2_dev; key.envh = graph_env_hash();
     for (int i = 0; i < C1D_NGRAPH; ++i)
       if (ctx->graphs[i].exec && graph_key_eq(ctx->graphs[i], key)) {
         C1D_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)ctx->graphs[i].exec, s));

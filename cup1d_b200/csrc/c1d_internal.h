@@ -74,6 +74,7 @@ struct Workspace {
   double* chi2p;   // [cap*(ldd/64)] partial dense chi2 per 64-column tile
   double* lnp;     // [cap]   (host-variant staging on the device)
   double* xdev;    // [cap*ndim]
+  double* xt;      // [ndim*cap] transposed cube coordinates of a chunk (stage 1 of large batches)
   double* out7;    // [cap*7] packed (lnP, blob[6]) rows for the host variant
   double* factors; // [cap] (n-1) ln z of the stretch-move proposals
   double* blobs_q; // [cap*6] blobs of the proposals
@@ -86,6 +87,7 @@ struct c1d_graph_entry {
   uint32_t flags;
   const double* x;
   double *lnp, *lnl_z, *blobs, *chi2;
+  uint64_t envh;     // hash of the diagnostic environment switches the launchers read
   void* exec;        // cudaGraphExec_t
   int64_t nlaunch;   // kernels in the graph
   uint64_t stamp;    // last use (least recently used entry is replaced)

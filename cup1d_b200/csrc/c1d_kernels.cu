@@ -24,15 +24,46 @@
 // ---------------------------------------------------------------------------------------
 // stage 1
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double param_value(const DevCtx& c, const double* xw, int i) {
+// the walker's cube coordinates: row w of x[W][ndim], or column w of the transposed copy xt[ndim][W] (large batches:
+// the lanes of a warp are consecutive walkers, so a coordinate of 32 walkers is one 256-byte segment of xt against 32
+// lines of x - the row-major gather kept the kernel at the L1 tag rate, ~100 loads x 32 lines per warp)
+template <bool XT>
+struct XRow {
+  const double* p;
+  int64_t stride;
+  __device__ __forceinline__ double operator[](int i) const { return XT ? p[(int64_t)i * stride] : p[i]; }
+};
+template <bool XT>
+__device__ __forceinline__ double param_value(const DevCtx& c, const XRow<XT>& xw, int i) {
   // likelihood_parameter.py:58-61
   return c.pmin[i] + xw[i] * c.pscale[i];
+}
+
+// xt[i][w] = x[w][i] through 32 x 33 shared-memory tiles
+__global__ void __launch_bounds__(256)
+k_transpose_x(const double* __restrict__ x, int64_t W, int ndim, double* __restrict__ xt) {
+  __shared__ double tile[32][33];
+  const int64_t w0 = (int64_t)blockIdx.x * 32;
+  const int i0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t w = w0 + r;
+    const int i = i0 + tx;
+    tile[r][tx] = (w < W && i < ndim) ? x[w * ndim + i] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r;
+    const int64_t w = w0 + tx;
+    if (i < ndim && w < W) xt[(int64_t)i * W + w] = tile[tx][r];
+  }
 }
 
 // One thread per (walker, z): blockIdx.y is the redshift bin.  The z = 0 thread of a walker also does
 // the walker-level work (cube test, Gaussian prior, blobs, star-prior box).  The status word is zeroed
 // before the launch and combined with atomicMax (out of cube > rejected > ok).
 #define S1_THREADS 128
+template <bool XT, int EW>  // EW: compile-time ELL width (0 = read it from the context)
 __global__ void __launch_bounds__(S1_THREADS)
 k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ status,
          double* __restrict__ lnprior, double* __restrict__ blobs, double* __restrict__ emu_in,
@@ -66,7 +97,7 @@ k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ st
   const int64_t w = wb0 + threadIdx.x;
   const bool live = w < W;
   if (live) {
-  const double* xw = x + w * c.ndim;
+  const XRow<XT> xw = {XT ? x + w : x + w * c.ndim, W};
 
   // primordial-power rescaling (lya_theory.py:281-307, 542-580)
   double ratio_As = 1.0, d_ns = 0.0, d_nrun = 0.0;
@@ -115,6 +146,34 @@ k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ st
   // rows of walkers that end up rejected are written too (finite or not): later stages skip them by status
   {
     double q[C1D_NQ];
+    if (EW > 0) {
+      // the coordinates of four quantities at a time: their loads are independent and in flight together (the kernel
+      // is bound by the latency of these gathers: one dependent round trip per quantity otherwise)
+      static_assert(C1D_NQ % 4 == 0, "quantities in groups of four");
+#pragma unroll 1
+      for (int iq0 = 0; iq0 < C1D_NQ; iq0 += 4) {
+        double xv[4][EW > 0 ? EW : 1];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int e = 0; e < EW; ++e) {
+            const int idx = s_idx[(iq0 + a) * EW + e];
+            xv[a][e] = xw[idx >= 0 ? idx : 0];
+          }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int iq = iq0 + a;
+          double lin = c.zbase[iq * c.nz + z];
+#pragma unroll
+          for (int e = 0; e < EW; ++e) {
+            const int t = iq * EW + e;
+            if (s_idx[t] >= 0) lin += s_wgt[t] * (s_pm[t] + xv[a][e] * s_ps[t]);  // same operations in the same order as below
+          }
+          double v = c.zotype[iq] ? exp(lin) : lin;
+          q[iq] = (lin <= c.znull[iq]) ? 0.0 : v;
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int iq = 0; iq < C1D_NQ; ++iq) {
       int row = iq * c.nz + z;
@@ -127,6 +186,7 @@ k_stage1(DevCtx c, const double* __restrict__ x, int64_t W, int* __restrict__ st
       // zero the '<= null' values (si_mult.py:170-176), then the output type
       double v = c.zotype[iq] ? exp(lin) : lin;
       q[iq] = (lin <= c.znull[iq]) ? 0.0 : v;
+    }
     }
     double M = c.mz[z];
     // IGM histories (mean_flux_class.py:51-61, thermal_class.py:52-72, pressure_class.py:51-56)
@@ -221,8 +281,19 @@ int c1d_launch_stage1(c1d_ctx* ctx, const double* x, int64_t W, double* blobs_ou
   int64_t blocks = (W + threads - 1) / threads;
   C1D_CUDA(ctx, cudaMemsetAsync(ctx->ws.status, 0, (size_t)W * sizeof(int), s));
   const size_t smem1 = (size_t)C1D_NQ * ctx->cfg.ell_width * (3 * sizeof(double) + sizeof(int));
-  k_stage1<<<dim3((unsigned)blocks, (unsigned)ctx->cfg.nz), threads, smem1, s>>>(ctx->d, x, W, ctx->ws.status, ctx->ws.lnprior,
-                                                 blobs_out, ctx->ws.emu_in, ctx->ws.amp, flags);
+  // from a few thousand walkers on the kernel reads a transposed copy of the coordinates (one more small launch)
+  static const int64_t xt_min = getenv("C1D_S1_XT_MIN") ? atoll(getenv("C1D_S1_XT_MIN")) : 4096;
+  if (W >= xt_min) {
+    k_transpose_x<<<dim3((unsigned)((W + 31) / 32), (unsigned)((ctx->cfg.ndim + 31) / 32)), 256, 0, s>>>(x, W, ctx->cfg.ndim, ctx->ws.xt);
+    ctx->launches++;
+    auto kern = ctx->cfg.ell_width == 2 ? k_stage1<true, 2> : ctx->cfg.ell_width == 4 ? k_stage1<true, 4> : k_stage1<true, 0>;
+    kern<<<dim3((unsigned)blocks, (unsigned)ctx->cfg.nz), threads, smem1, s>>>(ctx->d, ctx->ws.xt, W, ctx->ws.status, ctx->ws.lnprior, blobs_out,
+                                                                               ctx->ws.emu_in, ctx->ws.amp, flags);
+  } else {
+    auto kern = ctx->cfg.ell_width == 2 ? k_stage1<false, 2> : ctx->cfg.ell_width == 4 ? k_stage1<false, 4> : k_stage1<false, 0>;
+    kern<<<dim3((unsigned)blocks, (unsigned)ctx->cfg.nz), threads, smem1, s>>>(ctx->d, x, W, ctx->ws.status, ctx->ws.lnprior, blobs_out,
+                                                                               ctx->ws.emu_in, ctx->ws.amp, flags);
+  }
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
   return C1D_OK;
