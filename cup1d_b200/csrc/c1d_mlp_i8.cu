@@ -549,9 +549,11 @@ int c1d_i8_prepare(c1d_ctx* ctx) {
           qd[(size_t)n * kpad[l] + k] = ((uint32_t)(int32_t)q + 0x80808080u) ^ 0x80808080u;
         }
     }
-    // blocks
-    int nbs[2] = {npad[l], 0};
-    if (nblk[l] == 2) { nbs[0] = 128; nbs[1] = npad[l] - 128; }
+    // blocks.  On the N side a layer is padded to 16 columns only (the MMA shapes need no more): the k columns of the
+    // next operand between that and its 32-k padding are never written, and meet zero weight digits.
+    const int n16 = (N + 15) & ~15;
+    int nbs[2] = {n16, 0};
+    if (nblk[l] == 2) { nbs[0] = 128; nbs[1] = n16 - 128; }
     const bool out_groups = (mode[l] == 1);  // this layer's blocks become the K-groups of the next layer
     int n0 = 0;
     for (int b = 0; b < nblk[l]; ++b) {
