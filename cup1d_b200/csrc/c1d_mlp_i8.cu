@@ -112,7 +112,6 @@ struct I8Params {
   int n_units, n_blocks, n_in, last_out;
   int col_off[C1D_MAX_LAYERS];  // offset of the layer in sw / bias
   double slope;
-  int merge;  // 1: two digit pairs per tcgen05.mma (level accumulators nb columns apart); C1D_I8_MERGE=0 keeps ten instructions per unit
   int exp;  // C1D_I8_EXP (measurements only, results are wrong): 1 = no weight copies, 2 = epilogues without arithmetic
   long long* dbg;  // C1D_I8_DEBUG=1: CTA 0 records the clock of its second tile per (layer, n-block), 8 slots each
   I8Blk blk[I8_MAX_BLOCKS];
@@ -381,13 +380,50 @@ k_mlp_i8(I8Params p, const double* __restrict__ emu_in, int64_t nrows, double* _
     const uint64_t desc_sw64_0 = make_desc_sw64(0), desc_sw32_0 = make_desc_sw32(0);
     const uint32_t base16 = base >> 4, ring16 = ring >> 4;
     uint32_t go_phase = 0, g = 0;
+    // The fields of a unit (constant-bank loads indexed by the unit, descriptor arithmetic, the moves into uniform
+    // registers) are prepared one unit AHEAD, before the MMAs of the current unit are issued: the issue of an MMA waits
+    // for the tensor pipe, so whatever sits between the last MMA of one unit and the first of the next is idle tensor
+    // time (measured: ~240 cycles per unit, 40 units per tile, before this change)
+    uint32_t n_flags, n_idesc, n_d0, n_ls, n_slot;
+    uint64_t n_ad0, n_astep, n_bd0, n_bstep;
+    uint32_t r_flags, r_idesc, r_a16, r_apst, r_dcol, r_ls;  // raw fields of the unit after the current one
+#define I8_LOAD(U_)                       \
+  do {                                    \
+    r_flags = p.units[U_].flags;          \
+    r_idesc = p.units[U_].idesc;          \
+    r_a16 = p.units[U_].a16;              \
+    r_apst = p.units[U_].a_pstride16;     \
+    r_dcol = p.units[U_].dcol;            \
+    r_ls = p.units[U_].lstride;           \
+  } while (0)
+#define I8_DERIVE(G_)                                                                \
+  do {                                                                               \
+    n_flags = r_flags;                                                               \
+    n_idesc = r_idesc;                                                               \
+    n_slot = (G_) % I8_NSLOT;                                                        \
+    n_ad0 = desc_sw64_0 | (uint64_t)(base16 + r_a16);                                \
+    n_astep = r_apst;                                                                \
+    n_bd0 = desc_sw32_0 | (uint64_t)(ring16 + n_slot * (I8_SLOT >> 4));              \
+    n_bstep = (r_idesc >> 17) << 4; /* nb rows x 32 B per plane, / 16 */             \
+    n_d0 = tmem_base + r_dcol;                                                       \
+    n_ls = r_ls;                                                                     \
+  } while (0)
+    I8_LOAD(0);
+    I8_DERIVE(g);
     for (int64_t it = 0; it < tiles_per_cta; ++it) {
       const bool dbg = p.dbg && blockIdx.x == 0 && leader && it == 1;
       const bool dbgw = p.dbg && blockIdx.x == 0 && it == 1;
       long long st0 = 0, st1 = 0, st2 = 0;  // per-unit clocks, one unit per lane (cheap: no memory traffic inside the loop)
       int bidx = -1;
       for (int u = 0; u < p.n_units; ++u, ++g) {
-        const uint32_t uflags = p.units[u].flags;
+        const uint32_t uflags = n_flags, idesc = n_idesc, d0 = n_d0, ls = n_ls, slot = n_slot;
+        // descriptors: constant fields | address >> 4 (addresses stay below 2^18, no masking needed)
+        const uint64_t ad0 = n_ad0, astep = n_astep, bd0 = n_bd0, bstep = n_bstep;
+        // the constant-bank loads of the next unit are issued here and consumed after this unit's MMAs are issued
+        // (the asm pins them in program order: the MMAs below are volatile statements)
+        const int un = (u + 1 < p.n_units) ? u + 1 : 0;
+        I8_LOAD(un);
+        asm volatile("" : "+r"(r_flags), "+r"(r_idesc), "+r"(r_a16), "+r"(r_apst), "+r"(r_dcol), "+r"(r_ls)::"memory");
         if (uflags & 4u) {
           ++bidx;
           if (dbg) p.dbg[8 * bidx + 4] = clock64();
@@ -396,46 +432,37 @@ k_mlp_i8(I8Params p, const double* __restrict__ emu_in, int64_t nrows, double* _
           tc_fence_after();
           if (dbg) p.dbg[8 * bidx + 5] = clock64();
         }
-        const uint32_t slot = g % I8_NSLOT;
         if (!(p.exp & 1)) mbar_wait(bar_bfull + 8 * slot, (g / I8_NSLOT) & 1u);
         tc_fence_after();
-        const uint32_t idesc = p.units[u].idesc;
-        // descriptors: constant fields | address >> 4 (addresses stay below 2^18, no masking needed)
-        const uint64_t ad0 = desc_sw64_0 | (uint64_t)(base16 + p.units[u].a16), astep = p.units[u].a_pstride16;
-        const uint64_t bd0 = desc_sw32_0 | (uint64_t)(ring16 + slot * (I8_SLOT >> 4)), bstep = (idesc >> 17) << 4;  // nb rows x 32 B per plane, / 16
-        const uint32_t d0 = tmem_base + p.units[u].dcol, ls = p.units[u].lstride;
         const uint32_t keep = (uflags & 1u) ? 0u : 1u;
-        if (leader && p.merge) {
+        if (leader) {
           // Digit planes j, j + 1 of the weights are consecutive row groups of one operand and the level accumulators
           // consecutive column groups (lstride = nb), so one instruction of N = 2 nb serves two pairs: six instructions
           // instead of ten, 64 KB instead of 80 KB of operand reads per unit (the SS form is shared-memory bound at
           // N <= 128: tools/i8_probe.cu)
-          const uint32_t idesc2 = idesc + (idesc & (63u << 17));  // N -> 2 N
+          const uint32_t nfield = idesc & (63u << 17);
+          const uint32_t idesc2 = idesc + nfield;  // N -> 2 N
+          if (nfield <= (8u << 17)) {
+            // blocks of at most 64 columns: plane i of the activations against ALL the weight planes it pairs with
+            // (N = (4 - i) nb <= 256), four instructions per unit and each A plane read once
+            mma_i8_ss(d0, ad0, bd0, idesc2 + 2 * nfield, keep);                   // (0,0..3) -> levels 0..3
+            mma_i8_ss(d0 + ls, ad0 + astep, bd0, idesc2 + nfield, 1u);            // (1,0..2) -> levels 1..3
+            mma_i8_ss(d0 + 2 * ls, ad0 + 2 * astep, bd0, idesc2, 1u);             // (2,0..1) -> levels 2, 3
+            mma_i8_ss(d0 + 3 * ls, ad0 + 3 * astep, bd0, idesc, 1u);              // (3,0)    -> level 3
+          } else {
           mma_i8_ss(d0, ad0, bd0, idesc2, keep);                                  // (0,0) (0,1) -> levels 0, 1
           mma_i8_ss(d0 + 2 * ls, ad0, bd0 + 2 * bstep, idesc2, keep);             // (0,2) (0,3) -> levels 2, 3
           mma_i8_ss(d0 + ls, ad0 + astep, bd0, idesc2, 1u);                       // (1,0) (1,1) -> levels 1, 2
           mma_i8_ss(d0 + 3 * ls, ad0 + astep, bd0 + 2 * bstep, idesc, 1u);        // (1,2)       -> level 3
           mma_i8_ss(d0 + 2 * ls, ad0 + 2 * astep, bd0, idesc2, 1u);               // (2,0) (2,1) -> levels 2, 3
           mma_i8_ss(d0 + 3 * ls, ad0 + 3 * astep, bd0, idesc, 1u);                // (3,0)       -> level 3
-          tc_commit(bar_bempty + 8 * slot);
-          if (uflags & 2u) tc_commit(bar_dfull);
-          if (dbg && (uflags & 2u)) p.dbg[8 * bidx + 6] = clock64();
-        } else if (leader) {
-          // the pairs (0, j) are the first writers of the level accumulators
-          mma_i8_ss(d0, ad0, bd0, idesc, keep);
-          mma_i8_ss(d0 + ls, ad0, bd0 + bstep, idesc, keep);
-          mma_i8_ss(d0 + 2 * ls, ad0, bd0 + 2 * bstep, idesc, keep);
-          mma_i8_ss(d0 + 3 * ls, ad0, bd0 + 3 * bstep, idesc, keep);
-          mma_i8_ss(d0 + ls, ad0 + astep, bd0, idesc, 1u);
-          mma_i8_ss(d0 + 2 * ls, ad0 + astep, bd0 + bstep, idesc, 1u);
-          mma_i8_ss(d0 + 3 * ls, ad0 + astep, bd0 + 2 * bstep, idesc, 1u);
-          mma_i8_ss(d0 + 2 * ls, ad0 + 2 * astep, bd0, idesc, 1u);
-          mma_i8_ss(d0 + 3 * ls, ad0 + 2 * astep, bd0 + bstep, idesc, 1u);
-          mma_i8_ss(d0 + 3 * ls, ad0 + 3 * astep, bd0, idesc, 1u);
+          }
           tc_commit(bar_bempty + 8 * slot);
           if (uflags & 2u) tc_commit(bar_dfull);
           if (dbg && (uflags & 2u)) p.dbg[8 * bidx + 6] = clock64();
         }
+        I8_DERIVE(g + 1);
+        asm volatile("" : "+r"(n_flags), "+r"(n_idesc), "+r"(n_d0), "+r"(n_ls), "+r"(n_slot), "+l"(n_ad0), "+l"(n_astep), "+l"(n_bd0), "+l"(n_bstep)::"memory");
         __syncwarp();
         if (dbgw) {
           const long long now = clock64();
@@ -526,7 +553,6 @@ int c1d_i8_prepare(c1d_ctx* ctx) {
   p.n_in = c.layer_dims[0];
   p.last_out = c.layer_dims[L];
   p.slope = c.nn_slope;
-  p.merge = getenv("C1D_I8_MERGE") ? atoi(getenv("C1D_I8_MERGE")) : 1;
   std::vector<I8Unit> units;
   std::vector<I8Blk> blks;
   std::vector<uint8_t> img;
@@ -586,7 +612,7 @@ int c1d_i8_prepare(c1d_ctx* ctx) {
       if (gin[l] == 2) { B.dcol = 0; B.lstride = 64; B.gstride = 256; }
       else if (b == 1 && mode[l] == 0) { B.dcol = 256; B.lstride = 64; B.gstride = 0; }
       else { B.dcol = 0; B.lstride = 128; B.gstride = 0; }
-      if (p.merge) B.lstride = (uint16_t)nb;  // consecutive level accumulators: one MMA covers two of them
+      B.lstride = (uint16_t)nb;  // consecutive level accumulators: one MMA covers two of them
       B.hlo = B.dcol;
       B.hhi = (uint16_t)(B.dcol + B.lstride);
       if (out_groups) {
