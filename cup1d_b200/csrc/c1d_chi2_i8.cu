@@ -330,8 +330,7 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
         const int nu = p.tile_units[t];
         for (int u = 0; u < nu; ++u, ++g) {
           const uint32_t slot = g % CQ_NSLOT;
-          mbar_wait(bar_bfull + 8 * slot, (g / CQ_NSLOT) & 1u);
-          tc_fence_after();
+          mbar_wait_fast(bar_bfull + 8 * slot, (g / CQ_NSLOT) & 1u);  // (complete_tx orders the bulk copy before the MMAs)
           const uint64_t ad0 = desc0 | (uint64_t)(ring16 + slot * (CQ_AUNIT >> 4));
           const uint64_t bd0 = desc0 | (uint64_t)(base16 + (uint32_t)u * (CQ_BUNIT >> 4));
           const uint32_t keep = u ? 1u : 0u;

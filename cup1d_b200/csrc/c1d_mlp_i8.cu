@@ -80,7 +80,8 @@ struct I8Unit {        // one weight unit = 32 k of one (layer, n-block, K-group
   uint16_t dcol;       // TMEM column of the level-0 accumulator of this (block, group)
   uint8_t lstride;     // columns between level accumulators
   uint8_t flags;       // 1 first k-step of its (block, group): overwrite; 2 last unit of its block: signal the
-                       // epilogue; 4 first unit of its block: wait for the epilogue's go
+                       // epilogue; 4 first unit of its block: wait for the epilogue's go; 8 two k-steps (the second 32 k
+                       // follow in the A chunk and in the weight image)
 };
 static_assert(sizeof(I8Unit) == 16, "I8Unit layout");
 
@@ -424,6 +425,9 @@ k_mlp_i8(I8Params p, const double* __restrict__ emu_in, int64_t nrows, double* _
         const int un = (u + 1 < p.n_units) ? u + 1 : 0;
         I8_LOAD(un);
         asm volatile("" : "+r"(r_flags), "+r"(r_idesc), "+r"(r_a16), "+r"(r_apst), "+r"(r_dcol), "+r"(r_ls)::"memory");
+        const bool dbgu = dbg && p.dbg && (p.exp & 4) && u < 64;
+        long long q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+        if (dbgu) q0 = clock64();
         if (uflags & 4u) {
           ++bidx;
           if (dbg) p.dbg[8 * bidx + 4] = clock64();
@@ -432,9 +436,11 @@ k_mlp_i8(I8Params p, const double* __restrict__ emu_in, int64_t nrows, double* _
           tc_fence_after();
           if (dbg) p.dbg[8 * bidx + 5] = clock64();
         }
-        if (!(p.exp & 1)) mbar_wait(bar_bfull + 8 * slot, (g / I8_NSLOT) & 1u);
-        tc_fence_after();
+        // (no tcgen05 fence here: the barrier's complete_tx orders the bulk copy before the MMAs that read it; the fence
+        // after the `go` wait above orders the epilogue warps' tensor-memory accesses)
+        if (!(p.exp & 1)) mbar_wait_fast(bar_bfull + 8 * slot, (g / I8_NSLOT) & 1u);
         const uint32_t keep = (uflags & 1u) ? 0u : 1u;
+        if (dbgu) q1 = clock64();
         if (leader) {
           // Digit planes j, j + 1 of the weights are consecutive row groups of one operand and the level accumulators
           // consecutive column groups (lstride = nb), so one instruction of N = 2 nb serves two pairs: six instructions
@@ -449,6 +455,13 @@ k_mlp_i8(I8Params p, const double* __restrict__ emu_in, int64_t nrows, double* _
             mma_i8_ss(d0 + ls, ad0 + astep, bd0, idesc2 + nfield, 1u);            // (1,0..2) -> levels 1..3
             mma_i8_ss(d0 + 2 * ls, ad0 + 2 * astep, bd0, idesc2, 1u);             // (2,0..1) -> levels 2, 3
             mma_i8_ss(d0 + 3 * ls, ad0 + 3 * astep, bd0, idesc, 1u);              // (3,0)    -> level 3
+            if (uflags & 8u) {  // the unit's second k-step: 32 bytes on in the A chunk, four planes on in the slot
+              const uint64_t ad1 = ad0 + 2, bd1 = bd0 + 4 * bstep;
+              mma_i8_ss(d0, ad1, bd1, idesc2 + 2 * nfield, 1u);
+              mma_i8_ss(d0 + ls, ad1 + astep, bd1, idesc2 + nfield, 1u);
+              mma_i8_ss(d0 + 2 * ls, ad1 + 2 * astep, bd1, idesc2, 1u);
+              mma_i8_ss(d0 + 3 * ls, ad1 + 3 * astep, bd1, idesc, 1u);
+            }
           } else {
           mma_i8_ss(d0, ad0, bd0, idesc2, keep);                                  // (0,0) (0,1) -> levels 0, 1
           mma_i8_ss(d0 + 2 * ls, ad0, bd0 + 2 * bstep, idesc2, keep);             // (0,2) (0,3) -> levels 2, 3
@@ -457,9 +470,15 @@ k_mlp_i8(I8Params p, const double* __restrict__ emu_in, int64_t nrows, double* _
           mma_i8_ss(d0 + 2 * ls, ad0 + 2 * astep, bd0, idesc2, 1u);               // (2,0) (2,1) -> levels 2, 3
           mma_i8_ss(d0 + 3 * ls, ad0 + 3 * astep, bd0, idesc, 1u);                // (3,0)       -> level 3
           }
+          if (dbgu) q2 = clock64();
           tc_commit(bar_bempty + 8 * slot);
           if (uflags & 2u) tc_commit(bar_dfull);
           if (dbg && (uflags & 2u)) p.dbg[8 * bidx + 6] = clock64();
+          if (dbgu) {
+            q3 = clock64();
+            long long* o = p.dbg + 8 * I8_MAX_BLOCKS + 96 + 4 * u;
+            o[0] = q0; o[1] = q1; o[2] = q2; o[3] = q3;
+          }
         }
         I8_DERIVE(g + 1);
         asm volatile("" : "+r"(n_flags), "+r"(n_idesc), "+r"(n_d0), "+r"(n_ls), "+r"(n_slot), "+l"(n_ad0), "+l"(n_astep), "+l"(n_bd0), "+l"(n_bstep)::"memory");
@@ -487,7 +506,7 @@ k_mlp_i8(I8Params p, const double* __restrict__ emu_in, int64_t nrows, double* _
         const uint32_t slot = g % I8_NSLOT;
         if (g >= (uint32_t)I8_NSLOT) mbar_wait(bar_bempty + 8 * slot, ((g / I8_NSLOT) - 1u) & 1u);
         if (leader && !(p.exp & 1)) {
-          const uint32_t bytes = ((p.units[u].idesc >> 17) & 63u) << 10;  // nb x 128 B
+          const uint32_t bytes = (((p.units[u].idesc >> 17) & 63u) << 10) << ((p.units[u].flags >> 3) & 1u);  // nb x 128 B per k-step
           mbar_expect_tx(bar_bfull + 8 * slot, bytes);
           bulk_g2s(ring + slot * I8_SLOT, p.wimg + p.units[u].w_off, bytes, bar_bfull + 8 * slot);
         }
@@ -635,6 +654,9 @@ int c1d_i8_prepare(c1d_ctx* ctx) {
         const uint32_t a_pstride = (gin[l] == 2 && g == 0) ? I8_Y_PSTRIDE : I8_X_PSTRIDE;
         const int nks = (k_hi - k_lo) / 32;
         for (int ks = 0; ks < nks; ++ks) {
+          // blocks of at most 64 columns take two k-steps per unit where a pair exists (their MMAs are short: the fixed
+          // cost of a unit - barrier check, commit, loop - is what paces them)
+          const int nk = (nb <= 64 && !(ks & 1) && ks + 1 < nks) ? 2 : 1;
           I8Unit u;
           memset(&u, 0, sizeof(u));
           u.w_off = (uint32_t)img.size();
@@ -643,16 +665,19 @@ int c1d_i8_prepare(c1d_ctx* ctx) {
           u.idesc = (2u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)nb >> 3) << 17) | ((128u >> 4) << 24);  // make_idesc_s8(nb)
           u.dcol = (uint16_t)(B.dcol + g * B.gstride);
           u.lstride = (uint8_t)B.lstride;
-          u.flags = (uint8_t)((ks == 0 ? 1 : 0) | ((g == gin[l] - 1 && ks == nks - 1) ? 2 : 0) | ((g == 0 && ks == 0) ? 4 : 0));
+          u.flags = (uint8_t)((ks == 0 ? 1 : 0) | ((g == gin[l] - 1 && ks + nk == nks) ? 2 : 0) | ((g == 0 && ks == 0) ? 4 : 0) | (nk == 2 ? 8 : 0));
           units.push_back(u);
-          const size_t o = img.size();
-          img.resize(o + (size_t)nb * 128, 0);
-          for (int pl = 0; pl < 4; ++pl)
-            for (int n = 0; n < nb; ++n)
-              for (int kk = 0; kk < 32; ++kk) {
-                const uint32_t v = qd[(size_t)(n0 + n) * kpad[l] + (k_lo + 32 * ks + kk)];
-                img[o + (size_t)pl * nb * 32 + sw32_off((uint32_t)n, (uint32_t)kk >> 4) + (kk & 15)] = (uint8_t)(v >> (8 * (3 - pl)));
-              }
+          for (int sk = 0; sk < nk; ++sk) {
+            const size_t o = img.size();
+            img.resize(o + (size_t)nb * 128, 0);
+            for (int pl = 0; pl < 4; ++pl)
+              for (int n = 0; n < nb; ++n)
+                for (int kk = 0; kk < 32; ++kk) {
+                  const uint32_t v = qd[(size_t)(n0 + n) * kpad[l] + (k_lo + 32 * (ks + sk) + kk)];
+                  img[o + (size_t)pl * nb * 32 + sw32_off((uint32_t)n, (uint32_t)kk >> 4) + (kk & 15)] = (uint8_t)(v >> (8 * (3 - pl)));
+                }
+          }
+          ks += nk - 1;
         }
       }
       n0 += nb;
@@ -728,6 +753,13 @@ int c1d_i8_launch(c1d_ctx* ctx, const double* emu_in, int64_t nrows, double* out
       for (int u = 0; u < st->p.n_units; ++u)
         fprintf(stderr, "  unit %2d nb %3d flags %d: issued %6lld cycles after the previous unit\n", u, (int)(((st->p.units[u].idesc >> 17) & 63u) << 3),
                 (int)st->p.units[u].flags, u ? q[u] - q[u - 1] : 0LL);
+    }
+    if (st->p.exp & 4) {
+      const long long* q = h + 8 * I8_MAX_BLOCKS + 96;
+      for (int u = 0; u < st->p.n_units && u < 64; ++u)
+        fprintf(stderr, "  unit %2d nb %3d: top->waited %5lld  MMAs issued %5lld  commits %5lld | top since previous top %6lld\n", u,
+                (int)(((st->p.units[u].idesc >> 17) & 63u) << 3), q[4 * u + 1] - q[4 * u], q[4 * u + 2] - q[4 * u + 1], q[4 * u + 3] - q[4 * u + 2],
+                u ? q[4 * u] - q[4 * u - 4] : 0LL);
     }
     fprintf(stderr, "i8 tile: MMA (go->dfull) %lld  pass1 %lld  quant %lld  whole tile %lld cycles\n", t_mma, t_p1, t_q,
             h[8 * (st->p.n_blocks - 1) + 3] - h[4]);

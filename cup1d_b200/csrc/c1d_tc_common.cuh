@@ -54,6 +54,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
          (int)threadIdx.x, bar, parity);
   __trap();
 }
+// the same with a non-blocking test first: a phase that is already complete (the usual case for the weight ring of
+// the MMA issuers) costs one check instead of the blocking form's suspend / resume path (~180 cycles measured)
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  if (!done) mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
