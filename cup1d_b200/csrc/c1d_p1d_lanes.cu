@@ -319,7 +319,11 @@ k_fused_p1d_lanes(DevCtx c, const int* __restrict__ seg, int nseg, const int* __
 #define WS_PREG_ 64
 #define WS_CREG_ 96
 #endif
+// 12 pairs: `setmaxnreg` acts on warpgroups (four consecutive warps), so the producer warps [0, WS_PAIRS) must fill
+// whole warpgroups - 13 or 14 pairs put both roles into one warpgroup and hang - and 16 pairs would need 18 of the 16
+// named barriers (and leave 64 registers per thread at launch)
 constexpr int WS_PAIRS = 12, WS_THREADS = 64 * WS_PAIRS;
+static_assert(WS_PAIRS % 4 == 0 && WS_PAIRS + 2 <= 16, "producer warps in whole warpgroups; one named barrier per pair");
 constexpr int WS_CH = WS_CH_, WS_NBUF = 2;  // points per chunk, chunks in the ring (double buffer)
 constexpr int WS_UNROLL = WS_UNROLL_;
 constexpr int WS_WAVES = 3;
