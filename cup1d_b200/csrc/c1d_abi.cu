@@ -424,6 +424,9 @@ static int run_chain(c1d_ctx* ctx, const double* x, int64_t n, double* lnp, doub
 // allocation and function attribute of that configuration exists before the capture.  Anything that changes what the
 // kernel parameters point to (workspace growth, uploads, re-finalisation) drops the cache.  C1D_GRAPH=0 disables it.
 void c1d_graphs_clear(c1d_ctx* ctx) {
+  bool any = false;
+  for (int i = 0; i < C1D_NGRAPH; ++i) any = any || ctx->graphs[i].exec;
+  if (any) cudaDeviceSynchronize();  // no replay in flight when its executable graph goes
   for (int i = 0; i < C1D_NGRAPH; ++i) {
     if (ctx->graphs[i].exec) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graphs[i].exec);
     memset(&ctx->graphs[i], 0, sizeof(ctx->graphs[i]));
