@@ -443,7 +443,7 @@ static bool graph_key_eq(const c1d_graph_entry& a, const c1d_graph_entry& b) {
 // captured under one setting must not serve a call made under another (the tests flip them between calls)
 static uint64_t graph_env_hash() {
   static const char* names[] = {"C1D_P1D_LAYOUT", "C1D_P1D_PARTS", "C1D_GP_KERNEL", "C1D_CHI2_GROUP", "C1D_CHI2_STAGES",
-                                "C1D_MLP64_G", "C1D_TC_CLUSTER"};
+                                "C1D_MLP64_G", "C1D_TC_CLUSTER", "C1D_CHI2_SPLIT"};
   uint64_t h = 1469598103934665603ull;  // FNV-1a
   for (const char* n : names) {
     const char* v = getenv(n);

@@ -66,6 +66,9 @@ struct CQParams {
   int tile_r0[CQ_MAX_TILES];      // first row of the tile
   int tile_rows[CQ_MAX_TILES];    // rows of the tile (<= 128)
   int tile_units[CQ_MAX_TILES];   // k units of the tile (k < end of the tile)
+  int tile_u0[CQ_MAX_TILES];      // first unit of the tile in the image
+  uint32_t part_mask[2];          // nsplit = 2: the row tiles of each half of a group's work (balanced by units)
+  int part_rs[2];                 // ... and the tile after whose epilogue the next item's scales are found
   uint32_t off_ring, off_sd, off_bar;  // shared-memory offsets (the residual operand starts at 0)
   long long* dbg;  // C1D_CHI2_DEBUG=1: clocks of CTA 0's second group (phases of warp 0 and of the MMA warp)
 };
@@ -83,7 +86,7 @@ __device__ __forceinline__ double cq_i2d(uint32_t x) {  // exact int32 -> float6
 }
 
 __global__ void __launch_bounds__(CQ_THREADS, 1)
-k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __restrict__ chi2p, int ntj) {
+k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __restrict__ chi2p, int ntj, int nsplit) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   const uint32_t ring = base + p.off_ring;
@@ -118,8 +121,14 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_p, 0);
 
-  const int64_t ngroups = (W + CQ_NW - 1) / CQ_NW;
-  const int64_t groups_per_cta = (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x;  // this CTA's groups: blockIdx.x, + gridDim.x, ..
+  // Work items: a 48-walker group, or (nsplit = 2: small and medium batches, where whole groups leave SMs idle or
+  // fill a last round badly) one of the two halves of its row tiles; both halves quantise the group and write their
+  // partial sum to their own slot of the walker's chi2p row.  Items blockIdx.x, + gridDim.x, ..
+  const int64_t nitems = ((W + CQ_NW - 1) / CQ_NW) * nsplit;
+  const int64_t groups_per_cta = (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  auto item_w0 = [&](int64_t it) { return ((it * gridDim.x + blockIdx.x) / nsplit) * CQ_NW; };
+  auto item_part = [&](int64_t it) { return (int)((it * gridDim.x + blockIdx.x) % nsplit); };
+  const uint32_t all_tiles = (1u << p.ntile) - 1u;
   const int ldd = p.ldd;
 
   if (warp < CQ_EPI_WARPS) {
@@ -164,10 +173,12 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
       asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(src));
       asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[4]), "=d"(x[5]), "=d"(x[6]), "=d"(x[7]) : "l"(src + 4));
     };
-    const int tpre = p.ntile > 3 ? p.ntile - 3 : 0;  // the next group's scales are found under the long tiles of this one
 
     for (int64_t it = 0; it < groups_per_cta; ++it) {
-      const int64_t w0 = (it * gridDim.x + blockIdx.x) * CQ_NW;
+      const int64_t w0 = item_w0(it);
+      const int part = item_part(it);
+      const uint32_t tmask = nsplit == 2 ? p.part_mask[part] : all_tiles;
+      const int tpre = nsplit == 2 ? p.part_rs[part] : (p.ntile > 3 ? p.ntile - 3 : 0);  // the next item's scales are found under the long tiles of this one
       const int sel = (int)(it & 1);
       const double* sdc = sd_s + sel * CQ_NW;
       const bool dbg = p.dbg && blockIdx.x == 0 && tid == 0 && it == 1;
@@ -234,7 +245,8 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
       double acc[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) acc[c] = 0.0;
-      for (int t = 0; t < p.ntile; ++t, ++tcount) {
+      for (int t = 0; t < p.ntile; ++t) {
+        if (!((tmask >> t) & 1u)) continue;
         const uint32_t buf = tcount & 1u;
         const int r = (int)(quad * 32u) + lane;             // row of the tile this lane holds
         const bool rvalid = r < p.tile_rows[t] && p.tile_r0[t] + r < p.nd;
@@ -282,8 +294,9 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
         mbar_arrive(bar_dfree + 8 * buf);
         if (dbg) p.dbg[10 + 4 * t] = clock64();
         // the next group's scales under this group's long tiles (the loads also bring its residuals into L2)
-        if (t == tpre && it + 1 < groups_per_cta) row_scales(((it + 1) * gridDim.x + blockIdx.x) * CQ_NW, sel ^ 1);
+        if (t == tpre && it + 1 < groups_per_cta) row_scales(item_w0(it + 1), sel ^ 1);
         if (dbg) p.dbg[11 + 4 * t] = clock64();
+        ++tcount;
       }
       // ---- sum over the lanes (rows) in a fixed order, then over the four quadrants ----
 #pragma unroll
@@ -300,9 +313,10 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
       cq_epi_bar();
       if (tid < CQ_NW && w0 + tid < W) {
         const double v = ((red_s[tid] + red_s[CQ_NW + tid]) + (red_s[2 * CQ_NW + tid] + red_s[3 * CQ_NW + tid])) * sdc[tid];
-        double* o = chi2p + (w0 + tid) * ntj;
-        o[0] = v;  // k_finalize adds the ntj partial sums of the walker: the rest are zero
-        for (int q = 1; q < ntj; ++q) o[q] = 0.0;
+        double* o = chi2p + (w0 + tid) * ntj;  // k_finalize adds the ntj partial sums of the walker
+        o[part] = v;
+        if (part == 0)
+          for (int q = nsplit; q < ntj; ++q) o[q] = 0.0;
       }
       if (dbg) p.dbg[2] = clock64();
       cq_epi_bar();  // red_s lies in the operand region the next group's digits overwrite; the scale buffers alternate
@@ -315,7 +329,9 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
     uint32_t g = 0, tcount = 0;
     for (int64_t it = 0; it < groups_per_cta; ++it) {
       const bool dbg = p.dbg && blockIdx.x == 0 && leader && it == 1;
-      for (int t = 0; t < p.ntile; ++t, ++tcount) {
+      const uint32_t tmask = nsplit == 2 ? p.part_mask[item_part(it)] : all_tiles;
+      for (int t = 0; t < p.ntile; ++t) {
+        if (!((tmask >> t) & 1u)) continue;
         const uint32_t buf = tcount & 1u;
         if (dbg) p.dbg[48 + 4 * t] = clock64();
         mbar_wait(bar_tready + 8 * t, (uint32_t)it & 1u);  // the k units of this tile are in shared memory
@@ -347,23 +363,26 @@ k_chi2_i8(CQParams p, const double* __restrict__ dvec, int64_t W, double* __rest
           __syncwarp();
         }
         if (dbg) p.dbg[51 + 4 * t] = clock64();
+        ++tcount;
       }
     }
   } else {
     // ============================== streamer of C^-1 ==============================
     const bool leader = lane == 0;
     uint32_t g = 0;
-    int total_units = 0;
-    for (int t = 0; t < p.ntile; ++t) total_units += p.tile_units[t];
     for (int64_t it = 0; it < groups_per_cta; ++it) {
-      for (int u = 0; u < total_units; ++u, ++g) {
-        const uint32_t slot = g % CQ_NSLOT;
-        if (g >= (uint32_t)CQ_NSLOT) mbar_wait(bar_bempty + 8 * slot, ((g / CQ_NSLOT) - 1u) & 1u);
-        if (leader) {
-          mbar_expect_tx(bar_bfull + 8 * slot, CQ_AUNIT);
-          bulk_g2s(ring + slot * CQ_AUNIT, p.img + (size_t)u * CQ_AUNIT, CQ_AUNIT, bar_bfull + 8 * slot);
+      const uint32_t tmask = nsplit == 2 ? p.part_mask[item_part(it)] : all_tiles;
+      for (int t = 0; t < p.ntile; ++t) {
+        if (!((tmask >> t) & 1u)) continue;
+        for (int u = p.tile_u0[t]; u < p.tile_u0[t] + p.tile_units[t]; ++u, ++g) {
+          const uint32_t slot = g % CQ_NSLOT;
+          if (g >= (uint32_t)CQ_NSLOT) mbar_wait(bar_bempty + 8 * slot, ((g / CQ_NSLOT) - 1u) & 1u);
+          if (leader) {
+            mbar_expect_tx(bar_bfull + 8 * slot, CQ_AUNIT);
+            bulk_g2s(ring + slot * CQ_AUNIT, p.img + (size_t)u * CQ_AUNIT, CQ_AUNIT, bar_bfull + 8 * slot);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   }
@@ -406,7 +425,25 @@ int c1d_chi2i8_prepare(c1d_ctx* ctx) {
     p.tile_r0[t] = t ? h0 + 128 * (t - 1) : 0;
     p.tile_rows[t] = t ? 128 : h0;
     p.tile_units[t] = (p.tile_r0[t] + p.tile_rows[t]) / 32;
+    p.tile_u0[t] = total_units;
     total_units += p.tile_units[t];
+  }
+  {
+    // two halves of a group's row tiles with equal units: the largest tile first, each to the lighter half
+    int load[2] = {0, 0};
+    p.part_mask[0] = p.part_mask[1] = 0;
+    for (int t = ntile - 1; t >= 0; --t) {
+      const int h = load[1] < load[0] ? 1 : 0;
+      p.part_mask[h] |= 1u << t;
+      load[h] += p.tile_units[t];
+    }
+    for (int h = 0; h < 2; ++h) {
+      // the next item's scales after the second-last tile of the half (the last one's MMAs run meanwhile)
+      int last = -1, prev = -1;
+      for (int t = 0; t < ntile; ++t)
+        if ((p.part_mask[h] >> t) & 1u) { prev = last; last = t; }
+      p.part_rs[h] = prev >= 0 ? prev : last;
+    }
   }
   std::vector<double> A((size_t)nd * nd);
   C1D_CUDA(ctx, cudaMemcpy(A.data(), ctx->dev[C1D_F_ICOV_FULL], A.size() * sizeof(double), cudaMemcpyDeviceToHost));
@@ -474,11 +511,18 @@ int c1d_chi2i8_launch(c1d_ctx* ctx, int64_t W, int ntj, cudaStream_t s) {
     return C1D_ERR_STATE;
   }
   const int64_t ngroups = (W + CQ_NW - 1) / CQ_NW;
-  const int grid = (int)(ngroups < ctx->num_sms ? ngroups : ctx->num_sms);
-  k_chi2_i8<<<grid, CQ_THREADS, st->smem, s>>>(st->p, ctx->ws.dvec, W, ctx->ws.chi2p, ntj);
+  // halves of groups where whole groups would leave SMs idle (at most half a round) or fill a second round badly
+  // (up to one and a half rounds); a half costs more than half a group (it quantises the whole group), so larger
+  // batches keep whole groups
+  const int64_t sms = ctx->num_sms;
+  int nsplit = (st->p.ntile >= 2 && ntj >= 2 && (2 * ngroups <= sms || (ngroups > sms && 2 * ngroups <= 3 * sms))) ? 2 : 1;
+  if (const char* e = getenv("C1D_CHI2_SPLIT")) nsplit = (atoi(e) == 2 && st->p.ntile >= 2 && ntj >= 2) ? 2 : 1;
+  const int64_t nitems = ngroups * nsplit;
+  const int grid = (int)(nitems < sms ? nitems : sms);
+  k_chi2_i8<<<grid, CQ_THREADS, st->smem, s>>>(st->p, ctx->ws.dvec, W, ctx->ws.chi2p, ntj, nsplit);
   ctx->launches++;
   C1D_CUDA(ctx, cudaPeekAtLastError());
-  if (st->p.dbg && ngroups > 2 * grid) {
+  if (st->p.dbg && nitems > 2 * grid) {
     // diagnostic: the second group of CTA 0, cycles relative to its start; synchronises
     long long h[96];
     C1D_CUDA(ctx, cudaStreamSynchronize(s));
