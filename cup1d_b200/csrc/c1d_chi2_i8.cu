@@ -511,11 +511,13 @@ int c1d_chi2i8_launch(c1d_ctx* ctx, int64_t W, int ntj, cudaStream_t s) {
     return C1D_ERR_STATE;
   }
   const int64_t ngroups = (W + CQ_NW - 1) / CQ_NW;
-  // halves of groups where whole groups would leave SMs idle (at most half a round) or fill a second round badly
-  // (up to one and a half rounds); a half costs more than half a group (it quantises the whole group), so larger
-  // batches keep whole groups
+  // halves of groups where whole groups would leave at least half of the SMs idle (small batches: the kernel's latency
+  // drops by the share of the MMAs); a half costs more than half a group (it quantises the whole group), so larger
+  // batches keep whole groups.  (Halves between one and one and a half rounds of groups gained 2 % at 8192 walkers and
+  // are not used: the partial sums of a walker add in another order, and a shard of a large ensemble - 8192 walkers
+  // per GPU of 65 536 - would no longer equal the unsharded evaluation bit for bit.)
   const int64_t sms = ctx->num_sms;
-  int nsplit = (st->p.ntile >= 2 && ntj >= 2 && (2 * ngroups <= sms || (ngroups > sms && 2 * ngroups <= 3 * sms))) ? 2 : 1;
+  int nsplit = (st->p.ntile >= 2 && ntj >= 2 && 2 * ngroups <= sms) ? 2 : 1;
   if (const char* e = getenv("C1D_CHI2_SPLIT")) nsplit = (atoi(e) == 2 && st->p.ntile >= 2 && ntj >= 2) ? 2 : 1;
   const int64_t nitems = ngroups * nsplit;
   const int grid = (int)(nitems < sms ? nitems : sms);
