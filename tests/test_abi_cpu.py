@@ -42,3 +42,14 @@ def test_config_struct_matches_header():
         for part in m.group(2).split(","):
             names.append(re.sub(r"\[.*", "", part.strip()))
     assert names == [f[0] for f in _abi.Config._fields_]
+
+
+def test_flags_and_version_match_header():
+    """evaluation flags and the ABI version of the ctypes mirror == the header's #defines"""
+    txt = open(os.path.join(ROOT, "include", "cup1d_b200.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(C1D_[A-Z0-9_]+)\s+(\d+)u?\b", txt)}
+    assert defs["C1D_ABI_VERSION"] == _abi.ABI_VERSION
+    for name in ("ZMASK", "NO_HULL", "NO_CUBE", "EMU_TC", "EMU_I8", "CHI2_I8"):
+        assert defs["C1D_FLAG_" + name] == getattr(_abi, "FLAG_" + name), name
+    flags = [v for k, v in defs.items() if k.startswith("C1D_FLAG_")]
+    assert len(set(flags)) == len(flags) and all(v & (v - 1) == 0 for v in flags)  # distinct single bits
